@@ -1,0 +1,132 @@
+/* addvisor_b200.h - C ABI of libaddvisor_sm100.so
+ *
+ * B200 (sm_100a) kernels for the ADDvisor explanation-evaluation hot path.  The reference
+ * (davidcombei/xAI-Audio-Deepfakes) is pure Python and has no FFI of its own; the boundary
+ * a maintainer binds is its Python call surface.  Each entry point below names the
+ * reference call it replaces (paths relative to the reference checkout).  The ctypes
+ * binding that ships with this repo is xai-audio-deepfakes_b200/_lib.py; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer marked "dev" is a device pointer on the current CUDA device; "host" is host memory
+ *   - `stream` is a cudaStream_t passed as void*; all compute entry points are asynchronous on it
+ *   - return value: 0 (ADV_OK) or a negative adv_status; nothing throws; adv_strerror() names codes
+ *   - nothing is allocated behind the caller's back except plan-owned tables
+ *   - spectra are "frame-major": element (b, t, f) of a [B, T, F] complex64 array, i.e. the memory
+ *     layout torch.stft itself produces (its [B,F,T] result has strides (F*T, 1, F))
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns ADV_ERR_CUDA
+ */
+#ifndef ADDVISOR_B200_H
+#define ADDVISOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum adv_status {
+    ADV_OK = 0,
+    ADV_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, ...) */
+    ADV_ERR_UNSUPPORTED = -2, /* geometry outside what the kernels implement (n_fft not 512/1024, ...) */
+    ADV_ERR_NOLA = -3,        /* window overlap-add envelope vanishes: torch.istft "window overlap add min: 1" */
+    ADV_ERR_SHORT_INPUT = -4, /* reflect padding needs n_in > n_fft/2 (torch.stft raises too) */
+    ADV_ERR_CUDA = -5,        /* CUDA runtime error; see adv_last_cuda_error() */
+    ADV_ERR_SHAPE = -6        /* mask / spectrum shape inconsistent with the plan */
+} adv_status;
+
+typedef enum adv_mask_mode {
+    ADV_MASK_LOG1P = 0, /* LMAC_metrics.py:136-143,151-153: expm1(m * log1p(|X|)) * exp(i*phase) */
+    ADV_MASK_LINEAR = 1 /* loss_function.py:36-45:          (m * |X|) * exp(i*phase)            */
+} adv_mask_mode;
+
+typedef struct adv_plan adv_plan;
+typedef struct adv_c64 { float re, im; } adv_c64;
+
+int adv_version(void);
+const char* adv_strerror(int status);
+const char* adv_last_cuda_error(void);
+
+/* ---- plan = AudioProcessor.__init__ geometry (audioprocessor.py:22-44) bound to one clip length --------
+ * window_host: win_length taps or NULL for torch's default rectangular window (audioprocessor.py:102-108
+ * passes no window).  The window is centred in n_fft like torch.stft does.  n_frames = 1 + n_in / hop for
+ * the stft direction; n_out is torch.istft's `length` (audioprocessor.py:121-129) or hop*(n_frames-1)
+ * for the length=None call sites (hifigan.py:223-225).  Fails with ADV_ERR_NOLA exactly when torch.istft
+ * would raise on the envelope check. */
+int adv_plan_create(adv_plan** out, int n_fft, int hop, int win_length, const float* window_host,
+                    int n_frames, int n_in, int n_out);
+void adv_plan_destroy(adv_plan* plan);
+int adv_plan_bins(const adv_plan* plan);
+int adv_plan_frames(const adv_plan* plan);
+/* number of output tiles per clip the istft / explain kernels use for batch size B
+ * (= second dimension of the `stats` array below) */
+int adv_plan_tiles(const adv_plan* plan, int batch);
+
+/* ---- AudioProcessor.compute_stft (audioprocessor.py:82-112): torch.stft + .abs() + .angle() -----------
+ * wav: dev float [B][wav_stride], first n_in samples of each row are used (caller pads/crops, :83-98).
+ * X: dev complex64 [B][T][F] frame-major; mag / phase: dev float [B][T][F] or NULL to skip. */
+int adv_stft(const adv_plan* plan, const float* wav, int64_t wav_stride, int batch,
+             adv_c64* X, float* mag, float* phase, void* stream);
+
+/* ---- AudioProcessor.compute_invert_stft (audioprocessor.py:117-131): torch.istft ----------------------
+ * X: dev complex64, element (b,t,f) at X[b*sb + t*st + f*sf] (element strides); out: dev float [B][n_out].
+ * stats (nullable): dev double [B][tiles][2] per-tile (sum, sum of squares) of the output, for the
+ * normaliser that follows in extract_features (classifier_embedder.py:59-63). */
+int adv_istft(const adv_plan* plan, const adv_c64* X, int64_t sb, int64_t st, int64_t sf, int batch,
+              float* out, double* stats, void* stream);
+
+/* ---- fused explanation resynthesis: the LMAC_metrics.py:125-158 loop body without the classifier ------
+ * wave + mask -> STFT -> mask / (1-mask) applied to the (log-)magnitude with the original phase ->
+ * two iSTFTs.  Spectra never leave the SM.  mask: dev float [B][Fm][Tm] contiguous, Fm <= F, Tm <= T,
+ * cells outside the mask count as mask = 0.  rel / irr: dev float [B][n_out].
+ * stats (nullable): dev double [B][tiles][4] = per-tile (sum rel, sumsq rel, sum irr, sumsq irr). */
+int adv_explain(const adv_plan* plan, const float* wav, int64_t wav_stride, const float* mask, int Fm, int Tm,
+                int mode, int batch, float* rel, float* irr, double* stats, void* stream);
+/* same, starting from an existing spectrum (collate_fn already ran compute_stft, LMAC_metrics.py:109-114) */
+int adv_explain_spec(const adv_plan* plan, const adv_c64* X, int64_t sb, int64_t st, int64_t sf,
+                     const float* mask, int Fm, int Tm, int mode, int batch,
+                     float* rel, float* irr, double* stats, void* stream);
+
+/* ---- standalone mask-apply on (magnitude, phase) as the reference writes it ---------------------------
+ * mag / phase: dev float [B][T][F] frame-major; mask as above; rel / irr: dev complex64 [B][T][F]. */
+int adv_mask_apply(const float* mag, const float* phase, const float* mask, int batch, int T, int F,
+                   int Fm, int Tm, int mode, adv_c64* rel, adv_c64* irr, void* stream);
+
+/* ---- zero_mean_unit_var_norm (classifier_embedder.py:59-63): (x - mean) / (std_unbiased + 1e-7) -------
+ * adv_row_stats: per-row partial (sum, sumsq) -> stats dev double [B][parts][2], parts = adv_row_stats_parts(n).
+ * adv_normalize: in/out dev float [B][n] (may alias); stats dev double [B][parts][width], the (sum, sumsq)
+ * pair at column `col`.  Two launches, no host sync. */
+int adv_row_stats_parts(int n);
+int adv_row_stats(const float* in, int batch, int n, double* stats, void* stream);
+int adv_normalize(const float* in, float* out, int batch, int n, const double* stats, int parts, int width,
+                  int col, void* stream);
+
+/* ---- LMAC metrics (LMAC_metrics.py:31-73,160-172; sigmoid of classifier_embedder.py:36) ---------------
+ * p / theta / q: dev float [n] classifier outputs for the clean, masked-in and masked-out clips;
+ * is_logit != 0 applies the logistic sigmoid first.  scores (nullable): dev float [n][7] =
+ * (faithfulness, fidelity, AD, AI, AG, pc, oc) per sample, pc / oc = get_score_for_predicted_class of p / theta.  sums: dev double [6] = the five sums and the count
+ * (the vector the multi-GPU driver all-reduces).  block_partials: dev double scratch
+ * [adv_lmac_blocks(n)][5]. */
+int adv_lmac_blocks(int n);
+int adv_lmac_reduce(const float* p, const float* theta, const float* q, int n, int is_logit,
+                    float* scores, double* sums, double* block_partials, unsigned int* counter, void* stream);
+
+/* ---- gradient-saliency time-domain mask (captum_saliency.py:136-143) ----------------------------------
+ * m = |attr| / (max_row |attr| + 1e-8); rel = wave*m; irr = wave*(1-m).  rowmax: dev float [B] scratch. */
+int adv_td_mask(const float* wave, const float* attr, int batch, int n, float* mask_out, float* rel, float* irr,
+                float* rowmax, void* stream);
+
+/* ---- ADDvisor mask head (addvisor.py:57-60,82): sigmoid(conv1x1(32 -> 1)) -----------------------------
+ * y1: dev float [B][C][HW] contiguous, w: dev float [C], bias: dev float [1]; mask: dev float [B][HW]. */
+int adv_mask_head(const float* y1, const float* w, const float* bias, int batch, int channels, int64_t hw,
+                  float* mask, void* stream);
+
+/* ---- band swap (train_logReg_swapping.py:64-75, hifigan.py:206-214): rows [f_lo, f_hi) of `voc` replace
+ * those of `real`; all three frame-major [B][T][F] complex64. */
+int adv_band_swap(const adv_c64* real, const adv_c64* voc, int batch, int T, int F, int f_lo, int f_hi,
+                  adv_c64* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADDVISOR_B200_H */

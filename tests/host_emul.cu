@@ -1,0 +1,118 @@
+// CPU lane-by-lane emulation of the unit FFT data flow in csrc/fft_core.cuh.
+// Built and run by tests/test_host_emul.py (nvcc host compilation, no GPU needed).
+// Checks, for NF = 512 and 1024, against a float64 direct DFT:
+//   (1) forward FFT of two packed real frames + split  == rfft of each frame
+//   (2) merge + inverse FFT of two Hermitian spectra    == irfft of each (x NF)
+//   (3) bin_of() covers every one-sided bin exactly once
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <complex>
+#include "../xai-audio-deepfakes_b200/csrc/fft_core.cuh"
+
+using namespace adv;
+typedef std::complex<double> cd;
+
+template <int NF>
+int run() {
+    using G = Geo<NF>;
+    const int L = G::LANES;
+    std::vector<float> xa(NF), xb(NF);
+    srand(7 + NF);
+    for (int i = 0; i < NF; ++i) {
+        xa[i] = (float)rand() / RAND_MAX - 0.5f;
+        xb[i] = (float)rand() / RAND_MAX - 0.5f;
+    }
+    // float64 reference rfft
+    std::vector<cd> RA(NF / 2 + 1), RB(NF / 2 + 1);
+    for (int k = 0; k <= NF / 2; ++k) {
+        cd sa = 0, sb = 0;
+        for (int n = 0; n < NF; ++n) {
+            cd w = std::polar(1.0, -2.0 * M_PI * (double)((long)k * n % NF) / NF);
+            sa += (double)xa[n] * w;
+            sb += (double)xb[n] * w;
+        }
+        RA[k] = sa;
+        RB[k] = sb;
+    }
+    // per-lane twiddles
+    std::vector<std::vector<float2>> tw(L, std::vector<float2>(32));
+    for (int l = 0; l < L; ++l)
+        for (int k1 = 0; k1 < 32; ++k1) {
+            double a = -2.0 * M_PI * (double)(l * k1) / NF;
+            tw[l][k1] = make_float2((float)cos(a), (float)sin(a));
+        }
+    std::vector<std::vector<float2>> V(L, std::vector<float2>(32));
+    std::vector<float2> scratch(G::SCRATCH);
+    for (int l = 0; l < L; ++l)
+        for (int n1 = 0; n1 < 32; ++n1) V[l][n1] = make_float2(xa[n1 * G::R2 + l], xb[n1 * G::R2 + l]);
+    for (int l = 0; l < L; ++l) {
+        const float2* t = tw[l].data();
+        fwd_phase_a<NF>(V[l].data(), l, [t](int k) { return t[k]; }, scratch.data());
+    }
+    for (int l = 0; l < L; ++l) fwd_phase_b<NF>(V[l].data(), l, scratch.data());
+
+    // split
+    std::vector<std::vector<float2>> XA(L, std::vector<float2>(17)), XB(L, std::vector<float2>(17));
+    if constexpr (NF == 512) {
+        for (int l = 0; l < L; ++l) split512(V[l].data(), l, XA[l].data(), XB[l].data());
+    } else {
+        std::vector<std::vector<float2>> send(L, std::vector<float2>(16));
+        for (int l = 0; l < L; ++l) split1024_pre(V[l].data(), send[l].data());
+        for (int l = 0; l < L; ++l)
+            split1024_post(V[l].data(), l, send[(32 - l) & 31].data(), XA[l].data(), XB[l].data());
+    }
+    double err = 0, mx = 0;
+    std::vector<int> seen(NF / 2 + 1, 0);
+    for (int l = 0; l < L; ++l)
+        for (int i = 0; i < 17; ++i) {
+            int b = bin_of<NF>(l, i);
+            if (b < 0) continue;
+            if (b > NF / 2) { printf("bin out of range %d\n", b); return 1; }
+            seen[b]++;
+            err = fmax(err, std::abs(cd(XA[l][i].x, XA[l][i].y) - RA[b]));
+            err = fmax(err, std::abs(cd(XB[l][i].x, XB[l][i].y) - RB[b]));
+            mx = fmax(mx, std::abs(RA[b]));
+        }
+    for (int k = 0; k <= NF / 2; ++k)
+        if (seen[k] != 1) { printf("NF=%d bin %d seen %d times\n", NF, k, seen[k]); return 1; }
+    printf("NF=%d forward+split max err %.3e (max |X| %.3f)\n", NF, err, mx);
+    if (err > 2e-5 * mx) return 1;
+
+    // merge + inverse: feed back XA, XB (with garbage in Im of DC/Nyquist to test C2R semantics)
+    for (int l = 0; l < L; ++l)
+        for (int i = 0; i < 17; ++i) {
+            int b = bin_of<NF>(l, i);
+            if (b == 0 || b == NF / 2) { XA[l][i].y = 123.0f; XB[l][i].y = -77.0f; }
+            if (b < 0) { XA[l][i] = make_float2(0, 0); XB[l][i] = make_float2(0, 0); }
+        }
+    if constexpr (NF == 512) {
+        for (int l = 0; l < L; ++l) merge512(V[l].data(), l, XA[l].data(), XB[l].data());
+    } else {
+        std::vector<std::vector<float2>> send(L, std::vector<float2>(16));
+        for (int l = 0; l < L; ++l) merge1024_pre(V[l].data(), l, XA[l].data(), XB[l].data(), send[l].data());
+        for (int l = 0; l < L; ++l) merge1024_post(V[l].data(), l, send[(32 - l) & 31].data());
+    }
+    for (int l = 0; l < L; ++l) inv_phase_a<NF>(V[l].data(), l, scratch.data());
+    for (int l = 0; l < L; ++l) {
+        const float2* t = tw[l].data();
+        inv_phase_b<NF>(V[l].data(), l, [t](int k) { return t[k]; }, scratch.data());
+    }
+    double ierr = 0;
+    for (int l = 0; l < L; ++l)
+        for (int n1 = 0; n1 < 32; ++n1) {
+            int n = n1 * G::R2 + l;
+            ierr = fmax(ierr, fabs(V[l][n1].x / NF - xa[n]));
+            ierr = fmax(ierr, fabs(V[l][n1].y / NF - xb[n]));
+        }
+    printf("NF=%d merge+inverse round-trip max err %.3e\n", NF, ierr);
+    return ierr > 2e-6 ? 1 : 0;
+}
+
+int main() {
+    int rc = run<512>();
+    rc |= run<1024>();
+    printf(rc ? "FAIL\n" : "OK\n");
+    return rc;
+}

@@ -1,0 +1,192 @@
+"""ctypes binding of libaddvisor_sm100.so (the C ABI declared in include/addvisor_b200.h).
+
+There is no CPU fallback anywhere in this package: if the shared library is missing, importing
+this module raises; if no CUDA device is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libaddvisor_sm100.so"
+LIB_PATH = os.path.join(_HERE, LIB_NAME)
+CSRC = os.path.join(_HERE, "csrc")
+SOURCES = ["capi.cu", "transform_kernels.cu", "pointwise_kernels.cu", "mel_kernels.cu", "vocoder_kernels.cu"]
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC"]
+
+ADV_OK, ADV_ERR_INVALID, ADV_ERR_UNSUPPORTED, ADV_ERR_NOLA = 0, -1, -2, -3
+ADV_ERR_SHORT_INPUT, ADV_ERR_CUDA, ADV_ERR_SHAPE = -4, -5, -6
+MASK_LOG1P, MASK_LINEAR = 0, 1
+
+
+def sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = sources()
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(_HERE, "..", "include", "addvisor_b200.h"))
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(d) for d in deps)
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+_SIGS = {
+    # name: (restype, argtypes)
+    "adv_version": (C.c_int, []),
+    "adv_strerror": (C.c_char_p, [C.c_int]),
+    "adv_last_cuda_error": (C.c_char_p, []),
+    "adv_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_int]),
+    "adv_plan_destroy": (None, [C.c_void_p]),
+    "adv_plan_bins": (C.c_int, [C.c_void_p]),
+    "adv_plan_frames": (C.c_int, [C.c_void_p]),
+    "adv_plan_tiles": (C.c_int, [C.c_void_p, C.c_int]),
+    "adv_stft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                           C.c_void_p]),
+    "adv_istft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p,
+                            C.c_void_p, C.c_void_p]),
+    "adv_explain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adv_explain_spec": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adv_mask_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adv_row_stats_parts": (C.c_int, [C.c_int]),
+    "adv_row_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "adv_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p]),
+    "adv_lmac_blocks": (C.c_int, [C.c_int]),
+    "adv_lmac_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adv_td_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p]),
+    "adv_mask_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p,
+                                C.c_void_p]),
+    "adv_band_swap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                C.c_void_p]),
+}
+# entry points of later translation units, bound when present in the header
+_OPTIONAL_SIGS = {
+    "adv_mel_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float,
+                                  C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+}
+
+
+def lib():
+    """The loaded library (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise ImportError(
+                        f"{LIB_NAME} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a). This package has no CPU fallback.")
+                handle = C.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGS.items():
+                    fn = getattr(handle, name)  # AttributeError = header / library out of sync
+                    fn.restype, fn.argtypes = res, args
+                for name, (res, args) in _OPTIONAL_SIGS.items():
+                    if hasattr(handle, name):
+                        fn = getattr(handle, name)
+                        fn.restype, fn.argtypes = res, args
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    """Map a C status to the exception the reference path would have raised."""
+    if rc == ADV_OK:
+        return
+    L = lib()
+    msg = L.adv_strerror(rc).decode()
+    if rc == ADV_ERR_NOLA:  # torch.istft's own text
+        raise RuntimeError("window overlap add min: 1")
+    if rc == ADV_ERR_CUDA:
+        raise RuntimeError(f"{what}: CUDA error: {L.adv_last_cuda_error().decode()}")
+    if rc == ADV_ERR_UNSUPPORTED:
+        raise NotImplementedError(f"{what}: {msg}")
+    if rc in (ADV_ERR_SHAPE, ADV_ERR_SHORT_INPUT):
+        raise RuntimeError(f"{what}: {msg}")
+    raise ValueError(f"{what}: {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("addvisor_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Plan:
+    """Owner of one adv_plan (geometry + device tables)."""
+
+    def __init__(self, n_fft, hop, win_length, window, n_frames, n_in, n_out):
+        import numpy as np
+        require_cuda()
+        self.handle = C.c_void_p()
+        wptr = C.c_void_p(0)
+        if window is not None:
+            self._w = np.ascontiguousarray(window, dtype=np.float32)
+            if self._w.shape[0] != win_length:
+                raise ValueError("window length must equal win_length")
+            wptr = C.c_void_p(self._w.ctypes.data)
+        check(lib().adv_plan_create(C.byref(self.handle), n_fft, hop, win_length, wptr, n_frames, n_in, n_out),
+              "adv_plan_create")
+        self.n_fft, self.hop, self.win_length = n_fft, hop, win_length
+        self.n_frames, self.n_in, self.n_out = n_frames, n_in, n_out
+        self.bins = n_fft // 2 + 1
+
+    def tiles(self, batch):
+        return lib().adv_plan_tiles(self.handle, batch)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().adv_plan_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+_plans = {}
+
+
+def get_plan(n_fft, hop, win_length, window, n_frames, n_in, n_out):
+    import torch
+    wkey = None
+    if window is not None:
+        window = window.detach().float().cpu().numpy() if hasattr(window, "detach") else window
+        wkey = window.tobytes()
+    key = (n_fft, hop, win_length, wkey, n_frames, n_in, n_out, torch.cuda.current_device())
+    p = _plans.get(key)
+    if p is None:
+        p = _plans[key] = Plan(n_fft, hop, win_length, window, n_frames, n_in, n_out)
+    return p

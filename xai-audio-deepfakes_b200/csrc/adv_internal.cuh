@@ -1,0 +1,57 @@
+// Internal definitions shared by the kernel translation units of libaddvisor_sm100.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/addvisor_b200.h"
+
+namespace adv {
+
+constexpr int kThreads = 256;  // CTA size of the transform kernels
+
+// Plan fields the kernels read (passed by value as a kernel argument).
+struct PlanDev {
+    int n_fft, hop, T, n_in, n_out;
+    int wlo, whi;          // window support [wlo, whi) inside n_fft (non-zero taps)
+    int phases;            // ceil(support / hop): frames t and t+phases never overlap
+    const float* window;   // dev [n_fft], window centred in n_fft
+    const float* inv_env;  // dev [n_out], 1 / (n_fft * sum_t w^2), 0 where no frame lands
+    const float2* tw;      // dev [32][lanes], exp(-2*pi*i*l*k1/n_fft)
+};
+
+// Tiling of the output (sample) axis for the overlap-add kernels.
+struct Tiling {
+    int hops_per_tile;  // output samples per tile = hops_per_tile * hop
+    int tiles;          // tiles per clip
+};
+
+}  // namespace adv
+
+struct adv_plan {
+    adv::PlanDev d;
+    int win_length;
+    int frames_per_tile;  // capacity of one CTA pass: 2 * units
+    int max_hops;         // largest hops_per_tile whose frame span fits frames_per_tile
+    int device;
+    void* dev_block;      // single allocation holding window / inv_env / tw
+};
+
+namespace adv {
+void set_cuda_error(cudaError_t e);
+Tiling choose_tiling(const adv_plan* p, int batch);
+int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
+                float* phase, cudaStream_t s);
+int launch_istft(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
+                 double* stats, cudaStream_t s);
+int launch_explain(const adv_plan* p, const float* wav, int64_t wav_stride, const float2* X, int64_t sb,
+                   int64_t st, int64_t sf, const float* mask, int Fm, int Tm, int mode, int batch, float* rel,
+                   float* irr, double* stats, cudaStream_t s);
+}  // namespace adv
+
+#define ADV_CUDA_CHECK(expr)                         \
+    do {                                             \
+        cudaError_t _e = (expr);                     \
+        if (_e != cudaSuccess) {                     \
+            adv::set_cuda_error(_e);                 \
+            return ADV_ERR_CUDA;                     \
+        }                                            \
+    } while (0)

@@ -1,0 +1,226 @@
+// C-ABI entry points: plan management, argument validation, launch dispatch.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "adv_internal.cuh"
+#include "fft_core.cuh"
+
+namespace adv {
+
+static thread_local char g_cuda_err[256] = "";
+void set_cuda_error(cudaError_t e) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    (void)cudaGetLastError();
+}
+
+static int floordiv_h(int a, int b) {
+    int q = a / b;
+    return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+static int ceildiv_h(int a, int b) { return floordiv_h(a + b - 1, b); }
+
+// frames a tile of `k` hops needs, maximum over all tiles (same formulas as tile_geom() on the device)
+static int tile_frame_span(const PlanDev& d, int k) {
+    const int S = k * d.hop, half = d.n_fft / 2;
+    int worst = 0;
+    for (int s0 = 0; s0 < d.n_out; s0 += S) {
+        const int s1 = s0 + S < d.n_out ? s0 + S : d.n_out;
+        const int p0 = s0 + half, p1 = s1 + half;
+        int t_lo = ceildiv_h(p0 - d.whi + 1, d.hop);
+        int t_hi = floordiv_h(p1 - 1 - d.wlo, d.hop);
+        if (t_lo < 0) t_lo = 0;
+        if (t_hi > d.T - 1) t_hi = d.T - 1;
+        const int span = t_hi - t_lo + 1;
+        if (span > worst) worst = span;
+    }
+    return worst;
+}
+
+Tiling choose_tiling(const adv_plan* p, int batch) {
+    // total hops to cover, smallest tile count that fits the CTA's frame capacity, then trade a few
+    // more (smaller) tiles against wave quantisation on 148 SMs
+    const PlanDev& d = p->d;
+    const int total_hops = (d.n_out + d.hop - 1) / d.hop;
+    const int n_min = (total_hops + p->max_hops - 1) / p->max_hops;
+    const int halo = p->frames_per_tile - p->max_hops;
+    Tiling best{p->max_hops, n_min};
+    double best_cost = 1e300;
+    for (int n = n_min; n <= n_min + 8 && n <= total_hops; ++n) {
+        const int k = (total_hops + n - 1) / n;
+        const int tiles = (total_hops + k - 1) / k;
+        const long ctas = (long)tiles * (batch > 0 ? batch : 1);
+        const double waves = ceil((double)ctas / 148.0);
+        const double cost = waves * (double)(k + halo);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = Tiling{k, tiles};
+        }
+    }
+    return best;
+}
+
+}  // namespace adv
+
+using namespace adv;
+
+extern "C" {
+
+int adv_version(void) { return 100; }
+
+const char* adv_strerror(int status) {
+    switch (status) {
+        case ADV_OK: return "ok";
+        case ADV_ERR_INVALID: return "invalid argument";
+        case ADV_ERR_UNSUPPORTED: return "unsupported geometry (n_fft must be 512 or 1024, hop <= n_fft)";
+        case ADV_ERR_NOLA: return "window overlap add min: 1";
+        case ADV_ERR_SHORT_INPUT: return "input shorter than the reflect padding (n_in must exceed n_fft/2)";
+        case ADV_ERR_CUDA: return "CUDA error";
+        case ADV_ERR_SHAPE: return "shape mismatch with the plan";
+        default: return "unknown status";
+    }
+}
+
+const char* adv_last_cuda_error(void) { return g_cuda_err; }
+
+int adv_plan_create(adv_plan** out, int n_fft, int hop, int win_length, const float* window_host, int n_frames,
+                    int n_in, int n_out) {
+    if (!out) return ADV_ERR_INVALID;
+    *out = nullptr;
+    if (n_fft <= 0 || hop <= 0 || win_length <= 0 || win_length > n_fft || n_frames <= 0 || n_out < 0)
+        return ADV_ERR_INVALID;
+    if (n_fft != 512 && n_fft != 1024) return ADV_ERR_UNSUPPORTED;
+    if (n_in > 0 && n_in <= n_fft / 2) return ADV_ERR_SHORT_INPUT;
+    if (n_in > 0 && 1 + n_in / hop != n_frames) return ADV_ERR_SHAPE;
+
+    // window centred in n_fft (torch.stft pads win_length < n_fft on both sides)
+    std::vector<float> win(n_fft, 0.0f);
+    const int left = (n_fft - win_length) / 2;
+    for (int i = 0; i < win_length; ++i) win[left + i] = window_host ? window_host[i] : 1.0f;
+    int wlo = 0, whi = n_fft;
+    while (wlo < n_fft && win[wlo] == 0.0f) ++wlo;
+    while (whi > wlo && win[whi - 1] == 0.0f) --whi;
+    if (whi <= wlo) return ADV_ERR_NOLA;
+    const int support = whi - wlo;
+    const int phases = (support + hop - 1) / hop;
+    if (phases > 64) return ADV_ERR_UNSUPPORTED;
+
+    // overlap-add envelope over the kept span [n_fft/2, n_fft/2 + n_out) and torch.istft's NOLA check
+    const long full_len = (long)n_fft + (long)hop * (n_frames - 1);
+    std::vector<double> env(full_len, 0.0);
+    for (int t = 0; t < n_frames; ++t)
+        for (int n = wlo; n < whi; ++n) env[(long)t * hop + n] += (double)win[n] * (double)win[n];
+    std::vector<float> inv_env(n_out, 0.0f);
+    for (int s = 0; s < n_out; ++s) {
+        const long p = (long)s + n_fft / 2;
+        if (p >= full_len) break;  // torch zero-pads the tail when `length` exceeds the signal
+        if (fabs(env[p]) < 1e-11) return ADV_ERR_NOLA;
+        inv_env[s] = (float)(1.0 / ((double)n_fft * env[p]));
+    }
+
+    const int lanes = n_fft / 32;
+    std::vector<float2> tw((size_t)32 * lanes);
+    for (int k1 = 0; k1 < 32; ++k1)
+        for (int l = 0; l < lanes; ++l) {
+            const double a = -2.0 * M_PI * (double)((k1 * l) % n_fft) / (double)n_fft;
+            tw[(size_t)k1 * lanes + l] = make_float2((float)cos(a), (float)sin(a));
+        }
+
+    adv_plan* p = (adv_plan*)calloc(1, sizeof(adv_plan));
+    if (!p) return ADV_ERR_INVALID;
+    const size_t b_win = sizeof(float) * n_fft, b_env = sizeof(float) * (size_t)n_out, b_tw = sizeof(float2) * tw.size();
+    const size_t o_env = (b_win + 255) / 256 * 256, o_tw = o_env + (b_env + 255) / 256 * 256;
+    cudaError_t e = cudaMalloc(&p->dev_block, o_tw + b_tw);
+    if (e == cudaSuccess) e = cudaMemcpy((char*)p->dev_block, win.data(), b_win, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((char*)p->dev_block + o_env, inv_env.data(), b_env, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((char*)p->dev_block + o_tw, tw.data(), b_tw, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_cuda_error(e);
+        if (p->dev_block) cudaFree(p->dev_block);
+        free(p);
+        return ADV_ERR_CUDA;
+    }
+    cudaGetDevice(&p->device);
+    p->d.n_fft = n_fft;
+    p->d.hop = hop;
+    p->d.T = n_frames;
+    p->d.n_in = n_in;
+    p->d.n_out = n_out;
+    p->d.wlo = wlo;
+    p->d.whi = whi;
+    p->d.phases = phases;
+    p->d.window = (const float*)p->dev_block;
+    p->d.inv_env = (const float*)((char*)p->dev_block + o_env);
+    p->d.tw = (const float2*)((char*)p->dev_block + o_tw);
+    p->win_length = win_length;
+    p->frames_per_tile = 2 * (kThreads / lanes);
+    p->max_hops = n_out == 0 ? 1 : 0;  // n_out == 0: forward-only plan, no overlap-add tiling
+    for (int k = p->frames_per_tile; k >= 1 && n_out > 0; --k)
+        if (tile_frame_span(p->d, k) <= p->frames_per_tile) {
+            p->max_hops = k;
+            break;
+        }
+    {   // the fused explain kernel is the largest shared-memory user: keep its tile inside 227 KB
+        // (mirrors ExplainSmem<NF>::bytes in transform_kernels.cu)
+        const int units = kThreads / lanes, ft = 2 * units, pitch = lanes + 1, bins = n_fft / 2 + 1;
+        const size_t fixed = sizeof(float2) * (size_t)(32 * lanes + units * 32 * pitch) + sizeof(double) * 4 * (kThreads / 32) +
+                             sizeof(float) * (size_t)(n_fft + bins * (ft + 1)) + sizeof(float) * (size_t)((ft - 1) * hop + n_fft);
+        const size_t limit = 227 * 1024;
+        while (p->max_hops > 0 && fixed + sizeof(float2) * (size_t)p->max_hops * hop > limit) --p->max_hops;
+        if (n_out == 0) p->max_hops = 1;
+    }
+    if (p->max_hops == 0) {  // hop so small that even a one-hop tile needs more frames than a CTA holds
+        adv_plan_destroy(p);
+        return ADV_ERR_UNSUPPORTED;
+    }
+    *out = p;
+    return ADV_OK;
+}
+
+void adv_plan_destroy(adv_plan* plan) {
+    if (!plan) return;
+    if (plan->dev_block) cudaFree(plan->dev_block);
+    free(plan);
+}
+
+int adv_plan_bins(const adv_plan* plan) { return plan ? plan->d.n_fft / 2 + 1 : ADV_ERR_INVALID; }
+int adv_plan_frames(const adv_plan* plan) { return plan ? plan->d.T : ADV_ERR_INVALID; }
+int adv_plan_tiles(const adv_plan* plan, int batch) {
+    if (!plan || batch <= 0 || plan->d.n_out <= 0) return ADV_ERR_INVALID;
+    return choose_tiling(plan, batch).tiles;
+}
+
+int adv_stft(const adv_plan* plan, const float* wav, int64_t wav_stride, int batch, adv_c64* X, float* mag,
+             float* phase, void* stream) {
+    if (!plan || !wav || !X || batch <= 0 || plan->d.n_in <= 0 || wav_stride < plan->d.n_in) return ADV_ERR_INVALID;
+    return launch_stft(plan, wav, wav_stride, batch, (float2*)X, mag, phase, (cudaStream_t)stream);
+}
+
+int adv_istft(const adv_plan* plan, const adv_c64* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
+              double* stats, void* stream) {
+    if (!plan || !X || !out || batch <= 0 || plan->d.n_out <= 0) return ADV_ERR_INVALID;
+    return launch_istft(plan, (const float2*)X, sb, st, sf, batch, out, stats, (cudaStream_t)stream);
+}
+
+int adv_explain(const adv_plan* plan, const float* wav, int64_t wav_stride, const float* mask, int Fm, int Tm, int mode,
+                int batch, float* rel, float* irr, double* stats, void* stream) {
+    if (!plan || !wav || !mask || !rel || !irr || batch <= 0 || plan->d.n_in <= 0 || wav_stride < plan->d.n_in ||
+        plan->d.n_out <= 0)
+        return ADV_ERR_INVALID;
+    if (mode != ADV_MASK_LOG1P && mode != ADV_MASK_LINEAR) return ADV_ERR_INVALID;
+    if (Fm <= 0 || Tm <= 0 || Fm > plan->d.n_fft / 2 + 1 || Tm > plan->d.T) return ADV_ERR_SHAPE;
+    return launch_explain(plan, wav, wav_stride, nullptr, 0, 0, 0, mask, Fm, Tm, mode, batch, rel, irr, stats,
+                          (cudaStream_t)stream);
+}
+
+int adv_explain_spec(const adv_plan* plan, const adv_c64* X, int64_t sb, int64_t st, int64_t sf, const float* mask,
+                     int Fm, int Tm, int mode, int batch, float* rel, float* irr, double* stats, void* stream) {
+    if (!plan || !X || !mask || !rel || !irr || batch <= 0 || plan->d.n_out <= 0) return ADV_ERR_INVALID;
+    if (mode != ADV_MASK_LOG1P && mode != ADV_MASK_LINEAR) return ADV_ERR_INVALID;
+    if (Fm <= 0 || Tm <= 0 || Fm > plan->d.n_fft / 2 + 1 || Tm > plan->d.T) return ADV_ERR_SHAPE;
+    return launch_explain(plan, nullptr, 0, (const float2*)X, sb, st, sf, mask, Fm, Tm, mode, batch, rel, irr, stats,
+                          (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,312 @@
+// In-register radix FFT building blocks and the lane-cooperative NF-point complex FFT
+// ("unit FFT") used by the STFT / iSTFT / fused explain kernels.
+//
+// Design (B200, sm_100a):
+//   * One *unit* = NF/32 lanes of a warp (16 lanes for NF=512, a full warp for NF=1024).
+//     Every lane holds 32 complex values in registers.
+//   * NF = 32 x R2 four-step FFT:  radix-32 in registers over n1 (stride R2), twiddle
+//     W_NF^(n2*k1), ONE shared-memory transpose inside the unit (no block barrier, only
+//     __syncwarp), radix-R2 in registers over n2.  Output index k = k1 + 32*k2.
+//   * The inverse runs the mirrored data flow, so it consumes exactly the register layout
+//     the forward produces and vice versa: forward -> (mask) -> inverse needs no re-layout.
+//   * Row ownership after the transpose pairs row k1 with row 32-k1 in the same lane
+//     (NF=512) so that bins k and NF-k are in the same thread: the two-real-frames-in-one-
+//     complex-FFT split/merge is register-local.  For NF=1024 each lane owns one row and
+//     the mirror bin lives in lane (32-l)&31: one shuffle per value.
+//
+// Everything here is __host__ __device__ so tests/host_emul.cu can run the same code
+// lane-by-lane on the CPU (no GPU in the build container).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#define ADV_HD __host__ __device__ __forceinline__
+
+namespace adv {
+
+template <int I> struct IC { static constexpr int value = I; };
+template <int B, int E, class Fn>
+ADV_HD void static_for(Fn&& f) {
+    if constexpr (B < E) {
+        f(IC<B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+// cos/sin(2*pi*k/32), k = 0..15 (butterfly twiddles only need the upper half-plane)
+static constexpr float kCos32[16] = {
+    1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+    0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f,
+    0.0f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f,
+    -0.70710678118654746f, -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f};
+static constexpr float kSin32[16] = {
+    0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+    0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
+    1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f,
+    0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f};
+
+ADV_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+ADV_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+ADV_HD float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+ADV_HD float2 cmulc(float2 a, float2 b) {
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+ADV_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+// a * exp(DIR * 2*pi*i * K / N), K in [0, N/2), N in {2,4,8,16,32}; DIR = -1 forward, +1 inverse
+template <int N, int K, int DIR>
+ADV_HD float2 twmul(float2 a) {
+    static_assert(K >= 0 && 2 * K < N || N == 1, "butterfly twiddle index");
+    if constexpr (K == 0) {
+        return a;
+    } else if constexpr (4 * K == N) {
+        return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+    } else if constexpr (8 * K == N) {
+        constexpr float h = 0.70710678118654752f;
+        return DIR < 0 ? make_float2((a.x + a.y) * h, (a.y - a.x) * h)
+                       : make_float2((a.x - a.y) * h, (a.x + a.y) * h);
+    } else if constexpr (8 * K == 3 * N) {
+        constexpr float h = 0.70710678118654752f;
+        return DIR < 0 ? make_float2((a.y - a.x) * h, -(a.x + a.y) * h)
+                       : make_float2(-(a.x + a.y) * h, (a.x - a.y) * h);
+    } else {
+        constexpr int idx = K * (32 / N);
+        constexpr float c = kCos32[idx];
+        constexpr float s = (DIR < 0 ? -1.0f : 1.0f) * kSin32[idx];
+        return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+    }
+}
+
+// N-point DFT of in[0], in[S], in[2S], ... -> out[0..N-1] (natural order), all in registers.
+template <int N, int DIR>
+struct FFTReg {
+    template <int S>
+    static ADV_HD void run(const float2* in, float2* out) {
+        float2 e[N / 2], o[N / 2];
+        FFTReg<N / 2, DIR>::template run<2 * S>(in, e);
+        FFTReg<N / 2, DIR>::template run<2 * S>(in + S, o);
+        static_for<0, N / 2>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const float2 t = twmul<N, k, DIR>(o[k]);
+            out[k] = cadd(e[k], t);
+            out[k + N / 2] = csub(e[k], t);
+        });
+    }
+};
+template <int DIR>
+struct FFTReg<4, DIR> {
+    template <int S>
+    static ADV_HD void run(const float2* in, float2* out) {
+        const float2 a = cadd(in[0], in[2 * S]), b = csub(in[0], in[2 * S]);
+        const float2 c = cadd(in[S], in[3 * S]);
+        const float2 d = twmul<4, 1, DIR>(csub(in[S], in[3 * S]));
+        out[0] = cadd(a, c);
+        out[2] = csub(a, c);
+        out[1] = cadd(b, d);
+        out[3] = csub(b, d);
+    }
+};
+template <int DIR>
+struct FFTReg<2, DIR> {
+    template <int S>
+    static ADV_HD void run(const float2* in, float2* out) {
+        out[0] = cadd(in[0], in[S]);
+        out[1] = csub(in[0], in[S]);
+    }
+};
+
+template <int N, int DIR>
+ADV_HD void fft_inplace(float2* v) {
+    float2 t[N];
+    FFTReg<N, DIR>::template run<1>(v, t);
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = t[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Geometry of the lane-cooperative NF-point FFT
+// ---------------------------------------------------------------------------------------------
+template <int NF>
+struct Geo {
+    static_assert(NF == 512 || NF == 1024, "supported FFT sizes: 512, 1024");
+    static constexpr int R2 = NF / 32;      // second-step radix == lanes per unit
+    static constexpr int LANES = R2;        // lanes cooperating on one FFT
+    static constexpr int ROWS = 32 / LANES; // rows (k1) owned per lane after the transpose
+    static constexpr int PITCH = R2 + 1;    // scratch row pitch in float2 (odd: conflict-free)
+    static constexpr int SCRATCH = 32 * PITCH;  // float2 per unit
+    static constexpr int NBINS = NF / 2 + 1;
+    static constexpr int BINS_PER_LANE = 17;  // 16 (+ Nyquist on lane 0)
+};
+
+// Row k1 owned by lane l in slot r (r < ROWS).  NF=512: {l, 32-l} (lane 0: {0, 16}); NF=1024: {l}.
+template <int NF>
+ADV_HD int row_of(int l, int r) {
+    if constexpr (NF == 512) return r == 0 ? l : (l == 0 ? 16 : 32 - l);
+    else return l;
+}
+
+// One-sided bin index handled by lane l in slot i (0..16); -1 when the slot is empty.
+template <int NF>
+ADV_HD int bin_of(int l, int i) {
+    if constexpr (NF == 512) {
+        if (i < 8) return l + 32 * i;
+        if (i < 16) return (l == 0 ? 16 : 32 - l) + 32 * (i - 8);
+        return l == 0 ? 256 : -1;
+    } else {
+        if (i < 16) return l + 32 * i;
+        return l == 0 ? 512 : -1;
+    }
+}
+
+// ---- forward: time samples -> spectrum ------------------------------------------------------
+// in : v[n1] = z[n1*R2 + l]          (n1 = 0..31)
+// out: v[r*R2 + k2] = Z[row_of(l,r) + 32*k2]
+// tw : per-lane twiddles tw[k1] = exp(-2*pi*i * l*k1 / NF), read through a functor so the caller
+//      decides where they live (registers, shared memory)
+template <int NF, class TwFn>
+ADV_HD void fwd_phase_a(float2* v, int l, TwFn tw, float2* scratch) {
+    using G = Geo<NF>;
+    fft_inplace<32, -1>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+        const float2 w = k1 == 0 ? v[0] : cmul(v[k1], tw(k1));
+        scratch[k1 * G::PITCH + l] = w;
+    }
+}
+template <int NF>
+ADV_HD void fwd_phase_b(float2* v, int l, const float2* scratch) {
+    using G = Geo<NF>;
+#pragma unroll
+    for (int r = 0; r < G::ROWS; ++r) {
+        const int row = row_of<NF>(l, r);
+#pragma unroll
+        for (int i = 0; i < G::R2; ++i) v[r * G::R2 + i] = scratch[row * G::PITCH + i];
+        fft_inplace<G::R2, -1>(v + r * G::R2);
+    }
+}
+
+// ---- inverse: spectrum -> time samples (unnormalised) ---------------------------------------
+// in : v[r*R2 + k2] = Z[row_of(l,r) + 32*k2]
+// out: v[n1] = NF * z[n1*R2 + l]
+template <int NF>
+ADV_HD void inv_phase_a(float2* v, int l, float2* scratch) {
+    using G = Geo<NF>;
+#pragma unroll
+    for (int r = 0; r < G::ROWS; ++r) {
+        const int row = row_of<NF>(l, r);
+        fft_inplace<G::R2, +1>(v + r * G::R2);
+#pragma unroll
+        for (int i = 0; i < G::R2; ++i) scratch[row * G::PITCH + i] = v[r * G::R2 + i];
+    }
+}
+template <int NF, class TwFn>
+ADV_HD void inv_phase_b(float2* v, int l, TwFn tw, const float2* scratch) {
+    using G = Geo<NF>;
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+        const float2 w = scratch[k1 * G::PITCH + l];
+        v[k1] = k1 == 0 ? w : cmulc(w, tw(k1));
+    }
+    fft_inplace<32, +1>(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two real frames in one complex FFT: split (after forward) and merge (before inverse).
+//   Z = FFT(xa + i*xb)  =>  XA[k] = (Z[k] + conj Z[NF-k]) / 2,  XB[k] = (Z[k] - conj Z[NF-k]) / (2i)
+//   Z[k] = YA[k] + i*YB[k], Z[NF-k] = conj(YA[k]) + i*conj(YB[k])   (YA, YB Hermitian halves)
+// Lane l handles the one-sided bins bin_of(l, i), i = 0..16.
+// ---------------------------------------------------------------------------------------------
+ADV_HD void split_pair(float2 a, float2 b, float2& xa, float2& xb) {
+    // a = Z[k], b = Z[NF-k]
+    xa = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+    xb = make_float2(0.5f * (a.y + b.y), 0.5f * (b.x - a.x));
+}
+ADV_HD void merge_pair(float2 ya, float2 yb, float2& a, float2& b) {
+    // a = Z[k] = ya + i*yb ; b = Z[NF-k] = conj(ya) + i*conj(yb)
+    a = make_float2(ya.x - yb.y, ya.y + yb.x);
+    b = make_float2(ya.x + yb.y, yb.x - ya.y);
+}
+ADV_HD float2 sel(bool c, float2 a, float2 b) { return c ? a : b; }
+
+// NF = 512, register-local.  v holds the forward output layout; xa/xb get 17 slots.
+ADV_HD void split512(const float2* v, int l, float2* xa, float2* xb) {
+    const bool z = (l == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // bins l + 32 i (row r0); mirror in row r1 (lane 0: in row 0)
+        const float2 a = v[i];
+        const float2 b = sel(z, v[(16 - i) & 15], v[31 - i]);
+        split_pair(a, b, xa[i], xb[i]);
+    }
+#pragma unroll
+    for (int i = 8; i < 16; ++i) {  // bins r1 + 32 (i-8); mirror in row r0 (lane 0: in row 16)
+        const float2 a = v[i + 8];
+        const float2 b = sel(z, v[39 - i], v[23 - i]);
+        split_pair(a, b, xa[i], xb[i]);
+    }
+    // Nyquist (lane 0 only, bin 256 = row 0, k2 = 8): self-mirrored
+    split_pair(v[8], v[8], xa[16], xb[16]);
+}
+// Inverse of split512: builds the inverse-FFT input layout from two one-sided spectra.
+// Imaginary parts of DC / Nyquist are dropped (C2R semantics).
+ADV_HD void merge512(float2* v, int l, const float2* ya, const float2* yb) {
+    const bool z = (l == 0);
+    float2 za[17], zb[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) merge_pair(ya[i], yb[i], za[i], zb[i]);
+    const float2 dc = make_float2(ya[0].x, yb[0].x);
+    const float2 ny = make_float2(ya[16].x, yb[16].x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = za[i];
+#pragma unroll
+    for (int i = 8; i < 16; ++i) v[i + 8] = za[i];
+    if (z) v[0] = dc;
+    // mirrors: lane>0: zb[i<8] -> 31-i, zb[i>=8] -> 23-i ; lane 0: zb[i<8] -> 16-i (i>=1),
+    // zb[i>=8] -> 39-i, Nyquist -> 8
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        v[24 + q] = sel(z, zb[15 - q], zb[7 - q]);
+        v[8 + q] = sel(z, q == 0 ? ny : zb[8 - q], zb[15 - q]);
+    }
+}
+
+// NF = 1024: the mirror of bin l+32 i lives in lane (32-l)&31 at register 31-i (lane 0: own 32-i).
+// Split is 3 steps so the host emulation can perform the exchange: pre -> exchange16 -> post.
+ADV_HD void split1024_pre(const float2* v, float2* send) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) send[i] = v[31 - i];
+}
+ADV_HD void split1024_post(const float2* v, int l, const float2* recv, float2* xa, float2* xb) {
+    const bool z = (l == 0);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float2 b = sel(z, v[(32 - i) & 31], recv[i]);
+        split_pair(v[i], b, xa[i], xb[i]);
+    }
+    split_pair(v[16], v[16], xa[16], xb[16]);
+}
+ADV_HD void merge1024_pre(float2* v, int l, const float2* ya, const float2* yb, float2* send) {
+    const bool z = (l == 0);
+    float2 zb[17];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) merge_pair(ya[i], yb[i], v[i], zb[i]);
+    if (z) v[0] = make_float2(ya[0].x, yb[0].x);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) send[i] = zb[i];
+    // lane 0 keeps its own mirrors: zb[i] -> register 32-i (i = 1..15), Nyquist -> 16
+    if (z) {
+#pragma unroll
+        for (int i = 1; i < 16; ++i) v[32 - i] = zb[i];
+        v[16] = make_float2(ya[16].x, yb[16].x);
+    }
+}
+ADV_HD void merge1024_post(float2* v, int l, const float2* recv) {
+    if (l != 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[31 - i] = recv[i];
+    }
+}
+
+}  // namespace adv

@@ -1,0 +1,369 @@
+// HBM-bound elementwise / reduction kernels of the path (sm_100a):
+//   row_stats / normalize - zero_mean_unit_var_norm            classifier_embedder.py:59-63
+//   lmac_reduce           - sigmoid + FF/Fid/AD/AI/AG + sums   LMAC_metrics.py:31-73,160-172
+//   mask_apply            - standalone mask arithmetic         LMAC_metrics.py:136-143,151-153; loss_function.py:36-45
+//   td_mask               - saliency time-domain mask          captum_saliency.py:136-143
+//   mask_head             - 1x1 conv (C->1) + sigmoid          addvisor.py:57-60,82
+//   band_swap             - complex row replacement            train_logReg_swapping.py:64-75, hifigan.py:206-214
+// All are single-pass streaming kernels: coalesced 128-bit accesses where alignment allows, fp64
+// partial sums reduced in a fixed order (bit-reproducible for a given launch shape).
+#include "adv_internal.cuh"
+
+namespace adv {
+
+constexpr int kRowChunk = 8192;  // samples per row_stats block
+constexpr int kPwThreads = 256;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- per-row partial sums ----------------------------------------------------------------------
+__global__ void __launch_bounds__(kPwThreads)
+row_stats_kernel(const float* __restrict__ in, int n, int parts, double* __restrict__ stats) {
+    __shared__ double red[2][kPwThreads / 32];
+    const int b = blockIdx.y, part = blockIdx.x;
+    const float* row = in + (size_t)b * n;
+    const int lo = part * kRowChunk, hi = min(n, lo + kRowChunk);
+    double s = 0.0, ss = 0.0;
+    for (int i = lo + threadIdx.x; i < hi; i += kPwThreads) {
+        const float x = __ldg(row + i);
+        s += (double)x;
+        ss += (double)x * (double)x;
+    }
+    s = warp_sum_d(s);
+    ss = warp_sum_d(ss);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s;
+        red[1][threadIdx.x >> 5] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int k = 0; k < kPwThreads / 32; ++k) {
+            a += red[0][k];
+            c += red[1][k];
+        }
+        stats[((size_t)b * parts + part) * 2 + 0] = a;
+        stats[((size_t)b * parts + part) * 2 + 1] = c;
+    }
+}
+
+// ---- (x - mean) / (std_unbiased + 1e-7) -----------------------------------------------------------
+__global__ void __launch_bounds__(kPwThreads)
+normalize_kernel(const float* __restrict__ in, float* __restrict__ out, int n, const double* __restrict__ stats,
+                 int parts, int width, int col) {
+    __shared__ float s_mean, s_inv;
+    const int b = blockIdx.y;
+    if (threadIdx.x == 0) {
+        double s = 0.0, ss = 0.0;
+        const double* st = stats + (size_t)b * parts * width + col;
+        for (int k = 0; k < parts; ++k) {  // fixed order: same value in every block of the row
+            s += st[(size_t)k * width];
+            ss += st[(size_t)k * width + 1];
+        }
+        const double mean = s / (double)n;
+        double var = (ss - s * mean) / (double)(n - 1);  // unbiased (torch.std default)
+        if (var < 0.0) var = 0.0;
+        s_mean = (float)mean;
+        s_inv = (float)sqrt(var) + 1e-7f;
+    }
+    __syncthreads();
+    const float mean = s_mean, den = s_inv;
+    const float* row = in + (size_t)b * n;
+    float* orow = out + (size_t)b * n;
+    const int lo = blockIdx.x * kRowChunk, hi = min(n, lo + kRowChunk);
+    for (int i = lo + threadIdx.x; i < hi; i += kPwThreads) orow[i] = (__ldg(row + i) - mean) / den;
+}
+
+// ---- LMAC scores + deterministic two-level sum -----------------------------------------------------
+constexpr int kLmacPerBlock = 1024;
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(kPwThreads)
+lmac_kernel(const float* __restrict__ p_in, const float* __restrict__ th_in, const float* __restrict__ q_in, int n,
+            int is_logit, float* __restrict__ scores, double* __restrict__ sums, double* __restrict__ partials,
+            unsigned int* __restrict__ counter) {
+    __shared__ double red[5][kPwThreads / 32];
+    __shared__ bool last;
+    double acc[5] = {0, 0, 0, 0, 0};
+    const int lo = blockIdx.x * kLmacPerBlock, hi = min(n, lo + kLmacPerBlock);
+    for (int i = lo + threadIdx.x; i < hi; i += kPwThreads) {
+        float p = p_in[i], th = th_in[i], q = q_in[i];
+        if (is_logit) {  // classifier_embedder.py:36
+            p = sigmoidf_ref(p);
+            th = sigmoidf_ref(th);
+            q = sigmoidf_ref(q);
+        }
+        // LMAC_metrics.py:43-45 (pred*p + (1-pred)*(1-p) is exactly p or 1-p)
+        const float pc = (p > 0.5f) ? p : 1.0f - p;
+        const float oc = (th > 0.5f) ? th : 1.0f - th;
+        const float d = p - 0.5f;
+        const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+        const float ff = (p - q) * sgn;                                        // :48-52
+        const float fid = ((p > 0.5f) == (th > 0.5f)) ? 1.f : 0.f;             // :31-38
+        const float ad = (fmaxf(pc - oc, 0.f) / (pc + 1e-10f)) * 100.f;        // :55-59
+        const float ai = (oc > pc) ? 100.f : 0.f;                              // :62-66
+        const float ag = (fmaxf(oc - pc, 0.f) / ((1.f - pc) + 1e-10f)) * 100.f;  // :69-73
+        if (scores != nullptr) {
+            float* s = scores + (size_t)i * 7;
+            s[0] = ff; s[1] = fid; s[2] = ad; s[3] = ai; s[4] = ag; s[5] = pc; s[6] = oc;
+        }
+        acc[0] += ff; acc[1] += fid; acc[2] += ad; acc[3] += ai; acc[4] += ag;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        acc[k] = warp_sum_d(acc[k]);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double s = 0.0;
+        for (int w = 0; w < kPwThreads / 32; ++w) s += red[threadIdx.x][w];
+        partials[(size_t)blockIdx.x * 5 + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {  // the last block to finish folds the block partials in block order
+        __threadfence();
+        if (threadIdx.x < 5) {
+            double s = 0.0;
+            for (unsigned int k = 0; k < gridDim.x; ++k) s += partials[(size_t)k * 5 + threadIdx.x];
+            sums[threadIdx.x] = s;
+        }
+        if (threadIdx.x == 5) sums[5] = (double)n;
+        if (threadIdx.x == 0) *counter = 0u;  // re-arm for the next launch
+    }
+}
+
+// ---- standalone mask-apply on (mag, phase) ---------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kPwThreads)
+mask_apply_kernel(const float* __restrict__ mag, const float* __restrict__ phase, const float* __restrict__ mask,
+                  int T, int F, int Fm, int Tm, float2* __restrict__ rel, float2* __restrict__ irr) {
+    // 32(f) x 32(t) tile; the mask is [Fm][Tm] (t fastest), the spectra are frame-major (f fastest):
+    // transpose the mask tile through shared memory so both sides are coalesced
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, f0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const float* mrow = mask + (size_t)b * Fm * Tm;
+    for (int r = ty; r < 32; r += 8) {
+        const int f = f0 + r, t = t0 + tx;
+        tile[r][tx] = (f < Fm && t < Tm) ? __ldg(mrow + (size_t)f * Tm + t) : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int t = t0 + r, f = f0 + tx;
+        if (t >= T || f >= F) continue;
+        const size_t idx = ((size_t)b * T + t) * F + f;
+        const float m = tile[tx][r];
+        const float a = __ldg(mag + idx);
+        float s, c;
+        sincosf(__ldg(phase + idx), &s, &c);  // exp(1j*phase)
+        float ar, ai;
+        if (MODE == ADV_MASK_LINEAR) {
+            ar = m * a;
+            ai = (1.0f - m) * a;
+        } else {
+            const float lm = log1pf(a);
+            ar = expm1f(m * lm);
+            ai = expm1f((1.0f - m) * lm);
+        }
+        rel[idx] = make_float2(ar * c, ar * s);
+        irr[idx] = make_float2(ai * c, ai * s);
+    }
+}
+
+// ---- time-domain saliency mask --------------------------------------------------------------------
+__global__ void __launch_bounds__(kPwThreads)
+rowmax_abs_kernel(const float* __restrict__ attr, int n, float* __restrict__ rowmax) {
+    const int b = blockIdx.y;
+    const float* row = attr + (size_t)b * n;
+    const int lo = blockIdx.x * kRowChunk, hi = min(n, lo + kRowChunk);
+    float m = 0.f;
+    for (int i = lo + threadIdx.x; i < hi; i += kPwThreads) m = fmaxf(m, fabsf(__ldg(row + i)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // non-negative floats order like their bit patterns: integer atomicMax is exact and order-free
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(rowmax + b), __float_as_int(m));
+}
+__global__ void __launch_bounds__(kPwThreads)
+td_mask_kernel(const float* __restrict__ wave, const float* __restrict__ attr, int n,
+               const float* __restrict__ rowmax, float* __restrict__ mask_out, float* __restrict__ rel,
+               float* __restrict__ irr) {
+    const int b = blockIdx.y;
+    const float den = rowmax[b] + 1e-8f;
+    const size_t base = (size_t)b * n;
+    const int lo = blockIdx.x * kRowChunk, hi = min(n, lo + kRowChunk);
+    for (int i = lo + threadIdx.x; i < hi; i += kPwThreads) {
+        const float m = fabsf(__ldg(attr + base + i)) / den;
+        const float w = __ldg(wave + base + i);
+        if (mask_out != nullptr) mask_out[base + i] = m;
+        rel[base + i] = w * m;
+        irr[base + i] = w * (1.0f - m);
+    }
+}
+
+// ---- mask head: sigmoid(sum_c w_c * y1[b,c,:] + bias) ------------------------------------------------
+template <int C, bool VEC>
+__global__ void __launch_bounds__(kPwThreads)
+mask_head_kernel(const float* __restrict__ y1, const float* __restrict__ w, const float* __restrict__ bias,
+                 int64_t hw, float* __restrict__ mask) {
+    __shared__ float ws[C];
+    if (threadIdx.x < C) ws[threadIdx.x] = w[threadIdx.x];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const float bb = bias[0];
+    const float* src = y1 + (size_t)b * C * hw;
+    float* dst = mask + (size_t)b * hw;
+    if (VEC) {
+        const int64_t nv = hw / 4;
+        for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < nv; i += (int64_t)gridDim.x * kPwThreads) {
+            float4 v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * hw) + i);
+            float4 a = make_float4(bb, bb, bb, bb);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                a.x = fmaf(ws[c], v[c].x, a.x);
+                a.y = fmaf(ws[c], v[c].y, a.y);
+                a.z = fmaf(ws[c], v[c].z, a.z);
+                a.w = fmaf(ws[c], v[c].w, a.w);
+            }
+            a.x = sigmoidf_ref(a.x); a.y = sigmoidf_ref(a.y); a.z = sigmoidf_ref(a.z); a.w = sigmoidf_ref(a.w);
+            reinterpret_cast<float4*>(dst)[i] = a;
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < hw; i += (int64_t)gridDim.x * kPwThreads) {
+            float a = bb;
+#pragma unroll
+            for (int c = 0; c < C; ++c) a = fmaf(ws[c], __ldg(src + (size_t)c * hw + i), a);
+            dst[i] = sigmoidf_ref(a);
+        }
+    }
+}
+__global__ void __launch_bounds__(kPwThreads)
+mask_head_generic_kernel(const float* __restrict__ y1, const float* __restrict__ w, const float* __restrict__ bias,
+                         int C, int64_t hw, float* __restrict__ mask) {
+    const int b = blockIdx.y;
+    const float bb = bias[0];
+    const float* src = y1 + (size_t)b * C * hw;
+    for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < hw; i += (int64_t)gridDim.x * kPwThreads) {
+        float a = bb;
+        for (int c = 0; c < C; ++c) a = fmaf(__ldg(w + c), __ldg(src + (size_t)c * hw + i), a);
+        mask[(size_t)b * hw + i] = sigmoidf_ref(a);
+    }
+}
+
+// ---- band swap -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPwThreads)
+band_swap_kernel(const float2* __restrict__ real, const float2* __restrict__ voc, int64_t total, int F, int f_lo,
+                 int f_hi, float2* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kPwThreads) {
+        const int f = (int)(i % F);
+        out[i] = (f >= f_lo && f < f_hi) ? __ldg(voc + i) : __ldg(real + i);
+    }
+}
+
+}  // namespace adv
+
+using namespace adv;
+
+extern "C" {
+
+int adv_row_stats_parts(int n) { return n <= 0 ? 0 : (n + kRowChunk - 1) / kRowChunk; }
+
+int adv_row_stats(const float* in, int batch, int n, double* stats, void* stream) {
+    if (!in || !stats || batch <= 0 || n <= 1) return ADV_ERR_INVALID;
+    const int parts = adv_row_stats_parts(n);
+    row_stats_kernel<<<dim3(parts, batch), kPwThreads, 0, (cudaStream_t)stream>>>(in, n, parts, stats);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int adv_normalize(const float* in, float* out, int batch, int n, const double* stats, int parts, int width,
+                  int col, void* stream) {
+    if (!in || !out || !stats || batch <= 0 || n <= 1 || parts <= 0 || width < 2 || col < 0 || col + 2 > width)
+        return ADV_ERR_INVALID;
+    const int chunks = (n + kRowChunk - 1) / kRowChunk;
+    normalize_kernel<<<dim3(chunks, batch), kPwThreads, 0, (cudaStream_t)stream>>>(in, out, n, stats, parts, width, col);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int adv_lmac_blocks(int n) { return n <= 0 ? 0 : (n + kLmacPerBlock - 1) / kLmacPerBlock; }
+
+int adv_lmac_reduce(const float* p, const float* theta, const float* q, int n, int is_logit, float* scores,
+                    double* sums, double* block_partials, unsigned int* counter, void* stream) {
+    if (!p || !theta || !q || !sums || !block_partials || !counter || n <= 0) return ADV_ERR_INVALID;
+    lmac_kernel<<<adv_lmac_blocks(n), kPwThreads, 0, (cudaStream_t)stream>>>(p, theta, q, n, is_logit, scores, sums,
+                                                                            block_partials, counter);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int adv_mask_apply(const float* mag, const float* phase, const float* mask, int batch, int T, int F, int Fm, int Tm,
+                   int mode, adv_c64* rel, adv_c64* irr, void* stream) {
+    if (!mag || !phase || !mask || !rel || !irr || batch <= 0 || T <= 0 || F <= 0) return ADV_ERR_INVALID;
+    if (Fm > F || Tm > T || Fm <= 0 || Tm <= 0) return ADV_ERR_SHAPE;
+    dim3 grid((F + 31) / 32, (T + 31) / 32, batch);
+    if (mode == ADV_MASK_LOG1P)
+        mask_apply_kernel<ADV_MASK_LOG1P><<<grid, kPwThreads, 0, (cudaStream_t)stream>>>(
+            mag, phase, mask, T, F, Fm, Tm, (float2*)rel, (float2*)irr);
+    else if (mode == ADV_MASK_LINEAR)
+        mask_apply_kernel<ADV_MASK_LINEAR><<<grid, kPwThreads, 0, (cudaStream_t)stream>>>(
+            mag, phase, mask, T, F, Fm, Tm, (float2*)rel, (float2*)irr);
+    else
+        return ADV_ERR_INVALID;
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int adv_td_mask(const float* wave, const float* attr, int batch, int n, float* mask_out, float* rel, float* irr,
+                float* rowmax, void* stream) {
+    if (!wave || !attr || !rel || !irr || !rowmax || batch <= 0 || n <= 0) return ADV_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    ADV_CUDA_CHECK(cudaMemsetAsync(rowmax, 0, sizeof(float) * batch, s));
+    const int chunks = (n + kRowChunk - 1) / kRowChunk;
+    rowmax_abs_kernel<<<dim3(chunks, batch), kPwThreads, 0, s>>>(attr, n, rowmax);
+    td_mask_kernel<<<dim3(chunks, batch), kPwThreads, 0, s>>>(wave, attr, n, rowmax, mask_out, rel, irr);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int adv_mask_head(const float* y1, const float* w, const float* bias, int batch, int channels, int64_t hw, float* mask,
+                  void* stream) {
+    if (!y1 || !w || !bias || !mask || batch <= 0 || channels <= 0 || hw <= 0) return ADV_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(mask)) % 16 == 0);
+    const int64_t work = vec ? hw / 4 : hw;
+    int gx = (int)((work + kPwThreads - 1) / kPwThreads);
+    if (gx > 148 * 16) gx = 148 * 16;
+    if (channels == 32) {
+        if (vec) mask_head_kernel<32, true><<<dim3(gx, batch), kPwThreads, 0, s>>>(y1, w, bias, hw, mask);
+        else mask_head_kernel<32, false><<<dim3(gx, batch), kPwThreads, 0, s>>>(y1, w, bias, hw, mask);
+    } else {
+        mask_head_generic_kernel<<<dim3(gx, batch), kPwThreads, 0, s>>>(y1, w, bias, channels, hw, mask);
+    }
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int adv_band_swap(const adv_c64* real, const adv_c64* voc, int batch, int T, int F, int f_lo, int f_hi, adv_c64* out,
+                  void* stream) {
+    if (!real || !voc || !out || batch <= 0 || T <= 0 || F <= 0) return ADV_ERR_INVALID;
+    const int64_t total = (int64_t)batch * T * F;
+    int gx = (int)((total + kPwThreads - 1) / kPwThreads);
+    if (gx > 148 * 16) gx = 148 * 16;
+    band_swap_kernel<<<gx, kPwThreads, 0, (cudaStream_t)stream>>>((const float2*)real, (const float2*)voc, total, F,
+                                                                 f_lo, f_hi, (float2*)out);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+"""Tensor-level wrappers over the C ABI (torch is only the owner of device memory and streams).
+
+Every function here launches hand-written sm_100a kernels from libaddvisor_sm100.so on the
+current CUDA stream.  Inputs that live on the host are moved with ``.to(device)`` exactly like
+the reference does (audioprocessor.py:90,98); nothing is computed on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, get_plan, lib, ptr, stream_ptr
+
+MODES = {"log1p": _lib.MASK_LOG1P, "linear": _lib.MASK_LINEAR}
+
+
+def _dev():
+    _lib.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _f32_rows(x, name):
+    """float32 CUDA tensor [B, n] with unit stride on the last dim."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    x = x.to(_dev(), non_blocking=True)
+    if x.dim() != 2:
+        raise ValueError(f"{name} must be 2-D")
+    if x.stride(1) != 1 or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
+        x = x.contiguous()
+    return x
+
+
+def _mask3(mask):
+    if mask.dim() == 4 and mask.shape[1] == 1:  # UNet output [B,1,F,T] (addvisor.py:82)
+        mask = mask[:, 0]
+    if mask.dim() != 3:
+        raise ValueError("mask must be [B,F,T] (or [B,1,F,T])")
+    return mask.to(_dev(), torch.float32, non_blocking=True).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+def stft(wave, n_fft, hop, win_length, window=None, want_mag=True, want_phase=True):
+    """wave [B,n] -> (X [B,F,T] complex64 with torch.stft's frame-major strides, mag, phase)."""
+    wave = _f32_rows(wave, "waveform")
+    B, n = wave.shape
+    T, Fb = 1 + n // hop, n_fft // 2 + 1
+    plan = get_plan(n_fft, hop, win_length, window, T, n, 0)  # forward-only plan
+    X = torch.empty((B, T, Fb), dtype=torch.complex64, device=wave.device)
+    mag = torch.empty((B, T, Fb), dtype=torch.float32, device=wave.device) if want_mag else None
+    ph = torch.empty((B, T, Fb), dtype=torch.float32, device=wave.device) if want_phase else None
+    check(lib().adv_stft(plan.handle, ptr(wave), wave.stride(0), B, ptr(X), ptr(mag), ptr(ph), stream_ptr()),
+          "adv_stft")
+    tr = lambda t: None if t is None else t.transpose(1, 2)
+    return tr(X), tr(mag), tr(ph)
+
+
+def _spec_strides(spec):
+    """(tensor, sb, st, sf) element strides of a complex [B,F,T] tensor, no copy when possible."""
+    if spec.dtype != torch.complex64:
+        spec = spec.to(torch.complex64)
+    spec = spec.to(_dev(), non_blocking=True)
+    return spec, spec.stride(0), spec.stride(2), spec.stride(1)
+
+
+def istft(spec, n_fft, hop, win_length, length=None, window=None, return_stats=False):
+    """spec complex [B,F,T] (any strides) -> wave [B, length]; length=None => hop*(T-1)."""
+    spec, sb, st, sf = _spec_strides(spec)
+    B, Fb, T = spec.shape
+    if Fb != n_fft // 2 + 1:  # torch.istft raises on a wrong bin count
+        raise RuntimeError(f"istft: expected {n_fft // 2 + 1} frequency bins, got {Fb}")
+    n_out = int(length) if length is not None else hop * (T - 1)
+    plan = get_plan(n_fft, hop, win_length, window, T, 0, n_out)
+    out = torch.empty((B, n_out), dtype=torch.float32, device=spec.device)
+    stats = None
+    if return_stats:
+        stats = torch.empty((B, plan.tiles(B), 2), dtype=torch.float64, device=spec.device)
+    check(lib().adv_istft(plan.handle, ptr(spec), sb, st, sf, B, ptr(out), ptr(stats), stream_ptr()), "adv_istft")
+    return (out, stats) if return_stats else out
+
+
+def normalize_(x, stats=None, width=2, col=0, out=None):
+    """(x - mean) / (std_unbiased + 1e-7) per row (classifier_embedder.py:59-63); ``stats`` are the
+    per-tile partial sums an upstream kernel already produced, else one extra pass computes them."""
+    x = _f32_rows(x, "waveform")
+    B, n = x.shape
+    if x.stride(0) != n:
+        x = x.contiguous()
+    if stats is None:
+        parts = lib().adv_row_stats_parts(n)
+        stats = torch.empty((B, parts, 2), dtype=torch.float64, device=x.device)
+        check(lib().adv_row_stats(ptr(x), B, n, ptr(stats), stream_ptr()), "adv_row_stats")
+        width, col = 2, 0
+    parts = stats.shape[1]
+    out = torch.empty_like(x) if out is None else out
+    check(lib().adv_normalize(ptr(x), ptr(out), B, n, ptr(stats), parts, width, col, stream_ptr()), "adv_normalize")
+    return out
+
+
+def explain(wave, mask, n_fft, hop, win_length, length=None, mode="log1p", window=None, normalize=False):
+    """Fused wave + mask -> (masked-in wave, masked-out wave) [B, length] (LMAC_metrics.py:136-157)."""
+    wave = _f32_rows(wave, "waveform")
+    mask = _mask3(mask)
+    B, n = wave.shape
+    if mask.shape[0] != B:
+        raise ValueError("mask batch does not match the waveforms")
+    T = 1 + n // hop
+    n_out = int(length) if length is not None else hop * (T - 1)
+    plan = get_plan(n_fft, hop, win_length, window, T, n, n_out)
+    rel = torch.empty((B, n_out), dtype=torch.float32, device=wave.device)
+    irr = torch.empty_like(rel)
+    stats = torch.empty((B, plan.tiles(B), 4), dtype=torch.float64, device=wave.device) if normalize else None
+    check(lib().adv_explain(plan.handle, ptr(wave), wave.stride(0), ptr(mask), mask.shape[1], mask.shape[2],
+                            MODES[mode], B, ptr(rel), ptr(irr), ptr(stats), stream_ptr()), "adv_explain")
+    if normalize:
+        normalize_(rel, stats, 4, 0, out=rel)
+        normalize_(irr, stats, 4, 2, out=irr)
+    return rel, irr
+
+
+def explain_spec(spec, mask, n_fft, hop, win_length, length=None, mode="log1p", window=None, normalize=False):
+    """Same as :func:`explain` starting from an STFT (complex [B,F,T])."""
+    spec, sb, st, sf = _spec_strides(spec)
+    mask = _mask3(mask)
+    B, Fb, T = spec.shape
+    if Fb != n_fft // 2 + 1:
+        raise RuntimeError(f"istft: expected {n_fft // 2 + 1} frequency bins, got {Fb}")
+    n_out = int(length) if length is not None else hop * (T - 1)
+    plan = get_plan(n_fft, hop, win_length, window, T, 0, n_out)
+    rel = torch.empty((B, n_out), dtype=torch.float32, device=spec.device)
+    irr = torch.empty_like(rel)
+    stats = torch.empty((B, plan.tiles(B), 4), dtype=torch.float64, device=spec.device) if normalize else None
+    check(lib().adv_explain_spec(plan.handle, ptr(spec), sb, st, sf, ptr(mask), mask.shape[1], mask.shape[2],
+                                 MODES[mode], B, ptr(rel), ptr(irr), ptr(stats), stream_ptr()), "adv_explain_spec")
+    if normalize:
+        normalize_(rel, stats, 4, 0, out=rel)
+        normalize_(irr, stats, 4, 2, out=irr)
+    return rel, irr
+
+
+def mask_apply(mag, phase, mask, mode="log1p"):
+    """(|X|, angle X, mask) [B,F,T] -> (rel, irr) complex [B,F,T] exactly as the reference spells it
+    (expm1(m*log1p(mag)) * exp(1j*phase)); outputs are frame-major like torch.stft's."""
+    dev = _dev()
+    B, Fb, T = mag.shape
+    fm = lambda t: t.to(dev, torch.float32).transpose(1, 2).contiguous()  # no-op copy for our own outputs
+    mag_fm, ph_fm = fm(mag), fm(phase)
+    mask = _mask3(mask)
+    rel = torch.empty((B, T, Fb), dtype=torch.complex64, device=dev)
+    irr = torch.empty_like(rel)
+    check(lib().adv_mask_apply(ptr(mag_fm), ptr(ph_fm), ptr(mask), B, T, Fb, mask.shape[1], mask.shape[2],
+                               MODES[mode], ptr(rel), ptr(irr), stream_ptr()), "adv_mask_apply")
+    return rel.transpose(1, 2), irr.transpose(1, 2)
+
+
+class LmacWorkspace:
+    """Device scratch for the metric reduction (block partials, ticket counter, result)."""
+
+    def __init__(self, n, device):
+        blocks = lib().adv_lmac_blocks(n)
+        self.n = n
+        self.partials = torch.empty((blocks, 5), dtype=torch.float64, device=device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.sums = torch.empty(6, dtype=torch.float64, device=device)
+
+
+def lmac(p, theta, q, is_logit=False, want_scores=True, workspace=None):
+    """Three [N] or [N,1] tensors -> (scores [N,7] or None, sums float64 [6]) on the device.
+    Score columns: faithfulness, fidelity, AD, AI, AG, pc, oc; sums = the first five summed, then N."""
+    dev = _dev()
+    flat = lambda t: t.to(dev, torch.float32).reshape(-1).contiguous()
+    p, theta, q = flat(p), flat(theta), flat(q)
+    n = p.numel()
+    if theta.numel() != n or q.numel() != n:
+        raise ValueError("prediction tensors differ in length")
+    ws = workspace if workspace is not None and workspace.n == n else LmacWorkspace(n, dev)
+    scores = torch.empty((n, 7), dtype=torch.float32, device=dev) if want_scores else None
+    check(lib().adv_lmac_reduce(ptr(p), ptr(theta), ptr(q), n, int(bool(is_logit)), ptr(scores), ptr(ws.sums),
+                                ptr(ws.partials), ptr(ws.counter), stream_ptr()), "adv_lmac_reduce")
+    return scores, ws.sums
+
+
+def td_mask(wave, attribution, want_mask=True):
+    """captum_saliency.py:136-143 per clip: returns (mask, wave*mask, wave*(1-mask))."""
+    wave = _f32_rows(wave if wave.dim() == 2 else wave.unsqueeze(0), "wave")
+    attr = _f32_rows(attribution if attribution.dim() == 2 else attribution.unsqueeze(0), "attribution")
+    wave, attr = wave.contiguous(), attr.contiguous()
+    B, n = wave.shape
+    m = torch.empty_like(wave) if want_mask else None
+    rel, irr = torch.empty_like(wave), torch.empty_like(wave)
+    rowmax = torch.empty(B, dtype=torch.float32, device=wave.device)
+    check(lib().adv_td_mask(ptr(wave), ptr(attr), B, n, ptr(m), ptr(rel), ptr(irr), ptr(rowmax), stream_ptr()),
+          "adv_td_mask")
+    return m, rel, irr
+
+
+def mask_head(y1, weight, bias):
+    """sigmoid(conv1x1(C->1)) on [B,C,H,W] -> [B,1,H,W] (addvisor.py:57-60,82)."""
+    dev = _dev()
+    y1 = y1.to(dev, torch.float32).contiguous()
+    B, Cc, H, W = y1.shape
+    w = weight.to(dev, torch.float32).reshape(-1).contiguous()
+    b = bias.to(dev, torch.float32).reshape(-1).contiguous()
+    if w.numel() != Cc:
+        raise ValueError("mask head weight does not match the channel count")
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+    check(lib().adv_mask_head(ptr(y1), ptr(w), ptr(b), B, Cc, H * W, ptr(out), stream_ptr()), "adv_mask_head")
+    return out
+
+
+def band_swap(spec_real, spec_voc, f_lo, f_hi):
+    """Rows [f_lo, f_hi) of ``spec_voc`` replace those of ``spec_real`` (complex [B,F,T])."""
+    dev = _dev()
+    fm = lambda t: t.to(dev, torch.complex64).transpose(1, 2).contiguous()
+    a, b = fm(spec_real), fm(spec_voc)
+    B, T, Fb = a.shape
+    out = torch.empty_like(a)
+    check(lib().adv_band_swap(ptr(a), ptr(b), B, T, Fb, int(f_lo), int(f_hi), ptr(out), stream_ptr()), "adv_band_swap")
+    return out.transpose(1, 2)
