@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the ADDvisor explanation-evaluation hot path (BASELINE.json metric:
+"explained clips/s (4 s @ 16 kHz) STFT-mask-iSTFT + LMAC metrics").
+
+Workload = BASELINE.json configs[1]: synthetic batch of 64 x 4 s clips @ 16 kHz, n_fft 512, hop 160,
+rectangular win 512, mask on the [257, 401] grid.  One step = one batch through
+
+    explain (STFT -> mask / 1-mask on log1p magnitude -> 2 x iSTFT)  -> normalise x2
+    -> [SSL classifier: the reference's torch module, NOT part of the timed path; its logits are
+        synthetic N(0, 2^2)] -> lmac_reduce (sigmoid + FF/Fid/AD/AI/AG sums)
+
+value : clips/s with inputs resident in HBM (a pool of batches larger than L2 is rotated).
+e2e   : same step through the public API with pinned HOST inputs (H2D inside the timed region) and
+        the six metric sums read back to the host every step.
+roofline : the dominant kernel (fused explain) timed alone with CUDA events on its launch stream.
+cpu_baseline / --impl reference : the oracle port of the reference's torch-CPU path on the host cores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+For N > 1 launch with torch.distributed.run (one rank per GPU); ranks shard the clips, the only
+collective is one all-reduce of the six metric sums at the end of the evaluation.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(sampling_rate=16000, n_fft=512, hop_length=160, win_length=512, audio_length=4)
+BATCH = 64
+N = CFG["sampling_rate"] * CFG["audio_length"]
+T = 1 + N // CFG["hop_length"]
+F = CFG["n_fft"] // 2 + 1
+# algorithmic bytes per clip (SURVEY.md 8d / DESIGN.md): fused explain reads the wave (4N) and the mask
+# (4FT) and writes two waves (2*4N); stft = 4N + 8FT; istft = 8FT + 4N
+BYTES_EXPLAIN = 4 * N + 4 * F * T + 2 * 4 * N
+BYTES_STFT = 4 * N + 8 * F * T
+BYTES_ISTFT = 8 * F * T + 4 * N
+POOL = 16  # rotating input/output sets: 16 x 75.6 MB = 1.2 GB >> 126 MB L2
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the GPU is under load."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_path_step(R, wav, mask, logits):
+    """The reference's CPU path for one batch (oracle port, torch CPU fp32)."""
+    rel, irr = R.explain(wav, mask, mode="log1p", normalize=True, **CFG)
+    pr = torch.sigmoid(logits).unsqueeze(-1)
+    return rel, irr, R.lmac_sums(pr[0], pr[1], pr[2])
+
+
+def synth_host(seed, batch=BATCH):
+    g = torch.Generator().manual_seed(seed)
+    wav = 0.1 * torch.randn(batch, N, generator=g)
+    mask = torch.rand(batch, F, T, generator=g)
+    logits = 2.0 * torch.randn(3, batch, generator=g)
+    return wav, mask, logits
+
+
+def run_reference(args):
+    """--impl reference: the oracle port of the reference CPU path, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_path as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    wav, mask, logits = synth_host(1234)
+    steps, warm = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        cpu_path_step(R, wav, mask, logits)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_path_step(R, wav, mask, logits)
+    dt = (time.perf_counter() - t0) / steps
+    val = BATCH / dt
+    line = {
+        "impl": "reference", "metric": "explained clips/s", "value": val, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 64 x 4 s clips @16 kHz, n_fft 512 hop 160, mask -> iSTFT x2 -> "
+                               "normalise -> LMAC sums on given logits", "batch": BATCH},
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps x {BATCH} clips, torch {torch.__version__} CPU fp32"},
+        "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def time_loop(fn, iters):
+    """CUDA-event time of `iters` calls on the current stream, synchronised on both sides (seconds)."""
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3
+
+
+def main():
+    ap_ = argparse.ArgumentParser()
+    ap_.add_argument("--gpus", type=int, default=1)
+    ap_.add_argument("--steps", type=int, default=2000)
+    ap_.add_argument("--warmup", type=int, default=50)
+    ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap_.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap_.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    pkg = importlib.import_module("xai-audio-deepfakes_b200")
+    pkg._lib.build()
+    ops = pkg.ops
+    from importlib import import_module
+    pipeline = import_module("xai-audio-deepfakes_b200.pipeline")
+    ap = pkg.audioprocessor.AudioProcessor(**CFG)
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+
+    # ---- device-resident pool (each rank owns its shard of clips: weak scaling, B clips per rank-step)
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    pool = [pipeline.ExplainPipeline(ap, BATCH, use_graph=True, accumulate=True) for _ in range(POOL)]
+    for p in pool:
+        p.wav.copy_(0.1 * torch.randn(BATCH, N, generator=gen, device="cuda"))
+        p.mask.copy_(torch.rand(BATCH, F, T, generator=gen, device="cuda"))
+        p.logits.copy_(2.0 * torch.randn(3, BATCH, generator=gen, device="cuda"))
+    def step(i):  # 4 launches of ours (one graph replay); metric sums accumulate inside lmac_reduce
+        pool[i % POOL].step()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # warm-up: at least `warm` steps and at least ~0.7 s of load so the clock sampler sees the GPU busy
+    t_w = time.perf_counter()
+    done = 0
+    while done < warm or time.perf_counter() - t_w < 0.7:
+        step(done)
+        done += 1
+        if done % 256 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    for p in pool:
+        p.sums.zero_()
+        p.launches = 0
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        step(i)
+    total = torch.stack([p.sums for p in pool]).sum(dim=0)
+    if world > 1:  # the one real exchange: six float64 sums, once per evaluation
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    b.record()
+    torch.cuda.synchronize()
+    elapsed = torch.tensor([a.elapsed_time(b) * 1e-3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    elapsed = float(elapsed)
+    launches = sum(p.launches for p in pool)
+    value = world * BATCH * steps / elapsed
+    metrics = pkg.LMAC_metrics.finalize(total)
+
+    # ---- dominant kernel alone (CUDA events on its launch stream), pool rotated the same way
+    peak, peak_src = peaks()
+
+    def graph_time(fn, reps):
+        """avg seconds per launch of fn(i), i rotating over the pool, replayed from one CUDA graph"""
+        fn(0)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(POOL):
+                fn(i)
+        for _ in range(3):
+            g.replay()
+        return time_loop(lambda i: g.replay(), reps) / (reps * POOL)
+
+    kw = dict(n_fft=ap.n_fft, hop=ap.hop_length, win_length=ap.win_length)
+    reps = max(4, min(steps // POOL, 100))
+    t_k = graph_time(lambda i: ops.explain(pool[i].wav, pool[i].mask, length=N,
+                                           out=(pool[i].rel, pool[i].irr, pool[i].stats), **kw), reps)
+    ach = BYTES_EXPLAIN * BATCH / t_k / 1e9
+
+    # ---- API-boundary kernels the north star judges on HBM GB/s: stft (X only / X+mag+phase) and istft
+    specs = [ops.stft(p.wav, want_mag=False, want_phase=False, **kw)[0] for p in pool]
+    t_stft = graph_time(lambda i: ops.stft(pool[i].wav, want_mag=False, want_phase=False, **kw), reps)
+    t_stft3 = graph_time(lambda i: ops.stft(pool[i].wav, **kw), reps)
+    t_istft = graph_time(lambda i: ops.istft(specs[i], length=N, **kw), reps)
+    del specs
+
+    # ---- end to end through the public API with pinned host inputs
+    hp = pipeline.HostFedPipeline(ap, BATCH, use_graph=True)
+    host_sets = []
+    for k in range(4):
+        w, m, l = synth_host(99 + 10 * rank + k)
+        host_sets.append((w.pin_memory(), m.pin_memory(), l.pin_memory()))
+    e2e_steps = max(8, min(steps, 200))
+    for i in range(4):
+        hp.step_host(*host_sets[i % 4])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_e = time_loop(lambda i: hp.step_host(*host_sets[i % 4]), e2e_steps)
+    te = torch.tensor([t_e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * BATCH * e2e_steps / float(te)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (oracle port) on this box's host cores: bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_path as R
+        torch.set_num_threads(os.cpu_count() or 1)
+        w, m, l = synth_host(1234)
+        cpu_path_step(R, w, m, l)
+        reps_c, t0 = 0, time.perf_counter()
+        while reps_c < 3 or (time.perf_counter() - t0 < 10.0 and reps_c < 40):
+            cpu_path_step(R, w, m, l)
+            reps_c += 1
+        dtc = (time.perf_counter() - t0) / reps_c
+        cpu = {"value": BATCH / dtc, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{reps_c} x {BATCH} clips of the same workload, torch {torch.__version__} CPU fp32, "
+                         f"os.cpu_count()={os.cpu_count()}"}
+
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("explain_kernel_bytes_per_launch")
+
+    line = {
+        "metric": "explained clips/s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps,
+        "warmup": done, "ms_per_step": elapsed / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 64 x 4 s clips @16 kHz per GPU-step, n_fft 512 hop 160 win 512, "
+                               "fused STFT -> log1p mask / 1-mask -> 2 x iSTFT -> normalise x2 -> LMAC sums "
+                               "(classifier logits synthetic; SSL model is the reference's torch module, not timed)",
+                   "batch_per_gpu": BATCH, "parallelism": f"dp{world}",
+                   "l2": f"{POOL} rotating buffer sets (1.2 GB) > 126 MB L2", "cuda_graph": True},
+        "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": hp.h2d_bytes,
+                "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "explain_kernel<512,log1p> (fused STFT+mask+2xiSTFT)",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                     "peak_source": peak_src, "bytes_per_launch": BYTES_EXPLAIN * BATCH, "us_per_launch": t_k * 1e6},
+        "kernels": {
+            "stft_X": {"GBps": BYTES_STFT * BATCH / t_stft / 1e9, "frac": BYTES_STFT * BATCH / t_stft / 1e9 / peak,
+                       "us": t_stft * 1e6},
+            "stft_X_mag_phase": {"GBps": (BYTES_STFT + 8 * F * T) * BATCH / t_stft3 / 1e9,
+                                 "frac": (BYTES_STFT + 8 * F * T) * BATCH / t_stft3 / 1e9 / peak, "us": t_stft3 * 1e6},
+            "istft": {"GBps": BYTES_ISTFT * BATCH / t_istft / 1e9, "frac": BYTES_ISTFT * BATCH / t_istft / 1e9 / peak,
+                      "us": t_istft * 1e6},
+        },
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "lmac_means": metrics,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -103,12 +103,14 @@ int adv_normalize(const float* in, float* out, int batch, int n, const double* s
 
 /* ---- LMAC metrics (LMAC_metrics.py:31-73,160-172; sigmoid of classifier_embedder.py:36) ---------------
  * p / theta / q: dev float [n] classifier outputs for the clean, masked-in and masked-out clips;
- * is_logit != 0 applies the logistic sigmoid first.  scores (nullable): dev float [n][7] =
+ * flags: ADV_LMAC_LOGITS applies the logistic sigmoid first; ADV_LMAC_ACCUMULATE adds into `sums`
+ * instead of overwriting it (running totals over the batches of one evaluation).  scores (nullable): dev float [n][7] =
  * (faithfulness, fidelity, AD, AI, AG, pc, oc) per sample, pc / oc = get_score_for_predicted_class of p / theta.  sums: dev double [6] = the five sums and the count
  * (the vector the multi-GPU driver all-reduces).  block_partials: dev double scratch
  * [adv_lmac_blocks(n)][5]. */
+enum { ADV_LMAC_LOGITS = 1, ADV_LMAC_ACCUMULATE = 2 };
 int adv_lmac_blocks(int n);
-int adv_lmac_reduce(const float* p, const float* theta, const float* q, int n, int is_logit,
+int adv_lmac_reduce(const float* p, const float* theta, const float* q, int n, int flags,
                     float* scores, double* sums, double* block_partials, unsigned int* counter, void* stream);
 
 /* ---- gradient-saliency time-domain mask (captum_saliency.py:136-143) ----------------------------------

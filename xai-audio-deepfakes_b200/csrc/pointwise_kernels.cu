@@ -85,8 +85,9 @@ __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + e
 
 __global__ void __launch_bounds__(kPwThreads)
 lmac_kernel(const float* __restrict__ p_in, const float* __restrict__ th_in, const float* __restrict__ q_in, int n,
-            int is_logit, float* __restrict__ scores, double* __restrict__ sums, double* __restrict__ partials,
+            int flags, float* __restrict__ scores, double* __restrict__ sums, double* __restrict__ partials,
             unsigned int* __restrict__ counter) {
+    const bool is_logit = flags & ADV_LMAC_LOGITS, accumulate = flags & ADV_LMAC_ACCUMULATE;
     __shared__ double red[5][kPwThreads / 32];
     __shared__ bool last;
     double acc[5] = {0, 0, 0, 0, 0};
@@ -134,9 +135,9 @@ lmac_kernel(const float* __restrict__ p_in, const float* __restrict__ th_in, con
         if (threadIdx.x < 5) {
             double s = 0.0;
             for (unsigned int k = 0; k < gridDim.x; ++k) s += partials[(size_t)k * 5 + threadIdx.x];
-            sums[threadIdx.x] = s;
+            sums[threadIdx.x] = (accumulate ? sums[threadIdx.x] : 0.0) + s;
         }
-        if (threadIdx.x == 5) sums[5] = (double)n;
+        if (threadIdx.x == 5) sums[5] = (accumulate ? sums[5] : 0.0) + (double)n;
         if (threadIdx.x == 0) *counter = 0u;  // re-arm for the next launch
     }
 }
@@ -298,10 +299,10 @@ int adv_normalize(const float* in, float* out, int batch, int n, const double* s
 
 int adv_lmac_blocks(int n) { return n <= 0 ? 0 : (n + kLmacPerBlock - 1) / kLmacPerBlock; }
 
-int adv_lmac_reduce(const float* p, const float* theta, const float* q, int n, int is_logit, float* scores,
+int adv_lmac_reduce(const float* p, const float* theta, const float* q, int n, int flags, float* scores,
                     double* sums, double* block_partials, unsigned int* counter, void* stream) {
     if (!p || !theta || !q || !sums || !block_partials || !counter || n <= 0) return ADV_ERR_INVALID;
-    lmac_kernel<<<adv_lmac_blocks(n), kPwThreads, 0, (cudaStream_t)stream>>>(p, theta, q, n, is_logit, scores, sums,
+    lmac_kernel<<<adv_lmac_blocks(n), kPwThreads, 0, (cudaStream_t)stream>>>(p, theta, q, n, flags, scores, sums,
                                                                             block_partials, counter);
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;

@@ -15,6 +15,8 @@
 // Overlap-add is output-stationary: a CTA owns a span of output samples, recomputes the few halo
 // frames that overlap it, and adds frames into a shared-memory accumulator in `phases` rounds
 // (frames t, t+phases, ... never overlap) - no global or shared atomics, deterministic order.
+#include <mutex>
+#include <unordered_map>
 #include "adv_internal.cuh"
 #include "fft_core.cuh"
 
@@ -474,10 +476,19 @@ explain_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t wav_
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
+// cudaFuncSetAttribute once per (kernel, size high-water mark): keeps the launch path free of
+// attribute calls in steady state (and inside CUDA-graph capture)
 template <class K>
 static int set_smem(K kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, size_t> high;
     if (bytes > 227 * 1024) return ADV_ERR_UNSUPPORTED;
-    ADV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = high[reinterpret_cast<const void*>(kernel)];
+    if (bytes > cur) {
+        ADV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
     return ADV_OK;
 }
 

@@ -99,8 +99,10 @@ def normalize_(x, stats=None, width=2, col=0, out=None):
     return out
 
 
-def explain(wave, mask, n_fft, hop, win_length, length=None, mode="log1p", window=None, normalize=False):
-    """Fused wave + mask -> (masked-in wave, masked-out wave) [B, length] (LMAC_metrics.py:136-157)."""
+def explain(wave, mask, n_fft, hop, win_length, length=None, mode="log1p", window=None, normalize=False,
+            out=None):
+    """Fused wave + mask -> (masked-in wave, masked-out wave) [B, length] (LMAC_metrics.py:136-157).
+    ``out=(rel, irr, stats)`` reuses caller-owned buffers (stats: float64 [B, tiles, 4])."""
     wave = _f32_rows(wave, "waveform")
     mask = _mask3(mask)
     B, n = wave.shape
@@ -109,15 +111,25 @@ def explain(wave, mask, n_fft, hop, win_length, length=None, mode="log1p", windo
     T = 1 + n // hop
     n_out = int(length) if length is not None else hop * (T - 1)
     plan = get_plan(n_fft, hop, win_length, window, T, n, n_out)
-    rel = torch.empty((B, n_out), dtype=torch.float32, device=wave.device)
-    irr = torch.empty_like(rel)
-    stats = torch.empty((B, plan.tiles(B), 4), dtype=torch.float64, device=wave.device) if normalize else None
+    if out is not None:
+        rel, irr, stats = out
+    else:
+        rel = torch.empty((B, n_out), dtype=torch.float32, device=wave.device)
+        irr = torch.empty_like(rel)
+        stats = torch.empty((B, plan.tiles(B), 4), dtype=torch.float64, device=wave.device) if normalize else None
     check(lib().adv_explain(plan.handle, ptr(wave), wave.stride(0), ptr(mask), mask.shape[1], mask.shape[2],
                             MODES[mode], B, ptr(rel), ptr(irr), ptr(stats), stream_ptr()), "adv_explain")
     if normalize:
         normalize_(rel, stats, 4, 0, out=rel)
         normalize_(irr, stats, 4, 2, out=irr)
     return rel, irr
+
+
+def explain_tiles(n_fft, hop, win_length, n, batch, length=None, window=None):
+    """Tiles per clip the explain kernel will use (second dim of its ``stats`` buffer)."""
+    T = 1 + n // hop
+    n_out = int(length) if length is not None else hop * (T - 1)
+    return get_plan(n_fft, hop, win_length, window, T, n, n_out).tiles(batch)
 
 
 def explain_spec(spec, mask, n_fft, hop, win_length, length=None, mode="log1p", window=None, normalize=False):
@@ -163,10 +175,10 @@ class LmacWorkspace:
         self.n = n
         self.partials = torch.empty((blocks, 5), dtype=torch.float64, device=device)
         self.counter = torch.zeros(1, dtype=torch.int32, device=device)
-        self.sums = torch.empty(6, dtype=torch.float64, device=device)
+        self.sums = torch.zeros(6, dtype=torch.float64, device=device)
 
 
-def lmac(p, theta, q, is_logit=False, want_scores=True, workspace=None):
+def lmac(p, theta, q, is_logit=False, want_scores=True, workspace=None, accumulate=False):
     """Three [N] or [N,1] tensors -> (scores [N,7] or None, sums float64 [6]) on the device.
     Score columns: faithfulness, fidelity, AD, AI, AG, pc, oc; sums = the first five summed, then N."""
     dev = _dev()
@@ -177,7 +189,8 @@ def lmac(p, theta, q, is_logit=False, want_scores=True, workspace=None):
         raise ValueError("prediction tensors differ in length")
     ws = workspace if workspace is not None and workspace.n == n else LmacWorkspace(n, dev)
     scores = torch.empty((n, 7), dtype=torch.float32, device=dev) if want_scores else None
-    check(lib().adv_lmac_reduce(ptr(p), ptr(theta), ptr(q), n, int(bool(is_logit)), ptr(scores), ptr(ws.sums),
+    flags = (1 if is_logit else 0) | (2 if accumulate else 0)
+    check(lib().adv_lmac_reduce(ptr(p), ptr(theta), ptr(q), n, flags, ptr(scores), ptr(ws.sums),
                                 ptr(ws.partials), ptr(ws.counter), stream_ptr()), "adv_lmac_reduce")
     return scores, ws.sums
 

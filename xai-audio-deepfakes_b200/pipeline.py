@@ -1,0 +1,113 @@
+"""Steady-state evaluation pipeline: the per-batch GPU work of run_addvisor_metrics that we own,
+on preallocated buffers and (optionally) replayed as one CUDA graph.
+
+    wave [B,n] + mask [B,F,T] --explain--> rel, irr --normalise x2--> (SSL classifier, not ours)
+    logits p / theta / q [B] --lmac_reduce--> six float64 sums
+
+Launches per step: explain, normalize, normalize, lmac = 4 kernels, no allocation, no host sync.
+``step_host`` is the end-to-end entry: inputs arrive in pinned host memory, are copied to the device
+on a side stream (double-buffered against the previous step's compute), and the six sums come back
+to pinned host memory.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import check, lib, ptr, stream_ptr
+
+KERNELS_PER_STEP = 4
+
+
+class ExplainPipeline:
+    def __init__(self, audio_processor, batch, mode="log1p", use_graph=True, device=None, accumulate=False):
+        ap = audio_processor
+        self.accumulate = accumulate  # metric sums become running totals over the steps
+        self.ap, self.batch, self.mode = ap, batch, mode
+        self.dev = device or ops._dev()
+        self.n = int(ap.audio_length * ap.sampling_rate)
+        self.T, self.F = 1 + self.n // ap.hop_length, ap.n_fft // 2 + 1
+        tiles = ops.explain_tiles(ap.n_fft, ap.hop_length, ap.win_length, self.n, batch, length=self.n)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.wav = torch.zeros((batch, self.n), **f32)
+        self.mask = torch.zeros((batch, self.F, self.T), **f32)
+        self.logits = torch.zeros((3, batch), **f32)
+        self.rel = torch.empty((batch, self.n), **f32)
+        self.irr = torch.empty((batch, self.n), **f32)
+        self.stats = torch.empty((batch, tiles, 4), dtype=torch.float64, device=self.dev)
+        self.ws = ops.LmacWorkspace(batch, self.dev)
+        self.sums = self.ws.sums
+        self.graph = None
+        self.launches = 0
+        if use_graph:
+            self._capture()
+
+    # the four launches of one step, on the current stream
+    def _enqueue(self):
+        ap = self.ap
+        ops.explain(self.wav, self.mask, ap.n_fft, ap.hop_length, ap.win_length, length=self.n, mode=self.mode,
+                    normalize=True, out=(self.rel, self.irr, self.stats))
+        ops.lmac(self.logits[0], self.logits[1], self.logits[2], is_logit=True, want_scores=False,
+                 workspace=self.ws, accumulate=self.accumulate)
+
+    def _capture(self):
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm up outside capture (plans, function attributes)
+                self._enqueue()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+        self.sums.zero_()
+
+    def step(self):
+        """Run one batch on whatever is in self.wav / self.mask / self.logits; results in
+        self.rel / self.irr (normalised) and self.sums.  Asynchronous."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        self.launches += KERNELS_PER_STEP
+        return self.sums
+
+
+class HostFedPipeline:
+    """End-to-end stepping with host-resident inputs: two ExplainPipelines alternate so that the
+    H2D copy of step i+1 (copy stream) overlaps the kernels of step i (compute stream)."""
+
+    def __init__(self, audio_processor, batch, mode="log1p", use_graph=True):
+        self.pipes = [ExplainPipeline(audio_processor, batch, mode, use_graph) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream()
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.host_sums = [torch.empty(6, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.i = 0
+        p = self.pipes[0]
+        self.h2d_bytes = 4 * (p.wav.numel() + p.mask.numel() + p.logits.numel())
+        self.d2h_bytes = 8 * 6
+        for e in self.done:
+            e.record()
+
+    def step_host(self, wav_pinned, mask_pinned, logits_pinned):
+        k = self.i & 1
+        p = self.pipes[k]
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.done[k])      # buffers of slot k are free again
+            p.wav.copy_(wav_pinned, non_blocking=True)
+            p.mask.copy_(mask_pinned, non_blocking=True)
+            p.logits.copy_(logits_pinned, non_blocking=True)
+            self.copied[k].record()
+        main.wait_event(self.copied[k])
+        p.step()
+        self.host_sums[k].copy_(p.sums, non_blocking=True)
+        self.done[k].record(main)
+        self.i += 1
+        return self.host_sums[k]
+
+    @property
+    def launches(self):
+        return sum(p.launches for p in self.pipes)
