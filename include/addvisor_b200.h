@@ -100,6 +100,8 @@ int adv_row_stats_parts(int n);
 int adv_row_stats(const float* in, int batch, int n, double* stats, void* stream);
 int adv_normalize(const float* in, float* out, int batch, int n, const double* stats, int parts, int width,
                   int col, void* stream);
+/* both outputs of adv_explain normalised in place by one launch; stats = its [B][parts][4] array */
+int adv_normalize_pair(float* rel, float* irr, int batch, int n, const double* stats, int parts, void* stream);
 
 /* ---- LMAC metrics (LMAC_metrics.py:31-73,160-172; sigmoid of classifier_embedder.py:36) ---------------
  * p / theta / q: dev float [n] classifier outputs for the clean, masked-in and masked-out clips;

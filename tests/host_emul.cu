@@ -13,6 +13,10 @@
 
 using namespace adv;
 typedef std::complex<double> cd;
+struct Tw {
+    const float2* t;
+    __host__ __device__ float2 operator()(int k) const { return t[k]; }
+};
 
 template <int NF>
 int run() {
@@ -44,14 +48,15 @@ int run() {
             tw[l][k1] = make_float2((float)cos(a), (float)sin(a));
         }
     std::vector<std::vector<float2>> V(L, std::vector<float2>(32));
-    std::vector<float2> scratch(G::SCRATCH);
+    std::vector<float> scratch(G::SCRATCH);
     for (int l = 0; l < L; ++l)
         for (int n1 = 0; n1 < 32; ++n1) V[l][n1] = make_float2(xa[n1 * G::R2 + l], xb[n1 * G::R2 + l]);
-    for (int l = 0; l < L; ++l) {
-        const float2* t = tw[l].data();
-        fwd_phase_a<NF>(V[l].data(), l, [t](int k) { return t[k]; }, scratch.data());
+    for (int l = 0; l < L; ++l) fwd_cols<NF>(V[l].data(), Tw{tw[l].data()});
+    for (int im = 0; im < 2; ++im) {
+        for (int l = 0; l < L; ++l) scr_store_cols<NF>(V[l].data(), l, scratch.data(), im);
+        for (int l = 0; l < L; ++l) scr_load_rows<NF>(V[l].data(), l, scratch.data(), im);
     }
-    for (int l = 0; l < L; ++l) fwd_phase_b<NF>(V[l].data(), l, scratch.data());
+    for (int l = 0; l < L; ++l) fwd_rows<NF>(V[l].data());
 
     // split
     std::vector<std::vector<float2>> XA(L, std::vector<float2>(17)), XB(L, std::vector<float2>(17));
@@ -94,11 +99,12 @@ int run() {
         for (int l = 0; l < L; ++l) merge1024_pre(V[l].data(), l, XA[l].data(), XB[l].data(), send[l].data());
         for (int l = 0; l < L; ++l) merge1024_post(V[l].data(), l, send[(32 - l) & 31].data());
     }
-    for (int l = 0; l < L; ++l) inv_phase_a<NF>(V[l].data(), l, scratch.data());
-    for (int l = 0; l < L; ++l) {
-        const float2* t = tw[l].data();
-        inv_phase_b<NF>(V[l].data(), l, [t](int k) { return t[k]; }, scratch.data());
+    for (int l = 0; l < L; ++l) inv_rows<NF>(V[l].data());
+    for (int im = 0; im < 2; ++im) {
+        for (int l = 0; l < L; ++l) scr_store_rows<NF>(V[l].data(), l, scratch.data(), im);
+        for (int l = 0; l < L; ++l) scr_load_cols<NF>(V[l].data(), l, scratch.data(), im);
     }
+    for (int l = 0; l < L; ++l) inv_cols<NF>(V[l].data(), Tw{tw[l].data()});
     double ierr = 0;
     for (int l = 0; l < L; ++l)
         for (int n1 = 0; n1 < 32; ++n1) {

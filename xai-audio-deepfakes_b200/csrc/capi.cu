@@ -39,26 +39,14 @@ static int tile_frame_span(const PlanDev& d, int k) {
 }
 
 Tiling choose_tiling(const adv_plan* p, int batch) {
-    // total hops to cover, smallest tile count that fits the CTA's frame capacity, then trade a few
-    // more (smaller) tiles against wave quantisation on 148 SMs
+    // Every tile costs one CTA pass (each unit transforms its two frames whatever the tile length), so
+    // the cheapest tiling is the fewest tiles that fit the CTA's frame capacity, evenly sized.
+    (void)batch;
     const PlanDev& d = p->d;
     const int total_hops = (d.n_out + d.hop - 1) / d.hop;
     const int n_min = (total_hops + p->max_hops - 1) / p->max_hops;
-    const int halo = p->frames_per_tile - p->max_hops;
-    Tiling best{p->max_hops, n_min};
-    double best_cost = 1e300;
-    for (int n = n_min; n <= n_min + 8 && n <= total_hops; ++n) {
-        const int k = (total_hops + n - 1) / n;
-        const int tiles = (total_hops + k - 1) / k;
-        const long ctas = (long)tiles * (batch > 0 ? batch : 1);
-        const double waves = ceil((double)ctas / 148.0);
-        const double cost = waves * (double)(k + halo);
-        if (cost < best_cost - 1e-9) {
-            best_cost = cost;
-            best = Tiling{k, tiles};
-        }
-    }
-    return best;
+    const int k = (total_hops + n_min - 1) / n_min;
+    return Tiling{k, (total_hops + k - 1) / k};
 }
 
 }  // namespace adv
@@ -161,15 +149,6 @@ int adv_plan_create(adv_plan** out, int n_fft, int hop, int win_length, const fl
             p->max_hops = k;
             break;
         }
-    {   // the fused explain kernel is the largest shared-memory user: keep its tile inside 227 KB
-        // (mirrors ExplainSmem<NF>::bytes in transform_kernels.cu)
-        const int units = kThreads / lanes, ft = 2 * units, pitch = lanes + 1, bins = n_fft / 2 + 1;
-        const size_t fixed = sizeof(float2) * (size_t)(32 * lanes + units * 32 * pitch) + sizeof(double) * 4 * (kThreads / 32) +
-                             sizeof(float) * (size_t)(n_fft + bins * (ft + 1)) + sizeof(float) * (size_t)((ft - 1) * hop + n_fft);
-        const size_t limit = 227 * 1024;
-        while (p->max_hops > 0 && fixed + sizeof(float2) * (size_t)p->max_hops * hop > limit) --p->max_hops;
-        if (n_out == 0) p->max_hops = 1;
-    }
     if (p->max_hops == 0) {  // hop so small that even a one-hop tile needs more frames than a CTA holds
         adv_plan_destroy(p);
         return ADV_ERR_UNSUPPORTED;

@@ -136,7 +136,8 @@ struct Geo {
     static constexpr int LANES = R2;        // lanes cooperating on one FFT
     static constexpr int ROWS = 32 / LANES; // rows (k1) owned per lane after the transpose
     static constexpr int PITCH = R2 + 1;    // scratch row pitch in float2 (odd: conflict-free)
-    static constexpr int SCRATCH = 32 * PITCH;  // float2 per unit
+    // floats per unit; +16 when two units share a warp so that their bank sets interleave
+    static constexpr int SCRATCH = 32 * PITCH + (LANES == 16 ? 16 : 0);
     static constexpr int NBINS = NF / 2 + 1;
     static constexpr int BINS_PER_LANE = 17;  // 16 (+ Nyquist on lane 0)
 };
@@ -161,57 +162,111 @@ ADV_HD int bin_of(int l, int i) {
     }
 }
 
-// ---- forward: time samples -> spectrum ------------------------------------------------------
-// in : v[n1] = z[n1*R2 + l]          (n1 = 0..31)
-// out: v[r*R2 + k2] = Z[row_of(l,r) + 32*k2]
-// tw : per-lane twiddles tw[k1] = exp(-2*pi*i * l*k1 / NF), read through a functor so the caller
-//      decides where they live (registers, shared memory)
-template <int NF, class TwFn>
-ADV_HD void fwd_phase_a(float2* v, int l, TwFn tw, float2* scratch) {
+// ---- transposes through shared memory, real and imaginary planes one after the other ------------
+// (halves the scratch footprint: 32 x PITCH floats per unit).  Every step is followed by a unit-wide
+// sync (the caller's __syncwarp); the host emulation runs each step over all lanes in turn.
+template <int NF>
+ADV_HD void scr_store_cols(const float2* v, int l, float* scr, bool imag) {
     using G = Geo<NF>;
-    fft_inplace<32, -1>(v);
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) {
-        const float2 w = k1 == 0 ? v[0] : cmul(v[k1], tw(k1));
-        scratch[k1 * G::PITCH + l] = w;
-    }
+    for (int k1 = 0; k1 < 32; ++k1) scr[k1 * G::PITCH + l] = imag ? v[k1].y : v[k1].x;
 }
 template <int NF>
-ADV_HD void fwd_phase_b(float2* v, int l, const float2* scratch) {
+ADV_HD void scr_load_rows(float2* v, int l, const float* scr, bool imag) {
     using G = Geo<NF>;
 #pragma unroll
     for (int r = 0; r < G::ROWS; ++r) {
         const int row = row_of<NF>(l, r);
 #pragma unroll
-        for (int i = 0; i < G::R2; ++i) v[r * G::R2 + i] = scratch[row * G::PITCH + i];
-        fft_inplace<G::R2, -1>(v + r * G::R2);
+        for (int i = 0; i < G::R2; ++i) {
+            const float x = scr[row * G::PITCH + i];
+            if (imag) v[r * G::R2 + i].y = x; else v[r * G::R2 + i].x = x;
+        }
+    }
+}
+template <int NF>
+ADV_HD void scr_store_rows(const float2* v, int l, float* scr, bool imag) {
+    using G = Geo<NF>;
+#pragma unroll
+    for (int r = 0; r < G::ROWS; ++r) {
+        const int row = row_of<NF>(l, r);
+#pragma unroll
+        for (int i = 0; i < G::R2; ++i) scr[row * G::PITCH + i] = imag ? v[r * G::R2 + i].y : v[r * G::R2 + i].x;
+    }
+}
+template <int NF>
+ADV_HD void scr_load_cols(float2* v, int l, const float* scr, bool imag) {
+    using G = Geo<NF>;
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+        const float x = scr[k1 * G::PITCH + l];
+        if (imag) v[k1].y = x; else v[k1].x = x;
     }
 }
 
+// ---- forward: time samples -> spectrum ------------------------------------------------------
+// in : v[n1] = z[n1*R2 + l]          (n1 = 0..31)
+// out: v[r*R2 + k2] = Z[row_of(l,r) + 32*k2]
+// tw : per-lane twiddles tw(k1) = exp(-2*pi*i * l*k1 / NF), read through a functor so the caller
+//      decides where they live (registers, shared memory)
+template <int NF, class TwFn>
+ADV_HD void fwd_cols(float2* v, TwFn tw) {  // radix-32 over n1 + twiddle
+    fft_inplace<32, -1>(v);
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) v[k1] = cmul(v[k1], tw(k1));
+}
+template <int NF>
+ADV_HD void fwd_rows(float2* v) {  // radix-R2 over n2 for each owned row
+    using G = Geo<NF>;
+#pragma unroll
+    for (int r = 0; r < G::ROWS; ++r) fft_inplace<G::R2, -1>(v + r * G::R2);
+}
 // ---- inverse: spectrum -> time samples (unnormalised) ---------------------------------------
 // in : v[r*R2 + k2] = Z[row_of(l,r) + 32*k2]
 // out: v[n1] = NF * z[n1*R2 + l]
 template <int NF>
-ADV_HD void inv_phase_a(float2* v, int l, float2* scratch) {
+ADV_HD void inv_rows(float2* v) {
     using G = Geo<NF>;
 #pragma unroll
-    for (int r = 0; r < G::ROWS; ++r) {
-        const int row = row_of<NF>(l, r);
-        fft_inplace<G::R2, +1>(v + r * G::R2);
-#pragma unroll
-        for (int i = 0; i < G::R2; ++i) scratch[row * G::PITCH + i] = v[r * G::R2 + i];
-    }
+    for (int r = 0; r < G::ROWS; ++r) fft_inplace<G::R2, +1>(v + r * G::R2);
 }
 template <int NF, class TwFn>
-ADV_HD void inv_phase_b(float2* v, int l, TwFn tw, const float2* scratch) {
-    using G = Geo<NF>;
+ADV_HD void inv_cols(float2* v, TwFn tw) {
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) {
-        const float2 w = scratch[k1 * G::PITCH + l];
-        v[k1] = k1 == 0 ? w : cmulc(w, tw(k1));
-    }
+    for (int k1 = 1; k1 < 32; ++k1) v[k1] = cmulc(v[k1], tw(k1));
     fft_inplace<32, +1>(v);
 }
+
+#ifdef __CUDACC__
+// Device-side composition; `scr` is the unit's private scratch.  Both functions begin with a
+// __syncwarp so that a previous transpose through the same scratch has been fully read.
+template <int NF, class TwFn>
+__device__ __forceinline__ void unit_fft_forward(float2* v, int l, TwFn tw, float* scr) {
+    fwd_cols<NF>(v, tw);
+    __syncwarp();
+    scr_store_cols<NF>(v, l, scr, false);
+    __syncwarp();
+    scr_load_rows<NF>(v, l, scr, false);
+    __syncwarp();
+    scr_store_cols<NF>(v, l, scr, true);
+    __syncwarp();
+    scr_load_rows<NF>(v, l, scr, true);
+    fwd_rows<NF>(v);
+}
+template <int NF, class TwFn>
+__device__ __forceinline__ void unit_fft_inverse(float2* v, int l, TwFn tw, float* scr) {
+    inv_rows<NF>(v);
+    __syncwarp();
+    scr_store_rows<NF>(v, l, scr, false);
+    __syncwarp();
+    scr_load_cols<NF>(v, l, scr, false);
+    __syncwarp();
+    scr_store_rows<NF>(v, l, scr, true);
+    __syncwarp();
+    scr_load_cols<NF>(v, l, scr, true);
+    inv_cols<NF>(v, tw);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Two real frames in one complex FFT: split (after forward) and merge (before inverse).

@@ -52,30 +52,61 @@ row_stats_kernel(const float* __restrict__ in, int n, int parts, double* __restr
 }
 
 // ---- (x - mean) / (std_unbiased + 1e-7) -----------------------------------------------------------
+// blockIdx.z selects one of up to two arrays that share a stats buffer (the explain kernel's rel / irr
+// outputs: (sum, sumsq) pairs at columns col and col + 2), so both normalisers are one launch.
 __global__ void __launch_bounds__(kPwThreads)
-normalize_kernel(const float* __restrict__ in, float* __restrict__ out, int n, const double* __restrict__ stats,
-                 int parts, int width, int col) {
-    __shared__ float s_mean, s_inv;
-    const int b = blockIdx.y;
-    if (threadIdx.x == 0) {
+normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const float* __restrict__ in1,
+                 float* __restrict__ out1, int n, const double* __restrict__ stats, int parts, int width, int col) {
+    __shared__ float s_mean, s_den;
+    const int b = blockIdx.y, z = blockIdx.z;
+    const float* in = z ? in1 : in0;
+    float* out = z ? out1 : out0;
+    if (threadIdx.x < 32) {  // warp 0 folds the per-tile partials in a fixed order (lane-strided + butterfly)
         double s = 0.0, ss = 0.0;
-        const double* st = stats + (size_t)b * parts * width + col;
-        for (int k = 0; k < parts; ++k) {  // fixed order: same value in every block of the row
+        const double* st = stats + (size_t)b * parts * width + col + 2 * z;
+        for (int k = threadIdx.x; k < parts; k += 32) {
             s += st[(size_t)k * width];
             ss += st[(size_t)k * width + 1];
         }
-        const double mean = s / (double)n;
-        double var = (ss - s * mean) / (double)(n - 1);  // unbiased (torch.std default)
-        if (var < 0.0) var = 0.0;
-        s_mean = (float)mean;
-        s_inv = (float)sqrt(var) + 1e-7f;
+        s = warp_sum_d(s);
+        ss = warp_sum_d(ss);
+        if (threadIdx.x == 0) {
+            const double mean = s / (double)n;
+            double var = (ss - s * mean) / (double)(n - 1);  // unbiased (torch.std default)
+            if (var < 0.0) var = 0.0;
+            s_mean = (float)mean;
+            s_den = (float)sqrt(var) + 1e-7f;
+        }
     }
     __syncthreads();
-    const float mean = s_mean, den = s_inv;
+    const float mean = s_mean, den = s_den;
     const float* row = in + (size_t)b * n;
     float* orow = out + (size_t)b * n;
     const int lo = blockIdx.x * kRowChunk, hi = min(n, lo + kRowChunk);
-    for (int i = lo + threadIdx.x; i < hi; i += kPwThreads) orow[i] = (__ldg(row + i) - mean) / den;
+    const bool vec = ((n & 3) == 0) && (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    if (vec) {
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        float4* o4 = reinterpret_cast<float4*>(orow);
+        constexpr int U = 4;
+        for (int i = lo / 4 + threadIdx.x; i < hi / 4; i += kPwThreads * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * kPwThreads < hi / 4) v[u] = __ldg(r4 + i + u * kPwThreads);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * kPwThreads < hi / 4) {
+                    float4 y;
+                    y.x = (v[u].x - mean) / den;
+                    y.y = (v[u].y - mean) / den;
+                    y.z = (v[u].z - mean) / den;
+                    y.w = (v[u].w - mean) / den;
+                    o4[i + u * kPwThreads] = y;
+                }
+        }
+    } else {
+        for (int i = lo + threadIdx.x; i < hi; i += kPwThreads) orow[i] = (__ldg(row + i) - mean) / den;
+    }
 }
 
 // ---- LMAC scores + deterministic two-level sum -----------------------------------------------------
@@ -292,7 +323,17 @@ int adv_normalize(const float* in, float* out, int batch, int n, const double* s
     if (!in || !out || !stats || batch <= 0 || n <= 1 || parts <= 0 || width < 2 || col < 0 || col + 2 > width)
         return ADV_ERR_INVALID;
     const int chunks = (n + kRowChunk - 1) / kRowChunk;
-    normalize_kernel<<<dim3(chunks, batch), kPwThreads, 0, (cudaStream_t)stream>>>(in, out, n, stats, parts, width, col);
+    normalize_kernel<<<dim3(chunks, batch, 1), kPwThreads, 0, (cudaStream_t)stream>>>(in, out, in, out, n, stats, parts,
+                                                                                     width, col);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int adv_normalize_pair(float* rel, float* irr, int batch, int n, const double* stats, int parts, void* stream) {
+    if (!rel || !irr || !stats || batch <= 0 || n <= 1 || parts <= 0) return ADV_ERR_INVALID;
+    const int chunks = (n + kRowChunk - 1) / kRowChunk;
+    normalize_kernel<<<dim3(chunks, batch, 2), kPwThreads, 0, (cudaStream_t)stream>>>(rel, rel, irr, irr, n, stats, parts, 4,
+                                                                                     0);
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }

@@ -10,11 +10,16 @@
 // torch.stft itself produces); masks [B][Fm][Tm] fp32 as the mask network emits them.
 //
 // CTA = 256 threads = 16 units (n_fft 512) or 8 units (n_fft 1024); a unit is the lane group that
-// cooperates on one complex FFT (fft_core.cuh).  Two real frames ride in one complex FFT; in the
-// explain kernel the masked-in and masked-out spectra of ONE frame ride in one inverse FFT.
-// Overlap-add is output-stationary: a CTA owns a span of output samples, recomputes the few halo
-// frames that overlap it, and adds frames into a shared-memory accumulator in `phases` rounds
-// (frames t, t+phases, ... never overlap) - no global or shared atomics, deterministic order.
+// cooperates on one complex FFT (fft_core.cuh) and owns TWO ADJACENT frames (2u, 2u+1) of the tile:
+//   * forward: both real frames ride in one complex FFT (split afterwards, register-local);
+//   * inverse (istft): both Hermitian spectra ride in one complex inverse FFT;
+//   * inverse (explain): the masked-in and masked-out spectra of ONE frame ride in one inverse FFT.
+// The waveform segment of a tile is staged by one bulk-async copy (cp.async.bulk, the 1-D TMA path)
+// completing on an mbarrier; tiles that touch the reflect-padded clip edges fall back to plain loads.
+// Overlap-add is output-stationary and barrier-free: every unit accumulates its two frames into a
+// PRIVATE shared-memory strip (hop + window-support samples); after one CTA barrier each output
+// sample gathers the <= ceil(strip / 2hop)+1 strips that cover it, in a fixed order, multiplies by the
+// precomputed reciprocal window envelope and is stored coalesced.  No atomics anywhere.
 #include <mutex>
 #include <unordered_map>
 #include "adv_internal.cuh"
@@ -68,16 +73,64 @@ __device__ __forceinline__ void merge_regs(float2* v, int l, const float2* ya, c
     }
 }
 
-// Stage `seglen` waveform samples starting at original index `base` (may be negative / past the end:
-// torch.stft's centre=True reflect padding) into shared memory.
-__device__ __forceinline__ void load_segment(float* seg, int seglen, const float* __restrict__ row, int base,
-                                             int n_in) {
+// ---- mbarrier + bulk-async copy (TMA 1-D) -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// Stage `seglen` waveform samples starting at original index `base` into shared memory and return the
+// offset (0..3 floats) at which the data starts inside `seg`.  Interior tiles: thread 0 issues ONE bulk
+// copy that lands asynchronously (complete on `bar`, phase 0); the caller overlaps its other loads and
+// then calls stage_wait().  Tiles that touch the clip edges (torch.stft's centre=True reflect padding)
+// or an unaligned row use plain loads.  `bulk` is CTA-uniform.
+__device__ __forceinline__ int stage_segment(float* seg, int seglen, const float* __restrict__ row, int base,
+                                             int n_in, uint64_t* bar, bool& bulk) {
+    const int a0 = base & ~3;
+    const int shift = base - a0;
+    const uint32_t bytes = (uint32_t)(((seglen + shift) * 4 + 15) & ~15);
+    bulk = base >= 0 && (a0 + (int)(bytes / 4)) <= n_in && ((reinterpret_cast<uintptr_t>(row + a0) & 15) == 0);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(seg, row + a0, bytes, bar);
+        }
+        return shift;
+    }
     for (int i = threadIdx.x; i < seglen; i += kThreads) {
         int idx = base + i;
         if (idx < 0) idx = -idx;
         else if (idx >= n_in) idx = 2 * (n_in - 1) - idx;
         seg[i] = (idx >= 0 && idx < n_in) ? __ldg(row + idx) : 0.0f;
     }
+    return 0;
+}
+// after a __syncthreads() (makes the barrier init / the plain stores visible)
+__device__ __forceinline__ void stage_wait(uint64_t* bar, bool bulk) {
+    if (bulk) mbar_wait(bar, 0);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -105,56 +158,94 @@ __device__ __forceinline__ void block_sum(double (&q)[NQ], double* red) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// STFT
-// ------------------------------------------------------------------------------------------------
+// shared-memory carving (all offsets 16-byte aligned)
+struct Carver {
+    unsigned char* p;
+    template <class T>
+    __device__ __forceinline__ T* take(size_t n) {
+        T* r = reinterpret_cast<T*>(p);
+        p += (n * sizeof(T) + 15) & ~size_t(15);
+        return r;
+    }
+};
+static size_t al16(size_t b) { return (b + 15) & ~size_t(15); }
+
 template <int NF>
-struct StftSmem {
+struct Cfg {
     using G = Geo<NF>;
     static constexpr int UNITS = kThreads / G::LANES;
     static constexpr int FT = 2 * UNITS;  // frames per CTA
-    static size_t bytes(int hop) {
-        return sizeof(float2) * (32 * G::LANES + UNITS * G::SCRATCH) + sizeof(float) * (NF + (FT - 1) * hop + NF);
+    static constexpr int MP = FT + 1;     // mask tile pitch (odd)
+    // private overlap-add strip length (elements): hop + support, padded so that the two units of a
+    // warp (n_fft 512) land in different banks
+    static __host__ __device__ int strip(int hop, int support) {
+        const int lb = hop + support;
+        return G::LANES == 16 ? (((lb + 31) & ~31) + 16) : ((lb + 3) & ~3);
+    }
+    static __host__ __device__ size_t seg_floats(int hop) { return (size_t)(FT - 1) * hop + NF + 8; }
+    static __host__ __device__ size_t strips_bytes(int hop, int support, bool from_spec) {
+        size_t b = sizeof(float2) * UNITS * strip(hop, support);
+        if (!from_spec && b < sizeof(float) * seg_floats(hop)) b = sizeof(float) * seg_floats(hop);
+        return b;
+    }
+    static size_t stft_bytes(int hop) {
+        return al16(sizeof(float2) * 32 * G::LANES) + al16(sizeof(float) * UNITS * G::SCRATCH) +
+               al16(sizeof(float) * NF) + al16(sizeof(float) * seg_floats(hop)) + 16;
+    }
+    static size_t istft_bytes(int hop, int support) {
+        return al16(sizeof(float2) * 32 * G::LANES) + al16(sizeof(float) * UNITS * G::SCRATCH) +
+               al16(sizeof(float) * NF) + al16(sizeof(float) * UNITS * strip(hop, support)) +
+               al16(sizeof(double) * 2 * (kThreads / 32));
+    }
+    static size_t explain_bytes(int hop, int support, bool from_spec) {
+        return al16(sizeof(float2) * 32 * G::LANES) + al16(sizeof(float) * UNITS * G::SCRATCH) +
+               al16(sizeof(float) * NF) + al16(strips_bytes(hop, support, from_spec)) +
+               al16(sizeof(double) * 4 * (kThreads / 32)) + al16(sizeof(float) * G::NBINS * MP) + 16;
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// STFT
+// ------------------------------------------------------------------------------------------------
 template <int NF, bool MAG, bool PHASE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 stft_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, float2* __restrict__ X,
             float* __restrict__ mag, float* __restrict__ phase) {
     using G = Geo<NF>;
-    constexpr int UNITS = StftSmem<NF>::UNITS, FT = StftSmem<NF>::FT;
+    using C = Cfg<NF>;
+    constexpr int UNITS = C::UNITS, FT = C::FT, F = G::NBINS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw_s = reinterpret_cast<float2*>(smem_raw);
-    float2* scratch = tw_s + 32 * G::LANES;
-    float* win_s = reinterpret_cast<float*>(scratch + UNITS * G::SCRATCH);
-    float* seg = win_s + NF;
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(32 * G::LANES);
+    float* scratch = cv.take<float>(UNITS * G::SCRATCH);
+    float* win_s = cv.take<float>(NF);
+    float* seg = cv.take<float>(C::seg_floats(P.hop));
+    uint64_t* bar = cv.take<uint64_t>(1);
 
     const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * FT;
+    bool bulk;
+    const int shift = stage_segment(seg, (FT - 1) * P.hop + NF, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2,
+                                    P.n_in, bar, bulk);
     for (int i = tid; i < 32 * G::LANES; i += kThreads) tw_s[i] = P.tw[i];
     for (int i = tid; i < NF; i += kThreads) win_s[i] = P.window[i];
-    load_segment(seg, (FT - 1) * P.hop + NF, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in);
     __syncthreads();
+    stage_wait(bar, bulk);
 
     const int u = tid / G::LANES, l = tid % G::LANES;
-    float2* my = scratch + u * G::SCRATCH;
-    const int fa = t0 + 2 * u, fb = fa + 1;  // adjacent frames share one complex FFT
-    const float* sa = seg + (2 * u) * P.hop;
+    const int fa = t0 + 2 * u, fb = fa + 1;
+    const float* sa = seg + shift + (2 * u) * P.hop + l;
     const float* sb = sa + P.hop;
+    const float* wl = win_s + l;
     float2 v[32];
 #pragma unroll
     for (int n1 = 0; n1 < 32; ++n1) {
-        const int n = n1 * G::R2 + l;
-        const float w = win_s[n];
-        v[n1] = make_float2(sa[n] * w, sb[n] * w);
+        const float w = wl[n1 * G::R2];
+        v[n1] = make_float2(sa[n1 * G::R2] * w, sb[n1 * G::R2] * w);
     }
-    fwd_phase_a<NF>(v, l, TwSmem<G::LANES>{tw_s, l}, my);
-    __syncwarp();
-    fwd_phase_b<NF>(v, l, my);
+    unit_fft_forward<NF>(v, l, TwSmem<G::LANES>{tw_s, l}, scratch + u * G::SCRATCH);
     float2 xa[17], xb[17];
     split_regs<NF>(v, l, xa, xb);
 
-    constexpr int F = G::NBINS;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int t = half ? fb : fa;
@@ -193,49 +284,65 @@ __device__ __forceinline__ TileGeom tile_geom(const PlanDev& P, const Tiling& TL
     return g;
 }
 
+// Sum of the private strips that cover offset x (samples past the first strip's origin).  Strip u
+// starts at 2*hop*u and holds `lb` elements.  Fixed (descending-u) order => bit-reproducible.
+template <int UNITS>
+__device__ __forceinline__ float gather1(const float* pb, int strip, int lb, int two_hop, float inv_two_hop, int x) {
+    int u = min(UNITS - 1, (int)(((float)x + 0.5f) * inv_two_hop));
+    int k = x - u * two_hop;
+    float acc = 0.0f;
+    while (u >= 0 && k < lb) {
+        acc += pb[u * strip + k];
+        --u;
+        k += two_hop;
+    }
+    return acc;
+}
+template <int UNITS>
+__device__ __forceinline__ float2 gather2(const float2* pb, int strip, int lb, int two_hop, float inv_two_hop, int x) {
+    int u = min(UNITS - 1, (int)(((float)x + 0.5f) * inv_two_hop));
+    int k = x - u * two_hop;
+    float2 acc = make_float2(0.f, 0.f);
+    while (u >= 0 && k < lb) {
+        const float2 c = pb[u * strip + k];
+        acc.x += c.x;
+        acc.y += c.y;
+        --u;
+        k += two_hop;
+    }
+    return acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // iSTFT
 // ------------------------------------------------------------------------------------------------
 template <int NF>
-struct IstftSmem {
-    using G = Geo<NF>;
-    static constexpr int UNITS = kThreads / G::LANES;
-    static constexpr int FT = 2 * UNITS;
-    static size_t bytes(int tile_samples) {
-        return sizeof(float2) * (32 * G::LANES + UNITS * G::SCRATCH) + sizeof(float) * (NF + tile_samples) +
-               sizeof(double) * 2 * (kThreads / 32);
-    }
-};
-
-template <int NF>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 istft_kernel(PlanDev P, Tiling TL, const float2* __restrict__ X, int64_t sb, int64_t st, int64_t sf,
              float* __restrict__ out, double* __restrict__ stats) {
     using G = Geo<NF>;
-    constexpr int UNITS = IstftSmem<NF>::UNITS;
+    using C = Cfg<NF>;
+    constexpr int UNITS = C::UNITS;
+    const int support = P.whi - P.wlo, lb = P.hop + support, strip = C::strip(P.hop, support);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw_s = reinterpret_cast<float2*>(smem_raw);
-    float2* scratch = tw_s + 32 * G::LANES;
-    double* red = reinterpret_cast<double*>(scratch + UNITS * G::SCRATCH);
-    float* win_s = reinterpret_cast<float*>(red + 2 * (kThreads / 32));
-    float* ola = win_s + NF;
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(32 * G::LANES);
+    float* scratch = cv.take<float>(UNITS * G::SCRATCH);
+    float* win_s = cv.take<float>(NF);
+    float* pb = cv.take<float>(UNITS * strip);
+    double* red = cv.take<double>(2 * (kThreads / 32));
 
     const int tid = threadIdx.x, b = blockIdx.y;
     const TileGeom g = tile_geom<NF>(P, TL, blockIdx.x);
     const int S = g.s1 - g.s0;
-    for (int i = tid; i < 32 * G::LANES; i += kThreads) tw_s[i] = P.tw[i];
-    for (int i = tid; i < NF; i += kThreads) win_s[i] = P.window[i];
-    for (int i = tid; i < S; i += kThreads) ola[i] = 0.0f;
-
     const int u = tid / G::LANES, l = tid % G::LANES;
-    float2* my = scratch + u * G::SCRATCH;
-    const int fa = g.t_lo + u, fb = fa + UNITS;
+    const int fa = g.t_lo + 2 * u, fb = fa + 1;
     const bool va = fa <= g.t_hi, vb = fb <= g.t_hi;
 
     float2 ya[17], yb[17];
     {
         const float2* xa_p = X + (size_t)b * sb + (size_t)fa * st;
-        const float2* xb_p = X + (size_t)b * sb + (size_t)fb * st;
+        const float2* xb_p = xa_p + st;
 #pragma unroll
         for (int i = 0; i < 17; ++i) {
             const int bin = bin_of<NF>(l, i);
@@ -244,44 +351,46 @@ istft_kernel(PlanDev P, Tiling TL, const float2* __restrict__ X, int64_t sb, int
             yb[i] = (vb && bin >= 0) ? __ldg(xb_p + (size_t)bin * sf) : z;
         }
     }
-    __syncthreads();  // tables + zeroed accumulator visible
+    for (int i = tid; i < 32 * G::LANES; i += kThreads) tw_s[i] = P.tw[i];
+    for (int i = tid; i < NF; i += kThreads) win_s[i] = P.window[i];
+    __syncthreads();
 
     float2 v[32];
     merge_regs<NF>(v, l, ya, yb);
-    inv_phase_a<NF>(v, l, my);
-    __syncwarp();
-    inv_phase_b<NF>(v, l, TwSmem<G::LANES>{tw_s, l}, my);
+    unit_fft_inverse<NF>(v, l, TwSmem<G::LANES>{tw_s, l}, scratch + u * G::SCRATCH);
 
-    // overlap-add, `phases` rounds per packed frame; frames a and b = a + UNITS share a round when
-    // UNITS is a multiple of `phases`
-    const bool same = (UNITS % P.phases) == 0;
-    for (int pass = 0; pass < (same ? 1 : 2); ++pass) {
-        for (int ph = 0; ph < P.phases; ++ph) {
+    // private strip of the unit: frame a at [0, support), frame b at [hop, hop + support)
+    {
+        float* pbu = pb + u * strip;
+        const float* wl = win_s + l;
+        const int c0 = l - P.wlo;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                if (!same && half != pass) continue;
-                const int t = half ? fb : fa;
-                const bool ok = (half ? vb : va) && (t % P.phases) == ph;
-                if (ok) {
-                    const int off = t * P.hop - g.p0;
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const int k = n1 * G::R2 + c0;
+            if ((unsigned)k < (unsigned)support) pbu[k] = v[n1].x * wl[n1 * G::R2];
+        }
+        const int ovl = support - P.hop;  // samples of frame b that land on frame a's
+        if (ovl < 0)  // degenerate (hop > support, only legal for single-frame plans): clear the gap
+            for (int k = support + l; k < P.hop; k += G::LANES) pbu[k] = 0.0f;
+        __syncwarp();
 #pragma unroll
-                    for (int n1 = 0; n1 < 32; ++n1) {
-                        const int n = n1 * G::R2 + l;
-                        const int q = off + n;
-                        if (n >= P.wlo && n < P.whi && q >= 0 && q < S)
-                            ola[q] += (half ? v[n1].y : v[n1].x) * win_s[n];
-                    }
-                }
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const int k = n1 * G::R2 + c0;
+            if ((unsigned)k < (unsigned)support) {
+                const float old = k < ovl ? pbu[P.hop + k] : 0.0f;
+                pbu[P.hop + k] = fmaf(v[n1].y, wl[n1 * G::R2], old);
             }
-            __syncthreads();
         }
     }
+    __syncthreads();
 
     double acc[2] = {0.0, 0.0};
     float* orow = out + (size_t)b * P.n_out + g.s0;
     const float* env = P.inv_env + g.s0;
+    const int two_hop = 2 * P.hop, x0 = g.p0 - (g.t_lo * P.hop + P.wlo);
+    const float inv_two_hop = 1.0f / (float)two_hop;
     for (int q = tid; q < S; q += kThreads) {
-        const float y = ola[q] * __ldg(env + q);
+        const float y = gather1<UNITS>(pb, strip, lb, two_hop, inv_two_hop, x0 + q) * __ldg(env + q);
         orow[q] = y;
         acc[0] += (double)y;
         acc[1] += (double)y * (double)y;
@@ -299,39 +408,60 @@ istft_kernel(PlanDev P, Tiling TL, const float2* __restrict__ X, int64_t sb, int
 // ------------------------------------------------------------------------------------------------
 // fused explain: wave (or spectrum) + mask -> masked-in / masked-out waveforms
 // ------------------------------------------------------------------------------------------------
-template <int NF>
-struct ExplainSmem {
-    using G = Geo<NF>;
-    static constexpr int UNITS = kThreads / G::LANES;
-    static constexpr int FT = 2 * UNITS;
-    static constexpr int MP = FT + 1;  // mask tile pitch (odd)
-    static size_t bytes(int hop, int tile_samples, bool from_spec) {
-        size_t b = sizeof(float2) * (32 * G::LANES + UNITS * G::SCRATCH + tile_samples) +
-                   sizeof(double) * 4 * (kThreads / 32) + sizeof(float) * (NF + G::NBINS * MP);
-        if (!from_spec) b += sizeof(float) * ((FT - 1) * hop + NF);
-        return b;
-    }
-};
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
+// Gains that turn X into the masked-in / masked-out spectra with the ORIGINAL phase:
+//   log1p mode (LMAC_metrics.py:138-143,151-153): expm1(m*log1p(a)) * e^{i phi} = X * expm1(m*log1p(a)) / a
+//   linear mode (loss_function.py:38-45):          m*a*e^{i phi} = m*X
+// With er = expm1(m*log1p(a)) the complementary term needs no second exponential:
+//   expm1((1-m)*log1p(a)) = (1+a)/(1+er) - 1 = (a - er)/(1 + er).
+// a >= 1/16: (1+a)^m through MUFU lg2/ex2 (abs. error of lg2.approx 2^-22.6 => error relative to the bin
+// magnitude <= 5e-6); a < 1/16: Taylor series of log1p and expm1 (truncation < 1e-8 relative).
 template <int MODE>
 __device__ __forceinline__ void mask_gains(float2 x, float m, float& g_rel, float& g_irr) {
-    if (MODE == ADV_MASK_LINEAR) {  // loss_function.py:38-45: m*|X|*e^{i phi} = m*X
+    if (MODE == ADV_MASK_LINEAR) {
         g_rel = m;
         g_irr = 1.0f - m;
         return;
     }
-    // LMAC_metrics.py:138-143: expm1(m*log1p(a)) * e^{i phi} = X * expm1(m*log1p(a)) / a
-    const float a = sqrtf(x.x * x.x + x.y * x.y);
-    const float lm = log1pf(a);
-    const float er = expm1f(m * lm), ei = expm1f((1.0f - m) * lm);
-    if (a > 1e-30f) {
-        const float ia = 1.0f / a;
-        g_rel = er * ia;
-        g_irr = ei * ia;
-    } else {  // limit a -> 0: expm1(m*log1p(a))/a -> m (the product with X is 0 either way)
+    const float r2 = fmaf(x.x, x.x, x.y * x.y);
+    if (r2 < 1e-30f) {  // limit a -> 0: gain -> m (the product with X vanishes either way)
         g_rel = m;
         g_irr = 1.0f - m;
+        return;
     }
+    const float ia = rsqrtf(r2);
+    const float a = r2 * ia;
+    float er;
+    if (a >= 0.0625f) {
+        er = ex2_approx(m * lg2_approx(1.0f + a)) - 1.0f;
+    } else {
+        // log1p(a)/a = 1 - a(1/2 - a(1/3 - a(1/4 - a(1/5 - a/6)))), next term a^6/7 < 1e-8
+        float L = fmaf(a, -1.0f / 6.0f, 0.2f);
+        L = fmaf(-a, L, 0.25f);
+        L = fmaf(-a, L, 1.0f / 3.0f);
+        L = fmaf(-a, L, 0.5f);
+        L = fmaf(-a, L, 1.0f);
+        L *= a;
+        const float y = m * L;
+        float e = fmaf(y, 1.0f / 120.0f, 1.0f / 24.0f);
+        e = fmaf(y, e, 1.0f / 6.0f);
+        e = fmaf(y, e, 0.5f);
+        e = fmaf(y, e, 1.0f);
+        er = y * e;
+    }
+    const float ei = __fdividef(a - er, 1.0f + er);
+    g_rel = er * ia;
+    g_irr = ei * ia;
 }
 
 template <int NF, int MODE, bool FROM_SPEC>
@@ -341,25 +471,30 @@ explain_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t wav_
                const float* __restrict__ mask, int Fm, int Tm,
                float* __restrict__ rel, float* __restrict__ irr, double* __restrict__ stats) {
     using G = Geo<NF>;
-    using SM = ExplainSmem<NF>;
-    constexpr int UNITS = SM::UNITS, FT = SM::FT, MP = SM::MP, F = G::NBINS;
+    using C = Cfg<NF>;
+    constexpr int UNITS = C::UNITS, FT = C::FT, MP = C::MP, F = G::NBINS;
+    const int support = P.whi - P.wlo, lb = P.hop + support, strip = C::strip(P.hop, support);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw_s = reinterpret_cast<float2*>(smem_raw);
-    float2* scratch = tw_s + 32 * G::LANES;
-    float2* ola = scratch + UNITS * G::SCRATCH;  // .x masked-in, .y masked-out
-    const int Smax = TL.hops_per_tile * P.hop;
-    double* red = reinterpret_cast<double*>(ola + Smax);
-    float* win_s = reinterpret_cast<float*>(red + 4 * (kThreads / 32));
-    float* mask_s = win_s + NF;
-    float* seg = mask_s + F * MP;
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(32 * G::LANES);
+    float* scratch = cv.take<float>(UNITS * G::SCRATCH);
+    float* win_s = cv.take<float>(NF);
+    // .x masked-in, .y masked-out; the staged waveform shares this memory (dead once in registers)
+    float2* pb = reinterpret_cast<float2*>(cv.take<unsigned char>(C::strips_bytes(P.hop, support, FROM_SPEC)));
+    float* seg = reinterpret_cast<float*>(pb);
+    double* red = cv.take<double>(4 * (kThreads / 32));
+    float* mask_s = cv.take<float>(F * MP);
+    uint64_t* bar = cv.take<uint64_t>(1);
 
     const int tid = threadIdx.x, b = blockIdx.y;
     const TileGeom g = tile_geom<NF>(P, TL, blockIdx.x);
     const int S = g.s1 - g.s0;
-    for (int i = tid; i < 32 * G::LANES; i += kThreads) tw_s[i] = P.tw[i];
-    for (int i = tid; i < NF; i += kThreads) win_s[i] = P.window[i];
-    for (int i = tid; i < S; i += kThreads) ola[i] = make_float2(0.f, 0.f);
-    {   // mask tile [F][FT] <- mask[b][f][t_lo + c], zero outside the mask / clip
+    bool bulk = false;
+    int shift = 0;
+    if (!FROM_SPEC)
+        shift = stage_segment(seg, (FT - 1) * P.hop + NF, wav + (size_t)b * wav_stride, g.t_lo * P.hop - NF / 2,
+                              P.n_in, bar, bulk);
+    {   // mask tile [F][FT] <- mask[b][f][t_lo + c], zero outside the mask / tile
         const float* mrow = mask + (size_t)b * Fm * Tm;
         for (int e = tid; e < F * FT; e += kThreads) {
             const int f = e / FT, c = e % FT;
@@ -367,20 +502,21 @@ explain_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t wav_
             mask_s[f * MP + c] = (f < Fm && t < Tm && t <= g.t_hi) ? __ldg(mrow + (size_t)f * Tm + t) : 0.0f;
         }
     }
-    if (!FROM_SPEC)
-        load_segment(seg, (FT - 1) * P.hop + NF, wav + (size_t)b * wav_stride, g.t_lo * P.hop - NF / 2, P.n_in);
+    for (int i = tid; i < 32 * G::LANES; i += kThreads) tw_s[i] = P.tw[i];
+    for (int i = tid; i < NF; i += kThreads) win_s[i] = P.window[i];
     __syncthreads();
 
     const int u = tid / G::LANES, l = tid % G::LANES;
-    float2* my = scratch + u * G::SCRATCH;
-    const int fa = g.t_lo + u, fb = fa + UNITS;
-    const bool va = fa <= g.t_hi, vb = fb <= g.t_hi;
+    float* my = scratch + u * G::SCRATCH;
+    const int fa = g.t_lo + 2 * u;
+    const float* wl = win_s + l;
 
     float2 v[32];
     float2 xa[17], xb[17];
     if (FROM_SPEC) {
+        const bool va = fa <= g.t_hi, vb = fa + 1 <= g.t_hi;
         const float2* xa_p = X + (size_t)b * sb + (size_t)fa * st;
-        const float2* xb_p = X + (size_t)b * sb + (size_t)fb * st;
+        const float2* xb_p = xa_p + st;
 #pragma unroll
         for (int i = 0; i < 17; ++i) {
             const int bin = bin_of<NF>(l, i);
@@ -389,70 +525,74 @@ explain_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t wav_
             xb[i] = (vb && bin >= 0) ? __ldg(xb_p + (size_t)bin * sf) : z;
         }
     } else {
-        const float* sa = seg + u * P.hop;
-        const float* sbp = sa + UNITS * P.hop;
+        stage_wait(bar, bulk);
+        const float* sa = seg + shift + (2 * u) * P.hop + l;
+        const float* sbp = sa + P.hop;
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
-            const int n = n1 * G::R2 + l;
-            const float w = win_s[n];
-            v[n1] = make_float2(va ? sa[n] * w : 0.f, vb ? sbp[n] * w : 0.f);
+            const float w = wl[n1 * G::R2];
+            v[n1] = make_float2(sa[n1 * G::R2] * w, sbp[n1 * G::R2] * w);
         }
-        fwd_phase_a<NF>(v, l, TwSmem<G::LANES>{tw_s, l}, my);
-        __syncwarp();
-        fwd_phase_b<NF>(v, l, my);
-        __syncwarp();
+        __syncthreads();  // every thread holds its samples: the segment's memory becomes the strips
+        unit_fft_forward<NF>(v, l, TwSmem<G::LANES>{tw_s, l}, my);
         split_regs<NF>(v, l, xa, xb);
     }
 
-#pragma unroll
+    float2* pbu = pb + u * strip;
+    const int c0 = l - P.wlo, ovl = support - P.hop;
+    if (ovl < 0)  // degenerate (hop > support, only legal for single-frame plans): clear the gap
+        for (int k = support + l; k < P.hop; k += G::LANES) pbu[k] = make_float2(0.f, 0.f);
+    // the two frames of the unit go through the same code: frame b's spectrum is rotated into xa
+#pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-        const int t = half ? fb : fa;
-        const bool valid = half ? vb : va;
-        const float2* x = half ? xb : xa;
-        const int col = t - g.t_lo;
-        float2 yr[17], yi[17];
+        const int t = fa + half;
+        const bool valid = t <= g.t_hi;
+        const int col = 2 * u + half;
+        {
+            float2 yr[17], yi[17];
 #pragma unroll
-        for (int i = 0; i < 17; ++i) {
-            const int bin = bin_of<NF>(l, i);
-            const float m = (bin >= 0 && valid) ? mask_s[bin * MP + col] : 0.0f;
-            float gr, gi;
-            mask_gains<MODE>(x[i], m, gr, gi);
-            const bool live = bin >= 0;
-            yr[i] = live ? make_float2(x[i].x * gr, x[i].y * gr) : make_float2(0.f, 0.f);
-            yi[i] = live ? make_float2(x[i].x * gi, x[i].y * gi) : make_float2(0.f, 0.f);
-        }
-        merge_regs<NF>(v, l, yr, yi);
-        inv_phase_a<NF>(v, l, my);
-        __syncwarp();
-        inv_phase_b<NF>(v, l, TwSmem<G::LANES>{tw_s, l}, my);
-        // v[n1] = n_fft * (rel[n], irr[n]) of frame t
-        for (int ph = 0; ph < P.phases; ++ph) {
-            if (valid && (t % P.phases) == ph) {
-                const int off = t * P.hop - g.p0;
-#pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    const int n = n1 * G::R2 + l;
-                    const int q = off + n;
-                    if (n >= P.wlo && n < P.whi && q >= 0 && q < S) {
-                        const float w = win_s[n];
-                        float2 o = ola[q];
-                        o.x += v[n1].x * w;
-                        o.y += v[n1].y * w;
-                        ola[q] = o;
-                    }
-                }
+            for (int i = 0; i < 17; ++i) {
+                const int bin = bin_of<NF>(l, i);
+                const bool live = bin >= 0 && valid;
+                const float m = live ? mask_s[bin * MP + col] : 0.0f;
+                float gr, gi;
+                mask_gains<MODE>(xa[i], m, gr, gi);
+                yr[i] = live ? make_float2(xa[i].x * gr, xa[i].y * gr) : make_float2(0.f, 0.f);
+                yi[i] = live ? make_float2(xa[i].x * gi, xa[i].y * gi) : make_float2(0.f, 0.f);
             }
-            __syncthreads();
+            merge_regs<NF>(v, l, yr, yi);
+        }
+#pragma unroll
+        for (int i = 0; i < 17; ++i) xa[i] = xb[i];
+        // (starts with a __syncwarp: frame a's strip stores below are visible to the whole unit
+        //  before frame b's read-modify-write)
+        unit_fft_inverse<NF>(v, l, TwSmem<G::LANES>{tw_s, l}, my);
+        // v[n1] = n_fft * (rel[n], irr[n]) of frame t -> private strip at [half*hop, half*hop + support)
+        float2* dst = pbu + half * P.hop;
+        const int keep = half ? ovl : 0;  // leading samples that add onto frame a's
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const int k = n1 * G::R2 + c0;
+            if ((unsigned)k < (unsigned)support) {
+                const float w = wl[n1 * G::R2];
+                float2 o = k < keep ? dst[k] : make_float2(0.f, 0.f);
+                o.x = fmaf(v[n1].x, w, o.x);
+                o.y = fmaf(v[n1].y, w, o.y);
+                dst[k] = o;
+            }
         }
     }
+    __syncthreads();
 
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     float* rrow = rel + (size_t)b * P.n_out + g.s0;
     float* irow = irr + (size_t)b * P.n_out + g.s0;
     const float* env = P.inv_env + g.s0;
+    const int two_hop = 2 * P.hop, x0 = g.p0 - (g.t_lo * P.hop + P.wlo);
+    const float inv_two_hop = 1.0f / (float)two_hop;
     for (int q = tid; q < S; q += kThreads) {
         const float e = __ldg(env + q);
-        const float2 o = ola[q];
+        const float2 o = gather2<UNITS>(pb, strip, lb, two_hop, inv_two_hop, x0 + q);
         const float yr = o.x * e, yi = o.y * e;
         rrow[q] = yr;
         irow[q] = yi;
@@ -495,8 +635,8 @@ static int set_smem(K kernel, size_t bytes) {
 template <int NF>
 static int launch_stft_nf(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X,
                           float* mag, float* phase, cudaStream_t s) {
-    constexpr int FT = StftSmem<NF>::FT;
-    const size_t smem = StftSmem<NF>::bytes(p->d.hop);
+    constexpr int FT = Cfg<NF>::FT;
+    const size_t smem = Cfg<NF>::stft_bytes(p->d.hop);
     dim3 grid((p->d.T + FT - 1) / FT, batch);
     int rc;
 #define ADV_LAUNCH_STFT(M, PH)                                                           \
@@ -523,7 +663,7 @@ template <int NF>
 static int launch_istft_nf(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch,
                            float* out, double* stats, cudaStream_t s) {
     const Tiling tl = choose_tiling(p, batch);
-    const size_t smem = IstftSmem<NF>::bytes(tl.hops_per_tile * p->d.hop);
+    const size_t smem = Cfg<NF>::istft_bytes(p->d.hop, p->d.whi - p->d.wlo);
     int rc = set_smem(istft_kernel<NF>, smem);
     if (rc != ADV_OK) return rc;
     dim3 grid(tl.tiles, batch);
@@ -542,7 +682,7 @@ template <int NF, int MODE, bool FROM_SPEC>
 static int launch_explain_inst(const adv_plan* p, const Tiling& tl, const float* wav, int64_t wav_stride,
                                const float2* X, int64_t sb, int64_t st, int64_t sf, const float* mask, int Fm,
                                int Tm, int batch, float* rel, float* irr, double* stats, cudaStream_t s) {
-    const size_t smem = ExplainSmem<NF>::bytes(p->d.hop, tl.hops_per_tile * p->d.hop, FROM_SPEC);
+    const size_t smem = Cfg<NF>::explain_bytes(p->d.hop, p->d.whi - p->d.wlo, FROM_SPEC);
     int rc = set_smem(explain_kernel<NF, MODE, FROM_SPEC>, smem);
     if (rc != ADV_OK) return rc;
     dim3 grid(tl.tiles, batch);

@@ -120,8 +120,8 @@ def explain(wave, mask, n_fft, hop, win_length, length=None, mode="log1p", windo
     check(lib().adv_explain(plan.handle, ptr(wave), wave.stride(0), ptr(mask), mask.shape[1], mask.shape[2],
                             MODES[mode], B, ptr(rel), ptr(irr), ptr(stats), stream_ptr()), "adv_explain")
     if normalize:
-        normalize_(rel, stats, 4, 0, out=rel)
-        normalize_(irr, stats, 4, 2, out=irr)
+        check(lib().adv_normalize_pair(ptr(rel), ptr(irr), B, n_out, ptr(stats), stats.shape[1], stream_ptr()),
+              "adv_normalize_pair")
     return rel, irr
 
 
@@ -147,8 +147,8 @@ def explain_spec(spec, mask, n_fft, hop, win_length, length=None, mode="log1p", 
     check(lib().adv_explain_spec(plan.handle, ptr(spec), sb, st, sf, ptr(mask), mask.shape[1], mask.shape[2],
                                  MODES[mode], B, ptr(rel), ptr(irr), ptr(stats), stream_ptr()), "adv_explain_spec")
     if normalize:
-        normalize_(rel, stats, 4, 0, out=rel)
-        normalize_(irr, stats, 4, 2, out=irr)
+        check(lib().adv_normalize_pair(ptr(rel), ptr(irr), B, n_out, ptr(stats), stats.shape[1], stream_ptr()),
+              "adv_normalize_pair")
     return rel, irr
 
 

@@ -4,7 +4,7 @@ on preallocated buffers and (optionally) replayed as one CUDA graph.
     wave [B,n] + mask [B,F,T] --explain--> rel, irr --normalise x2--> (SSL classifier, not ours)
     logits p / theta / q [B] --lmac_reduce--> six float64 sums
 
-Launches per step: explain, normalize, normalize, lmac = 4 kernels, no allocation, no host sync.
+Launches per step: explain, normalize (both waves), lmac = 3 kernels, no allocation, no host sync.
 ``step_host`` is the end-to-end entry: inputs arrive in pinned host memory, are copied to the device
 on a side stream (double-buffered against the previous step's compute), and the six sums come back
 to pinned host memory.
@@ -16,7 +16,7 @@ import torch
 from . import ops
 from ._lib import check, lib, ptr, stream_ptr
 
-KERNELS_PER_STEP = 4
+KERNELS_PER_STEP = 3
 
 
 class ExplainPipeline:
@@ -42,7 +42,7 @@ class ExplainPipeline:
         if use_graph:
             self._capture()
 
-    # the four launches of one step, on the current stream
+    # the three launches of one step, on the current stream
     def _enqueue(self):
         ap = self.ap
         ops.explain(self.wav, self.mask, ap.n_fft, ap.hop_length, ap.win_length, length=self.n, mode=self.mode,
