@@ -496,6 +496,7 @@ explain_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t wav_
                               P.n_in, bar, bulk);
     {   // mask tile [F][FT] <- mask[b][f][t_lo + c], zero outside the mask / tile
         const float* mrow = mask + (size_t)b * Fm * Tm;
+#pragma unroll 8
         for (int e = tid; e < F * FT; e += kThreads) {
             const int f = e / FT, c = e % FT;
             const int t = g.t_lo + c;
