@@ -181,6 +181,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # keeps stdout to the one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     pkg = importlib.import_module("xai-audio-deepfakes_b200")
