@@ -130,6 +130,34 @@ int adv_mask_head(const float* y1, const float* w, const float* bias, int batch,
 int adv_band_swap(const adv_c64* real, const adv_c64* voc, int batch, int T, int F, int f_lo, int f_hi,
                   adv_c64* out, void* stream);
 
+/* ==== tensor-core (tcgen05 / TMEM) entry points ========================================================== */
+
+/* ---- mel filterbank projection: MelSpectrogram / mel_spectogram (audioprocessor.py:38-44, hifigan.py:163-178)
+ * X: dev complex64 [rows = B*T][F] frame-major spectrum (adv_stft output); fb_hi / fb_lo: dev float [NM][Kpad],
+ * the transposed filterbank split into its tf32-representable part and the remainder (3xTF32 GEMM, fp32 accuracy),
+ * NM = n_mels rounded up to 64 / 80 / 128, Kpad a multiple of 32 >= F.  out: dev float [B][n_mels][T] =
+ * sum_f fb[f][mel] * |X|^power, then log(max(., clip)) when log_compress != 0. */
+int adv_mel_project(const adv_c64* X, int64_t rows, int T, int F, const float* fb_hi, const float* fb_lo, int Kpad,
+                    int n_mels, float power, int log_compress, float clip, float* out, void* stream);
+
+/* ---- HiFi-GAN generator layers (SpeechBrain HifiganGenerator behind hifi_gan.decode_batch, hifigan.py:180) -----
+ * adv_conv1d_bf16: channels-last bf16 conv1d as an implicit GEMM, "same" length, odd tap count:
+ *   out[b,l,n] = out_scale * ( bias[n] + sum_{tap,ci} w[n][tap*Cin+ci] * lrelu(in[b, l+(tap-center)*dil, ci], pre_slope)
+ *                              + resid[b,l,n] )
+ * in [B][L][Cin], w [N][Kpad] (Kpad multiple of 64, zero padded), resid / out [B][L][N]; Cin % 8 == 0, N % 16 == 0;
+ * pad_reflect selects reflect instead of zero padding; pre_slope = 1 disables the input activation.
+ * A transposed conv (stride s) is this conv with 3 taps and N = s*Cout phase-stacked weights. */
+int adv_conv1d_bf16(const void* in, const void* w, const float* bias, const void* resid, void* out, int batch, int L,
+                    int Cin, int taps, int dil, int N, int Kpad, int pad_reflect, float pre_slope, float out_scale,
+                    void* stream);
+/* mel [B][C][T] fp32 -> channels-last bf16 [B][T+2*pad][Cpad], replicate-padded in time (inference_padding) */
+int adv_mel_to_channels_last(const float* mel, int batch, int C, int T, int pad, int Cpad, void* out, void* stream);
+/* MRF average of the three resblock outputs (bf16, n elements) */
+int adv_avg3_bf16(const void* a, const void* b, const void* c, int64_t n, void* out, void* stream);
+/* LeakyReLU(slope) -> conv_post (C=32 -> 1, 7 taps, w [taps][C] fp32) -> tanh; out dev float [B][L] */
+int adv_post_conv_tanh(const void* in, const float* w, const float* bias, int batch, int L, int C, int taps, float slope,
+                       int pad_reflect, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

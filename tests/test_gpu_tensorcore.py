@@ -1,0 +1,139 @@
+"""GPU parity of the tcgen05 kernels: conv1d implicit GEMM, transposed conv, mel projection and the
+full HiFi-GAN generator, against torch fp32 references / the oracle restatement (oracle/vocoder.py).
+
+Tolerances: mel within 1e-4 (max|y-ref| / max|ref|, fp32 via 3xTF32); bf16 vocoder within 1e-2
+relative L2 (BASELINE.json north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden
+from oracle import ref_path as R
+from oracle import vocoder as V
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.fixture(scope="module")
+def H(pkg, built_lib):
+    assert torch.cuda.is_available()
+    return pkg.hifigan
+
+
+def run_conv(pkg, x_cl, w, b, dil, reflect=False, pre_slope=1.0, resid=None, scale=1.0):
+    """x_cl [B,L,Cin] bf16 cuda; w [Cout,Cin,k] fp32 -> out [B,L,Cout] bf16 (through the C ABI)."""
+    L_ = pkg._lib
+    gw, kpad = pkg.hifigan._gemm_weight(w)
+    gw, bias = gw.cuda(), b.float().cuda()
+    B, L, Cin = x_cl.shape
+    out = torch.empty(B, L, w.shape[0], dtype=torch.bfloat16, device="cuda")
+    L_.check(L_.lib().adv_conv1d_bf16(L_.ptr(x_cl), L_.ptr(gw), L_.ptr(bias), L_.ptr(resid), L_.ptr(out), B, L, Cin,
+                                      w.shape[2], dil, w.shape[0], kpad, int(reflect), float(pre_slope), float(scale),
+                                      L_.stream_ptr()), "adv_conv1d_bf16")
+    return out
+
+
+CONV_CASES = [
+    # B, L, Cin, Cout, k, dil, reflect, pre_slope, resid
+    (2, 300, 64, 64, 3, 1, False, 1.0, False),
+    (1, 1000, 80, 512, 7, 1, False, 1.0, False),     # conv_pre shape (Cin = 80: K padded 560 -> 576)
+    (2, 257, 32, 32, 11, 5, False, 0.1, True),       # narrow MRF stage: one K-block spans two taps
+    (3, 130, 128, 128, 7, 3, True, 0.1, True),       # reflect padding variant
+    (1, 64, 512, 256, 3, 1, False, 0.1, False),
+    (2, 90, 256, 2048, 3, 1, False, 0.1, False),     # phase-stacked transposed conv shape (N tiles of 256)
+    (1, 40, 16, 16, 5, 2, False, 1.0, False),        # smallest N tile
+]
+
+
+@pytest.mark.parametrize("B,L,Cin,Cout,k,dil,reflect,slope,use_resid", CONV_CASES)
+def test_conv1d_tc_matches_torch(pkg, H, B, L, Cin, Cout, k, dil, reflect, slope, use_resid):
+    g = torch.Generator().manual_seed(B * L + Cin + k)
+    x = bf16r(torch.randn(B, Cin, L, generator=g))
+    w = bf16r(0.1 * torch.randn(Cout, Cin, k, generator=g))
+    b = 0.1 * torch.randn(Cout, generator=g)
+    resid = bf16r(torch.randn(B, Cout, L, generator=g)) if use_resid else None
+    xin = F.leaky_relu(x, slope) if slope != 1.0 else x
+    ref = V._conv(bf16r(xin), w, b, dil, reflect)
+    if resid is not None:
+        ref = ref + resid
+    x_cl = x.transpose(1, 2).contiguous().to(torch.bfloat16).cuda()
+    r_cl = resid.transpose(1, 2).contiguous().to(torch.bfloat16).cuda() if use_resid else None
+    out = run_conv(pkg, x_cl, w, b, dil, reflect, slope, r_cl)
+    got = out.float().cpu().transpose(1, 2)
+    assert rel_l2(got, ref) < 4e-3      # bf16 output rounding (2^-9) dominates
+
+
+def test_transposed_conv_as_conv(pkg, H):
+    g = torch.Generator().manual_seed(3)
+    for cin, cout, k, s, L in [(64, 32, 16, 8, 50), (32, 16, 4, 2, 333)]:
+        x = bf16r(torch.randn(2, cin, L, generator=g))
+        w = bf16r(0.1 * torch.randn(cin, cout, k, generator=g))
+        b = 0.1 * torch.randn(cout, generator=g)
+        ref = F.conv_transpose1d(bf16r(F.leaky_relu(x, 0.1)), w, b, stride=s, padding=(k - s) // 2)
+        wc, bc = H._transposed_as_conv(w, b, s)
+        out = run_conv(pkg, x.transpose(1, 2).contiguous().to(torch.bfloat16).cuda(), wc, bc, 1, False, 0.1)
+        got = out.view(2, L * s, cout).float().cpu().transpose(1, 2)
+        assert got.shape == ref.shape and rel_l2(got, ref) < 4e-3
+
+
+@pytest.mark.parametrize("variant", ["torchaudio_default", "speechbrain_vocoder"])
+def test_mel_matches_oracle(pkg, variant):
+    g = torch.Generator().manual_seed(5)
+    wav = 0.1 * torch.randn(3, 16000, generator=g)
+    if variant == "torchaudio_default":     # audioprocessor.py:38-44
+        ap = pkg.audioprocessor.AudioProcessor(audio_length=1)
+        got = ap.mel_transform(wav)
+        ref = R.mel_transform(wav)
+        err = float((got.cpu() - ref).abs().max() / ref.abs().max())
+        assert got.shape == ref.shape and err < 1e-4, err
+    else:                                    # hifigan.py:163-178
+        got, _ = pkg.mel.mel_spectogram(audio=wav, sample_rate=16000, hop_length=256, win_length=1024, n_mels=80,
+                                        n_fft=1024, f_min=0.0, f_max=8000.0, power=1, normalized=False,
+                                        min_max_energy_norm=True, norm="slaney", mel_scale="slaney", compression=True)
+        ref = V.mel_spectogram(wav)
+        assert got.shape == ref.shape
+        # log domain: absolute error of log(x) == relative error of x
+        assert float((got.cpu() - ref).abs().max()) < 2e-4
+
+
+def test_mel_against_reference_golden(pkg):
+    g = golden("mel_default_small.npz")
+    sr, n_fft, hop, win, n_mels = (int(v) for v in g["params"])
+    ap = pkg.audioprocessor.AudioProcessor(sampling_rate=sr, n_fft=n_fft, hop_length=hop, win_length=win,
+                                           n_mels=n_mels, audio_length=1)
+    got = ap.mel_transform(torch.from_numpy(g["wav"])).cpu().numpy()
+    assert got.shape == g["mel"].shape
+    assert np.abs(got - g["mel"]).max() / np.abs(g["mel"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("reflect", [False, True])
+def test_hifigan_generator_matches_oracle(pkg, H, reflect):
+    """Whole generator (61 conv launches), seeded weights.  std 0.03 gives per-layer gains near 1 (the original
+    N(0, 0.01^2) init lets biases dominate); larger scales saturate tanh and make the comparison chaotic."""
+    cfg = type("Cfg", (H.HifiganConfig,), {"pad_reflect": reflect})
+    W = H.init_weights(cfg, seed=1, std=0.03)
+    gen = H.HifiganGenerator(W, cfg)
+    g = torch.Generator().manual_seed(2)
+    mel = -4 + 2 * torch.randn(2, 80, 9, generator=g)
+    wav = gen.decode_batch(mel)
+    assert wav.shape == (2, 1, (9 + 10) * 256)
+    Wq = {k: (bf16r(v) if k.endswith("weight") and not k.startswith("conv_post") else v) for k, v in W.items()}
+    ref = V.generator(mel, Wq, reflect=reflect)
+    # vs exact fp32 math on the same (bf16-rounded) weights
+    assert rel_l2(wav, ref) < 1e-2, rel_l2(wav, ref)
+    # vs the oracle with bf16 storage of activations modelled: tighter
+    refq = V.generator(mel, Wq, reflect=reflect, quantize=bf16r)
+    assert rel_l2(wav, refq) < 1e-2, rel_l2(wav, refq)
+    assert gen.launches == 1 + 4 * (1 + 18)   # conv_pre + 4 x (upsample + 3 resblocks x 3 x 2 convs)

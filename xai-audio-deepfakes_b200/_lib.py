@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libaddvisor_sm100.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "transform_kernels.cu", "pointwise_kernels.cu", "mel_kernels.cu", "vocoder_kernels.cu"]
+SOURCES = ["capi.cu", "transform_kernels.cu", "pointwise_kernels.cu", "gemm_kernels.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC"]
 
@@ -85,11 +85,18 @@ _SIGS = {
     "adv_band_swap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                 C.c_void_p]),
 }
-# entry points of later translation units, bound when present in the header
-_OPTIONAL_SIGS = {
-    "adv_mel_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float,
-                                  C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
-}
+_SIGS.update({
+    "adv_mel_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "adv_conv1d_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "adv_mel_to_channels_last": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p]),
+    "adv_avg3_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "adv_post_conv_tanh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                     C.c_int, C.c_void_p, C.c_void_p]),
+})
+_OPTIONAL_SIGS = {}
 
 
 def lib():

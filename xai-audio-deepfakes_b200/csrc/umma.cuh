@@ -1,0 +1,117 @@
+// Thin inline-PTX layer over the Blackwell tensor-core path (tcgen05 + TMEM) used by the
+// implicit-GEMM kernels (mel filterbank projection, HiFi-GAN convolutions).
+//
+// Conventions (sm_100a, cta_group::1, M = 128 per CTA):
+//   * operands live in shared memory, K-major, 128-byte rows, SWIZZLE_128B: element (row r, 16-byte
+//     chunk c) of a tile sits at  base + r*128 + ((c ^ (r & 7)) << 4),  base 1024-byte aligned;
+//     8-row groups are 1024 bytes apart (stride byte offset);
+//   * the accumulator D[128][N] lives in TMEM: lane = row, column = n (fp32);
+//   * one thread issues tcgen05.mma; tcgen05.commit arrives on an mbarrier when the MMAs retire;
+//   * the epilogue reads TMEM with tcgen05.ld.32x32b (warp w of the CTA owns lanes 32w..32w+31).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace adv {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- shared-memory matrix descriptor (K-major, SWIZZLE_128B) -----------------------------------
+// bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SW128)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)0 << 16;                  // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+
+// ---- instruction descriptor (kind::f16 / kind::tf32, fp32 accumulate, both operands K-major) -----
+enum : uint32_t { FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2 };
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
+    return (1u << 4)            // c_format = F32
+           | (fmt << 7)         // a_format
+           | (fmt << 10)        // b_format
+           | (0u << 15)         // a_major = K
+           | (0u << 16)         // b_major = K
+           | ((N >> 3) << 17)   // n_dim
+           | ((M >> 4) << 24);  // m_dim
+}
+
+// ---- TMEM allocation (whole warp executes) ---------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(smem_dst)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+
+// ---- fences ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand fetch)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- MMA issue (single thread) ---------------------------------------------------------------------
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on `bar` once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
+                 : "memory");
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// ---- TMEM -> registers: 32 lanes x 8 consecutive fp32 columns --------------------------------------
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of (row, 16-byte chunk) inside a SWIZZLE_128B K-major tile
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
+    return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+}  // namespace umma
+}  // namespace adv

@@ -1,0 +1,188 @@
+"""HiFi-GAN V1 generator on tcgen05 (the vocoder hifigan.py:106-110,180 runs through SpeechBrain).
+
+SpeechBrain is not vendored in the reference and not installed here, and the checkpoint
+(``speechbrain/tts-hifigan-libritts-16kHz``) is unreachable offline, so the architecture is restated from
+the published V1 design that SpeechBrain's ``HifiganGenerator`` implements: conv_pre(80->512, k7);
+4 x [LeakyReLU(0.1) -> ConvTranspose1d (x8, x8, x2, x2; k16, k16, k4, k4) -> mean of 3 ResBlock1
+(k 3/7/11, dilations 1/3/5, two convs each)]; LeakyReLU(0.01) -> conv_post(32->1, k7) -> tanh;
+``inference_padding`` = 5 replicate-padded mel frames per side.  Weights here are seeded random
+(N(0, 0.01^2), like the original init) with weight-norm already folded; a real checkpoint loads through
+``load_state_dict``-style tensors with the same shapes.  **Parity for this module is unpinned by the
+reference** (see oracle/vocoder.py); it is checked against a torch-fp32 restatement with the same weights.
+
+Execution: activations are channels-last bf16 [B][L][C]; every conv is ``adv_conv1d_bf16`` - an implicit
+GEMM (M = positions, N = C_out, K = taps*C_in) on tcgen05 with fp32 TMEM accumulation, LeakyReLU fused
+into the operand gather, bias / residual fused into the epilogue.  A ConvTranspose1d with stride s is the
+same kernel with 3 taps and N = s*C_out phase-stacked weights: its channels-last output [B][L][s*C_out]
+*is* the upsampled tensor [B][L*s][C_out].
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+from ._lib import check, lib, ptr, stream_ptr
+
+LRELU_SLOPE = 0.1
+
+
+class HifiganConfig:
+    in_channels = 80
+    upsample_initial_channel = 512
+    upsample_factors = (8, 8, 2, 2)
+    upsample_kernel_sizes = (16, 16, 4, 4)
+    resblock_kernel_sizes = (3, 7, 11)
+    resblock_dilation_sizes = ((1, 3, 5), (1, 3, 5), (1, 3, 5))
+    inference_padding = 5
+    conv_post_kernel = 7
+    pad_reflect = False  # zero "same" padding as in the original HiFi-GAN; see oracle/vocoder.py header
+
+
+def init_weights(cfg=HifiganConfig, seed=0, std=0.01):
+    """Seeded fp32 master weights in torch layout (Conv1d [Cout,Cin,k], ConvTranspose1d [Cin,Cout,k])."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: std * torch.randn(*s, generator=g)
+    W = {}
+    ch = cfg.upsample_initial_channel
+    W["conv_pre.weight"], W["conv_pre.bias"] = rn(ch, cfg.in_channels, 7), rn(ch)
+    for i, (s, k) in enumerate(zip(cfg.upsample_factors, cfg.upsample_kernel_sizes)):
+        cout = ch // 2
+        W[f"ups.{i}.weight"], W[f"ups.{i}.bias"] = rn(ch, cout, k), rn(cout)
+        for j, (ks, dils) in enumerate(zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes)):
+            for d in range(len(dils)):
+                r = f"resblocks.{i * len(cfg.resblock_kernel_sizes) + j}"
+                W[f"{r}.convs1.{d}.weight"], W[f"{r}.convs1.{d}.bias"] = rn(cout, cout, ks), rn(cout)
+                W[f"{r}.convs2.{d}.weight"], W[f"{r}.convs2.{d}.bias"] = rn(cout, cout, ks), rn(cout)
+        ch = cout
+    W["conv_post.weight"], W["conv_post.bias"] = rn(1, ch, cfg.conv_post_kernel), rn(1)
+    return W
+
+
+def fold_weight_norm(g, v, dim=0):
+    """weight = g * v / ||v|| (norm over every dim but ``dim``), as torch.nn.utils.weight_norm stores it."""
+    dims = [d for d in range(v.dim()) if d != dim]
+    return g * v / torch.linalg.vector_norm(v, dim=dims, keepdim=True)
+
+
+def _gemm_weight(w):
+    """Conv1d weight [Cout, Cin, k] -> bf16 [Cout][Kpad], K index = tap*Cin + ci, Kpad multiple of 64."""
+    cout, cin, k = w.shape
+    m = w.permute(0, 2, 1).reshape(cout, k * cin)
+    kpad = (k * cin + 63) // 64 * 64
+    out = torch.zeros(cout, kpad)
+    out[:, :k * cin] = m
+    return out.to(torch.bfloat16).contiguous(), kpad
+
+
+def _transposed_as_conv(w, bias, stride):
+    """ConvTranspose1d weight [Cin, Cout, k] (padding (k-stride)//2) -> equivalent Conv1d weight
+    [stride*Cout, Cin, taps] over the un-upsampled input: output phase r of position q reads
+    in[q + o] * w[:, :, kk] for every kk with kk = r + p - o*stride."""
+    cin, cout, k = w.shape
+    p = (k - stride) // 2
+    offs = [(r + p - kk) // stride for r in range(stride) for kk in range(k) if (r + p - kk) % stride == 0]
+    reach = max(abs(o) for o in offs)
+    taps = 2 * reach + 1
+    wc = torch.zeros(stride * cout, cin, taps)
+    for r in range(stride):
+        for kk in range(k):
+            if (r + p - kk) % stride == 0:
+                o = (r + p - kk) // stride
+                wc[r * cout:(r + 1) * cout, :, o + reach] = w[:, :, kk].t()
+    return wc, bias.repeat(stride)
+
+
+class _Layer:
+    def __init__(self, w, bias, dil, dev):
+        self.cout, self.cin, self.taps = w.shape
+        self.dil = dil
+        gw, self.kpad = _gemm_weight(w)
+        self.w = gw.to(dev)
+        self.bias = bias.float().to(dev).contiguous()
+
+
+class HifiganGenerator:
+    """``decode_batch(mel[B,80,T]) -> waveform [B,1,(T+10)*256]`` (SpeechBrain HIFIGAN.decode_batch)."""
+
+    def __init__(self, weights=None, cfg=HifiganConfig, device=None, seed=0):
+        self.cfg = cfg
+        self.dev = device or ops._dev()
+        W = weights if weights is not None else init_weights(cfg, seed)
+        self.master = W
+        L = lambda name, dil=1: _Layer(W[name + ".weight"], W[name + ".bias"], dil, self.dev)
+        self.conv_pre = L("conv_pre")
+        self.ups, self.blocks = [], []
+        nk = len(cfg.resblock_kernel_sizes)
+        for i, s in enumerate(cfg.upsample_factors):
+            wc, bc = _transposed_as_conv(W[f"ups.{i}.weight"], W[f"ups.{i}.bias"], s)
+            self.ups.append((_Layer(wc, bc, 1, self.dev), s))
+            stage = []
+            for j, dils in enumerate(cfg.resblock_dilation_sizes):
+                r = f"resblocks.{i * nk + j}"
+                stage.append([(L(f"{r}.convs1.{d}", dil), L(f"{r}.convs2.{d}", 1)) for d, dil in enumerate(dils)])
+            self.blocks.append(stage)
+        wp = W["conv_post.weight"]
+        self.post_w = wp[0].t().contiguous().float().to(self.dev)      # [taps][C]
+        self.post_b = W["conv_post.bias"].float().to(self.dev)
+        self.launches = 0
+
+    # one implicit-GEMM conv launch
+    def _conv(self, x, layer, B, L, pre_slope=1.0, resid=None, scale=1.0):
+        out = torch.empty((B, L, layer.cout), dtype=torch.bfloat16, device=self.dev)
+        check(lib().adv_conv1d_bf16(ptr(x), ptr(layer.w), ptr(layer.bias), ptr(resid), ptr(out), B, L, layer.cin,
+                                    layer.taps, layer.dil, layer.cout, layer.kpad, int(self.cfg.pad_reflect),
+                                    float(pre_slope), float(scale), stream_ptr()), "adv_conv1d_bf16")
+        self.launches += 1
+        return out
+
+    @torch.no_grad()
+    def forward_padded(self, mel):
+        """mel [B, 80, T] fp32 -> waveform [B, (T + 2*pad) * prod(upsample_factors)] fp32."""
+        cfg = self.cfg
+        mel = mel.to(self.dev, torch.float32).contiguous()
+        B, C, T = mel.shape
+        pad = cfg.inference_padding
+        L = T + 2 * pad
+        x = torch.empty((B, L, C), dtype=torch.bfloat16, device=self.dev)
+        check(lib().adv_mel_to_channels_last(ptr(mel), B, C, T, pad, C, ptr(x), stream_ptr()), "adv_mel_to_channels_last")
+        o = self._conv(x, self.conv_pre, B, L)
+        for (up, s), stage in zip(self.ups, self.blocks):
+            o = self._conv(o, up, B, L, pre_slope=LRELU_SLOPE)       # [B][L][s*Cout] == [B][L*s][Cout]
+            L, ch = L * s, up.cout // s
+            o = o.view(B, L, ch)
+            outs = []
+            for branch in stage:
+                xb = o
+                for c1, c2 in branch:
+                    xt = self._conv(xb, c1, B, L, pre_slope=LRELU_SLOPE)
+                    xb = self._conv(xt, c2, B, L, pre_slope=LRELU_SLOPE, resid=xb)
+                outs.append(xb)
+            o = torch.empty_like(outs[0])
+            check(lib().adv_avg3_bf16(ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), outs[0].numel(), ptr(o), stream_ptr()),
+                  "adv_avg3_bf16")
+        wav = torch.empty((B, L), dtype=torch.float32, device=self.dev)
+        check(lib().adv_post_conv_tanh(ptr(o), ptr(self.post_w), ptr(self.post_b), B, L, o.shape[2],
+                                       self.post_w.shape[0], 0.01, int(cfg.pad_reflect), ptr(wav), stream_ptr()),
+              "adv_post_conv_tanh")
+        return wav
+
+    def decode_batch(self, spectrogram):
+        """[B, 80, T] (or [80, T]) -> [B, 1, samples] like SpeechBrain's HIFIGAN.decode_batch."""
+        if spectrogram.dim() == 2:
+            spectrogram = spectrogram.unsqueeze(0)
+        return self.forward_padded(spectrogram).unsqueeze(1)
+
+    @staticmethod
+    def flops_per_clip(T, cfg=HifiganConfig):
+        """Dense MACs*2 of the generator for a T-frame mel."""
+        L = T + 2 * cfg.inference_padding
+        ch = cfg.upsample_initial_channel
+        fl = 2 * L * ch * cfg.in_channels * 7
+        for s, k in zip(cfg.upsample_factors, cfg.upsample_kernel_sizes):
+            fl += 2 * L * ch * (ch // 2) * k
+            L, ch = L * s, ch // 2
+            for ks, dils in zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes):
+                fl += 2 * len(dils) * 2 * L * ch * ch * ks
+        return fl + 2 * L * ch * cfg.conv_post_kernel

@@ -1,0 +1,114 @@
+"""Mel front-end on the tensor-core path.
+
+``MelSpectrogram`` mirrors ``torchaudio.transforms.MelSpectrogram`` as the reference constructs it
+(audioprocessor.py:38-44: hann(win_length) window, centre/reflect, power 2, HTK scale, no norm) and as
+SpeechBrain's ``mel_spectogram`` configures it for the vocoder (hifigan.py:163-178: slaney scale and
+norm, power 1, f_max 8000, followed by ``log(clamp(x, 1e-5))``).
+
+Pipeline: ``adv_stft`` (hann window, spectrum only) -> ``adv_mel_project``: |X|^power and the
+[F x n_mels] filterbank contraction as a 3xTF32 split GEMM on tcgen05 with fp32 TMEM accumulation
+(fp32-level accuracy; plain bf16/tf32 would miss the 1e-4 parity gate), log-compress in the epilogue.
+The filterbank itself is a constant built once on the host with the same formulas torchaudio uses.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+from ._lib import check, lib, ptr, stream_ptr
+
+
+def _hz_to_mel(f, scale):
+    if scale == "htk":
+        return 2595.0 * math.log10(1.0 + f / 700.0)
+    f_sp = 200.0 / 3
+    if f >= 1000.0:
+        return 15.0 + math.log(f / 1000.0) / (math.log(6.4) / 27.0)
+    return f / f_sp
+
+
+def _mel_to_hz(m, scale):
+    if scale == "htk":
+        return 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    f_sp = 200.0 / 3
+    freqs = f_sp * m
+    log_t = m >= 15.0
+    logstep = math.log(6.4) / 27.0
+    return torch.where(log_t, 1000.0 * torch.exp(logstep * (m - 15.0)), freqs)
+
+
+def melscale_fbanks(n_freqs, f_min, f_max, n_mels, sample_rate, norm=None, mel_scale="htk"):
+    """[n_freqs, n_mels] triangular filterbank, same construction as torchaudio.functional.melscale_fbanks."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_pts = torch.linspace(_hz_to_mel(f_min, mel_scale), _hz_to_mel(f_max, mel_scale), n_mels + 2)
+    f_pts = _mel_to_hz(m_pts, mel_scale)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    fb = torch.clamp(torch.min(down, up), min=0.0)
+    if norm == "slaney":
+        fb = fb * (2.0 / (f_pts[2:n_mels + 2] - f_pts[:n_mels])).unsqueeze(0)
+    return fb
+
+
+class MelSpectrogram:
+    def __init__(self, sample_rate=16000, n_fft=400, hop_length=None, win_length=None, n_mels=128, f_min=0.0,
+                 f_max=None, power=2.0, norm=None, mel_scale="htk", log_compress=False, clip=1e-5):
+        self.sample_rate, self.n_fft = sample_rate, n_fft
+        self.win_length = win_length if win_length is not None else n_fft
+        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
+        self.n_mels, self.power = n_mels, float(power)
+        self.log_compress, self.clip = bool(log_compress), float(clip)
+        f_max = float(sample_rate // 2) if f_max is None else float(f_max)
+        self.fb = melscale_fbanks(n_fft // 2 + 1, float(f_min), f_max, n_mels, sample_rate, norm, mel_scale)
+        self.window = torch.hann_window(self.win_length)
+        self._dev = None
+
+    def _tables(self, dev):
+        if self._dev != dev:
+            F = self.n_fft // 2 + 1
+            nm = 64 if self.n_mels <= 64 else (80 if self.n_mels <= 80 else 128)
+            if self.n_mels > 128:
+                raise NotImplementedError("n_mels > 128")
+            kpad = (F + 31) // 32 * 32
+            fbt = torch.zeros(nm, kpad)
+            fbt[:self.n_mels, :F] = self.fb.t()
+            hi = (fbt.view(torch.int32) & -8192).view(torch.float32)   # tf32-representable part (low 13 bits cleared)
+            self._hi, self._lo = hi.to(dev).contiguous(), (fbt - hi).to(dev).contiguous()
+            self._kpad, self._dev = kpad, dev
+        return self._hi, self._lo, self._kpad
+
+    def __call__(self, waveform):
+        shape = waveform.shape
+        wav = waveform.reshape(-1, shape[-1])
+        X, _, _ = ops.stft(wav, self.n_fft, self.hop_length, self.win_length, window=self.window, want_mag=False,
+                           want_phase=False)
+        B, F, T = X.shape
+        hi, lo, kpad = self._tables(X.device)
+        out = torch.empty((B, self.n_mels, T), dtype=torch.float32, device=X.device)
+        # X is a [B,F,T] view of frame-major memory: hand the kernel the [B*T][F] rows
+        check(lib().adv_mel_project(ptr(X), B * T, T, F, ptr(hi), ptr(lo), kpad, self.n_mels, self.power,
+                                    int(self.log_compress), self.clip, ptr(out), stream_ptr()), "adv_mel_project")
+        return out.reshape(*shape[:-1], self.n_mels, T)
+
+
+def mel_spectogram(sample_rate, hop_length, win_length, n_fft, n_mels, f_min, f_max, power, normalized,
+                   min_max_energy_norm, norm, mel_scale, compression, audio, return_energy=False):
+    """SpeechBrain ``lobes.models.FastSpeech2.mel_spectogram`` as hifigan.py:163-178 calls it.  Returns
+    ``(mel, rmse)``; the reference discards the second value (per-frame L2 norm of the uncompressed mel), so
+    it is only computed - by a second projection without the log epilogue - when ``return_energy`` is set."""
+    if normalized:
+        raise NotImplementedError("normalized=True is not used by the reference")
+    tr = MelSpectrogram(sample_rate, n_fft, hop_length, win_length, n_mels, f_min, f_max, power, norm, mel_scale,
+                        log_compress=bool(compression), clip=1e-5)
+    mel = tr(audio)
+    rmse = None
+    if return_energy:
+        tr.log_compress = False
+        rmse = torch.linalg.vector_norm(tr(audio), dim=-2)
+        if min_max_energy_norm:
+            rmse = (rmse - rmse.min()) / (rmse.max() - rmse.min())
+    return mel, rmse
