@@ -129,10 +129,11 @@ class HifiganGenerator:
         self.launches = 0
 
     # one implicit-GEMM conv launch
-    def _conv(self, x, layer, B, L, pre_slope=1.0, resid=None, scale=1.0):
+    def _conv(self, x, layer, B, L, pre_slope=1.0, resid=None, scale=1.0, reflect=None):
         out = torch.empty((B, L, layer.cout), dtype=torch.bfloat16, device=self.dev)
         check(lib().adv_conv1d_bf16(ptr(x), ptr(layer.w), ptr(layer.bias), ptr(resid), ptr(out), B, L, layer.cin,
-                                    layer.taps, layer.dil, layer.cout, layer.kpad, int(self.cfg.pad_reflect),
+                                    layer.taps, layer.dil, layer.cout, layer.kpad,
+                                    int(self.cfg.pad_reflect if reflect is None else reflect),
                                     float(pre_slope), float(scale), stream_ptr()), "adv_conv1d_bf16")
         self.launches += 1
         return out
@@ -149,7 +150,8 @@ class HifiganGenerator:
         check(lib().adv_mel_to_channels_last(ptr(mel), B, C, T, pad, C, ptr(x), stream_ptr()), "adv_mel_to_channels_last")
         o = self._conv(x, self.conv_pre, B, L)
         for (up, s), stage in zip(self.ups, self.blocks):
-            o = self._conv(o, up, B, L, pre_slope=LRELU_SLOPE)       # [B][L][s*Cout] == [B][L*s][Cout]
+            # transposed convs never reflect: taps that fall outside the input contribute nothing
+            o = self._conv(o, up, B, L, pre_slope=LRELU_SLOPE, reflect=False)   # [B][L][s*Cout] == [B][L*s][Cout]
             L, ch = L * s, up.cout // s
             o = o.view(B, L, ch)
             outs = []
