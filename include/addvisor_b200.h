@@ -145,15 +145,24 @@ int adv_mel_project(const adv_c64* X, int64_t rows, int T, int F, const float* f
  *   out[b,l,n] = out_scale * ( bias[n] + sum_{tap,ci} w[n][tap*Cin+ci] * lrelu(in[b, l+(tap-center)*dil, ci], pre_slope)
  *                              + resid[b,l,n] )
  * in [B][L][Cin], w [N][Kpad] (Kpad multiple of 64, zero padded), resid / out [B][L][N]; Cin % 8 == 0, N % 16 == 0;
+ * out (raw) and / or out_act = LeakyReLU(act_slope) of the result are written;
  * pad_reflect selects reflect instead of zero padding; pre_slope = 1 disables the input activation.
  * A transposed conv (stride s) is this conv with 3 taps and N = s*Cout phase-stacked weights. */
-int adv_conv1d_bf16(const void* in, const void* w, const float* bias, const void* resid, void* out, int batch, int L,
-                    int Cin, int taps, int dil, int N, int Kpad, int pad_reflect, float pre_slope, float out_scale,
-                    void* stream);
+int adv_conv1d_bf16(const void* in, const void* w, const float* bias, const void* resid, void* out, void* out_act,
+                    int batch, int L, int Cin, int taps, int dil, int N, int Kpad, int pad_reflect, float pre_slope,
+                    float act_slope, float out_scale, void* stream);
+/* Same contraction on the production pipeline: operands fetched by TMA (3-D tensor map over [B][L][Cin], the tap
+ * is a row coordinate, zero padding = TMA out-of-bounds fill), warp-specialised producer / MMA / epilogue roles,
+ * persistent CTAs, double-buffered TMEM accumulators.  Zero padding only; Cin = 32 or a multiple of 64;
+ * N % 32 == 0; w [N][taps*Cin] unpadded.  out_raw and / or out_act (LeakyReLU(act_slope) of the result, for the
+ * consuming layer) are written; the input is used as stored (no activation on load). */
+int adv_conv1d_bf16_tma(const void* in, const void* w, const float* bias, const void* resid, void* out_raw,
+                        void* out_act, int batch, int L, int Cin, int taps, int dil, int N, float act_slope,
+                        float out_scale, void* stream);
 /* mel [B][C][T] fp32 -> channels-last bf16 [B][T+2*pad][Cpad], replicate-padded in time (inference_padding) */
 int adv_mel_to_channels_last(const float* mel, int batch, int C, int T, int pad, int Cpad, void* out, void* stream);
-/* MRF average of the three resblock outputs (bf16, n elements) */
-int adv_avg3_bf16(const void* a, const void* b, const void* c, int64_t n, void* out, void* stream);
+/* MRF average of the three resblock outputs (bf16, n elements), then LeakyReLU(act_slope) (1 = identity) */
+int adv_avg3_bf16(const void* a, const void* b, const void* c, int64_t n, float act_slope, void* out, void* stream);
 /* LeakyReLU(slope) -> conv_post (C=32 -> 1, 7 taps, w [taps][C] fp32) -> tanh; out dev float [B][L] */
 int adv_post_conv_tanh(const void* in, const float* w, const float* bias, int batch, int L, int C, int taps, float slope,
                        int pad_reflect, float* out, void* stream);

@@ -1,0 +1,338 @@
+// Warp-specialised, TMA-fed, persistent tcgen05 implicit-GEMM conv1d (bf16, channels-last) for sm_100a.
+//
+// This is the production path of the HiFi-GAN generator's convolutions (the first-generation kernel in
+// gemm_kernels.cu gathers its operands with ordinary loads and remains the fallback for reflect padding
+// and odd channel counts).  Reference call site: hifi_gan.decode_batch, hifigan.py:180.
+//
+//   D[128 positions][BN channels] (+)= A[128][taps*Cin] * W[BN][taps*Cin]^T        fp32 in TMEM
+//
+// * A comes straight from the channels-last activation [B][L][Cin] through a 3-D tensor map
+//   (box = BK channels x 128 positions x 1 clip): a tap is just a shifted row coordinate, and rows
+//   before 0 / past L are zero-filled by the TMA unit = the conv's zero padding, per clip.
+// * W [N][taps*Cin] through a 2-D tensor map (box = BK x BN).  Both land in the canonical K-major
+//   128-byte (Cin >= 64) or 64-byte (Cin = 32) swizzled layout that tcgen05.mma reads.
+// * Roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue
+//   (TMEM -> registers -> +bias, +residual -> raw bf16 and / or LeakyReLU'd bf16 stores).
+//   STAGES-deep full/empty mbarrier ring between producer and MMA; two TMEM accumulator buffers so
+//   the epilogue of tile i overlaps the MMAs of tile i+1; CTAs are persistent over a static tile list.
+// * LeakyReLU is applied by the PRODUCING layer's epilogue (it can write the activated tensor next
+//   to / instead of the raw one), so consumers load pure TMA tiles.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+#include <unordered_map>
+#include "adv_internal.cuh"
+#include "umma.cuh"
+
+namespace adv {
+
+using namespace umma;
+
+constexpr int kConvThreads = 192;  // 6 warps: producer, mma, 4 x epilogue
+
+struct ConvTmaArgs {
+    const float* bias;            // [N] or null
+    const __nv_bfloat16* resid;   // [B][L][N] or null
+    __nv_bfloat16* out_raw;       // [B][L][N] or null
+    __nv_bfloat16* out_act;       // [B][L][N] or null: LeakyReLU(act_slope) of the result
+    int B, L, Cin, taps, dil, center, N;
+    int tiles_l, tiles_n;         // tiles per clip along L, tiles along N
+    float act_slope, out_scale;
+};
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// K-major descriptor for 128-byte (BK = 64) or 64-byte (BK = 32) swizzled rows
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
+    constexpr uint32_t row_bytes = BK * 2;
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((8 * row_bytes) >> 4) << 32;         // stride between 8-row groups
+    d |= (uint64_t)1 << 46;                              // Blackwell descriptor version
+    d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;     // SWIZZLE_128B / SWIZZLE_64B
+    return d;
+}
+
+template <int BN, int BK, int STAGES>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv1d_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, ConvTmaArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kABytes = 128 * BK * 2, kBBytes = BN * BK * 2, kStage = kABytes + kBBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * kStage);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    constexpr uint32_t kCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            bar_init(&full[s], 1);
+            bar_init(&empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            bar_init(&tfull[i], 1);
+            bar_init(&tempty[i], 4);
+        }
+        bar_init_fence();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kCols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int cblocks = a.Cin / BK;
+    const int nkb = a.taps * cblocks;
+    const long total_tiles = (long)a.B * a.tiles_l * a.tiles_n;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int tn = (int)(tile % a.tiles_n);
+                const long tl = tile / a.tiles_n;
+                const int b = (int)(tl / a.tiles_l), l0 = (int)(tl % a.tiles_l) * 128;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    bar_wait(&empty[s], ph ^ 1);
+                    bar_expect_tx(&full[s], kStage);
+                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                    unsigned char* sA = smem + s * kStage;
+                    tma_load_3d(sA, &map_a, &full[s], cb * BK, l0 + (tap - a.center) * a.dil, b);
+                    tma_load_2d(sA + kABytes, &map_w, &full[s], kb * BK, tn * BN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, BN);
+            uint32_t it = 0, tcount = 0;
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+                bar_wait(&tempty[ab], aph ^ 1);  // the epilogue has drained this accumulator buffer
+                fence_after_sync();
+                const uint32_t tmem_d = tmem_base + ab * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    bar_wait(&full[s], ph);
+                    fence_after_sync();
+                    const uint32_t sA = smem_addr(smem + s * kStage);
+                    const uint64_t da = make_desc_k<BK>(sA), db = make_desc_k<BK>(sA + kABytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        mma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    mma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+                }
+                mma_commit(&tfull[ab]);     // accumulator complete
+            }
+        }
+    } else {
+        // ------------------------------ epilogue (4 warps) ------------------------------
+        const int quad = warp & 3;  // TMEM lanes 32*quad .. 32*quad+31 are the ones this warp may read
+        uint32_t tcount = 0;
+        for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int tn = (int)(tile % a.tiles_n);
+            const long tl = tile / a.tiles_n;
+            const int b = (int)(tl / a.tiles_l), l0 = (int)(tl % a.tiles_l) * 128;
+            const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+            bar_wait(&tfull[ab], aph);
+            fence_after_sync();
+            const int l = l0 + quad * 32 + lane;
+            const bool row_ok = l < a.L;
+            const size_t rowoff = ((size_t)b * a.L + l) * a.N + (size_t)tn * BN;
+            const uint32_t trow = tmem_base + ab * BN + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 8) {
+                float v[8];
+                tmem_ld8(trow + c0, v);
+                if (row_ok) {
+                    const int n = tn * BN + c0;
+                    if (a.bias != nullptr) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
+                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                    }
+                    if (a.resid != nullptr) {
+                        const int4 r = __ldg(reinterpret_cast<const int4*>(a.resid + rowoff + c0));
+                        const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = __bfloat1622float2(rp[j]);
+                            v[2 * j] += f.x;
+                            v[2 * j + 1] += f.y;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
+                    if (a.out_raw != nullptr) {
+                        int4 o;
+                        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        *reinterpret_cast<int4*>(a.out_raw + rowoff + c0) = o;
+                    }
+                    if (a.out_act != nullptr) {
+                        int4 o;
+                        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float x0 = v[2 * j], x1 = v[2 * j + 1];
+                            op[j] = __floats2bfloat162_rn(x0 > 0.f ? x0 : x0 * a.act_slope, x1 > 0.f ? x1 : x1 * a.act_slope);
+                        }
+                        *reinterpret_cast<int4*>(a.out_act + rowoff + c0) = o;
+                    }
+                }
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) bar_arrive(&tempty[ab]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kCols);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <class K>
+static int set_smem_attr2(K kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, size_t> high;
+    if (bytes > 227 * 1024) return ADV_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = high[reinterpret_cast<const void*>(kernel)];
+    if (bytes > cur) {
+        ADV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return ADV_OK;
+}
+
+template <int BN, int BK, int STAGES>
+static int launch_conv_tma(const CUtensorMap& ma, const CUtensorMap& mw, ConvTmaArgs& a, cudaStream_t s) {
+    constexpr size_t smem = (size_t)STAGES * (128 * BK * 2 + BN * BK * 2) + 256 + 1024;
+    int rc = set_smem_attr2(conv1d_tma_kernel<BN, BK, STAGES>, smem);
+    if (rc != ADV_OK) return rc;
+    a.tiles_n = a.N / BN;
+    const long tiles = (long)a.B * a.tiles_l * a.tiles_n;
+    const int per_sm = smem <= 110 * 1024 && 2 * BN <= 256 ? 2 : 1;
+    long grid = (long)num_sms() * per_sm;
+    if (grid > tiles) grid = tiles;
+    conv1d_tma_kernel<BN, BK, STAGES><<<(unsigned)grid, kConvThreads, smem, s>>>(ma, mw, a);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+}  // namespace adv
+
+using namespace adv;
+
+extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* bias, const void* resid, void* out_raw,
+                                   void* out_act, int batch, int L, int Cin, int taps, int dil, int N, float act_slope,
+                                   float out_scale, void* stream) {
+    if (!in || !w || (!out_raw && !out_act) || batch <= 0 || L <= 0 || taps <= 0 || dil <= 0 || N <= 0) return ADV_ERR_INVALID;
+    if ((taps & 1) == 0 || N % 32 != 0 || !(Cin == 32 || Cin % 64 == 0)) return ADV_ERR_SHAPE;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return ADV_ERR_UNSUPPORTED;
+    const int BK = Cin == 32 ? 32 : 64;
+    const int BN = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
+    const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+
+    CUtensorMap ma, mw;
+    {   // activations [B][L][Cin]: dims innermost first
+        cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)L, (cuuint64_t)batch};
+        cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)L * Cin * 2};
+        cuuint32_t box[3] = {(cuuint32_t)BK, 128, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(in), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return ADV_ERR_INVALID;
+    }
+    {   // weights [N][taps*Cin]
+        cuuint64_t dims[2] = {(cuuint64_t)taps * Cin, (cuuint64_t)N};
+        cuuint64_t strides[1] = {(cuuint64_t)taps * Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        if (enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return ADV_ERR_INVALID;
+    }
+    ConvTmaArgs a;
+    a.bias = bias;
+    a.resid = (const __nv_bfloat16*)resid;
+    a.out_raw = (__nv_bfloat16*)out_raw;
+    a.out_act = (__nv_bfloat16*)out_act;
+    a.B = batch; a.L = L; a.Cin = Cin; a.taps = taps; a.dil = dil; a.center = (taps - 1) / 2; a.N = N;
+    a.tiles_l = (L + 127) / 128; a.tiles_n = 0;
+    a.act_slope = act_slope; a.out_scale = out_scale;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (BK == 64) {
+        switch (BN) {
+            case 256: return launch_conv_tma<256, 64, 4>(ma, mw, a, s);
+            case 128: return launch_conv_tma<128, 64, 3>(ma, mw, a, s);
+            case 64: return launch_conv_tma<64, 64, 4>(ma, mw, a, s);
+            default: return launch_conv_tma<32, 64, 4>(ma, mw, a, s);
+        }
+    }
+    switch (BN) {
+        case 256: return launch_conv_tma<256, 32, 4>(ma, mw, a, s);
+        case 128: return launch_conv_tma<128, 32, 4>(ma, mw, a, s);
+        case 64: return launch_conv_tma<64, 32, 4>(ma, mw, a, s);
+        default: return launch_conv_tma<32, 32, 4>(ma, mw, a, s);
+    }
+}

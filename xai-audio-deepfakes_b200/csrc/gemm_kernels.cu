@@ -32,7 +32,9 @@ struct ConvArgs {
     const __nv_bfloat16* w;      // [N][Kpad], k = tap*Cin + ci
     const float* bias;           // [N] or null
     const __nv_bfloat16* resid;  // [B][L][N] or null
-    __nv_bfloat16* out;          // [B][L][N]
+    __nv_bfloat16* out;          // [B][L][N] or null
+    __nv_bfloat16* out_act;      // [B][L][N] or null: LeakyReLU(act_slope) of the result
+    float act_slope;
     int B, L, Cin, taps, dil, center, N, Kreal, Kpad, pad_reflect;
     float pre_slope;             // LeakyReLU slope applied to the input on load (1 = identity)
     float out_scale;
@@ -168,11 +170,25 @@ conv1d_tc_kernel(ConvArgs a) {
                     v[2 * j + 1] += f.y;
                 }
             }
-            int4 o;
-            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[2 * j] * a.out_scale, v[2 * j + 1] * a.out_scale);
-            *reinterpret_cast<int4*>(a.out + (size_t)m * a.N + n) = o;
+            for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
+            if (a.out != nullptr) {
+                int4 o;
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                *reinterpret_cast<int4*>(a.out + (size_t)m * a.N + n) = o;
+            }
+            if (a.out_act != nullptr) {
+                int4 o;
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float x0 = v[2 * j], x1 = v[2 * j + 1];
+                    op[j] = __floats2bfloat162_rn(x0 > 0.f ? x0 : x0 * a.act_slope, x1 > 0.f ? x1 : x1 * a.act_slope);
+                }
+                *reinterpret_cast<int4*>(a.out_act + (size_t)m * a.N + n) = o;
+            }
         }
     }
     fence_before_sync();
@@ -323,10 +339,12 @@ __global__ void mel_to_cl_kernel(const float* __restrict__ mel, int B, int C, in
 }
 // out = (a + b + c) / 3 (MRF average, HifiganGenerator.forward)
 __global__ void avg3_kernel(const __nv_bfloat162* __restrict__ a, const __nv_bfloat162* __restrict__ b,
-                            const __nv_bfloat162* __restrict__ c, long n2, __nv_bfloat162* __restrict__ out) {
+                            const __nv_bfloat162* __restrict__ c, long n2, float slope, __nv_bfloat162* __restrict__ out) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long)gridDim.x * blockDim.x) {
         const float2 x = __bfloat1622float2(a[i]), y = __bfloat1622float2(b[i]), z = __bfloat1622float2(c[i]);
-        out[i] = __floats2bfloat162_rn((x.x + y.x + z.x) * (1.0f / 3.0f), (x.y + y.y + z.y) * (1.0f / 3.0f));
+        // the mean is rounded to bf16 first (it is the tensor the reference would hold), then activated
+        const float2 m = __bfloat1622float2(__floats2bfloat162_rn((x.x + y.x + z.x) * (1.0f / 3.0f), (x.y + y.y + z.y) * (1.0f / 3.0f)));
+        out[i] = __floats2bfloat162_rn(m.x > 0.f ? m.x : m.x * slope, m.y > 0.f ? m.y : m.y * slope);
     }
 }
 // conv_post: LeakyReLU(slope) -> conv1d(C -> 1, taps) -> tanh; in channels-last bf16, out fp32 [B][L]
@@ -400,10 +418,10 @@ using namespace adv;
 
 extern "C" {
 
-int adv_conv1d_bf16(const void* in, const void* w, const float* bias, const void* resid, void* out, int batch, int L,
-                    int Cin, int taps, int dil, int N, int Kpad, int pad_reflect, float pre_slope, float out_scale,
-                    void* stream) {
-    if (!in || !w || !out || batch <= 0 || L <= 0 || Cin <= 0 || taps <= 0 || dil <= 0 || N <= 0) return ADV_ERR_INVALID;
+int adv_conv1d_bf16(const void* in, const void* w, const float* bias, const void* resid, void* out, void* out_act,
+                    int batch, int L, int Cin, int taps, int dil, int N, int Kpad, int pad_reflect, float pre_slope,
+                    float act_slope, float out_scale, void* stream) {
+    if (!in || !w || (!out && !out_act) || batch <= 0 || L <= 0 || Cin <= 0 || taps <= 0 || dil <= 0 || N <= 0) return ADV_ERR_INVALID;
     if (Cin % 8 != 0 || N % 16 != 0 || Kpad % 64 != 0 || Kpad < taps * Cin || (taps & 1) == 0) return ADV_ERR_SHAPE;
     ConvArgs a;
     a.in = (const __nv_bfloat16*)in;
@@ -411,6 +429,8 @@ int adv_conv1d_bf16(const void* in, const void* w, const float* bias, const void
     a.bias = bias;
     a.resid = (const __nv_bfloat16*)resid;
     a.out = (__nv_bfloat16*)out;
+    a.out_act = (__nv_bfloat16*)out_act;
+    a.act_slope = act_slope;
     a.B = batch; a.L = L; a.Cin = Cin; a.taps = taps; a.dil = dil; a.center = (taps - 1) / 2;
     a.N = N; a.Kreal = taps * Cin; a.Kpad = Kpad; a.pad_reflect = pad_reflect;
     a.pre_slope = pre_slope; a.out_scale = out_scale;
@@ -456,12 +476,12 @@ int adv_mel_to_channels_last(const float* mel, int batch, int C, int T, int pad,
     return ADV_OK;
 }
 
-int adv_avg3_bf16(const void* a, const void* b, const void* c, int64_t n, void* out, void* stream) {
+int adv_avg3_bf16(const void* a, const void* b, const void* c, int64_t n, float act_slope, void* out, void* stream) {
     if (!a || !b || !c || !out || n <= 0 || (n & 1)) return ADV_ERR_INVALID;
     int gx = (int)((n / 2 + 255) / 256);
     if (gx > 148 * 16) gx = 148 * 16;
     avg3_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat162*)a, (const __nv_bfloat162*)b,
-                                                     (const __nv_bfloat162*)c, n / 2, (__nv_bfloat162*)out);
+                                                     (const __nv_bfloat162*)c, n / 2, act_slope, (__nv_bfloat162*)out);
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }

@@ -100,15 +100,26 @@ class _Layer:
         self.dil = dil
         gw, self.kpad = _gemm_weight(w)
         self.w = gw.to(dev)
+        # unpadded [Cout][taps*Cin] for the TMA pipeline (its tensor map walks K in blocks of 64 / 32 channels)
+        self.tma_ok = (self.cin == 32 or self.cin % 64 == 0) and self.cout % 32 == 0
+        self.w_tma = (w.permute(0, 2, 1).reshape(self.cout, -1).to(torch.bfloat16).contiguous().to(dev)
+                      if self.tma_ok else None)
         self.bias = bias.float().to(dev).contiguous()
 
 
 class HifiganGenerator:
-    """``decode_batch(mel[B,80,T]) -> waveform [B,1,(T+10)*256]`` (SpeechBrain HIFIGAN.decode_batch)."""
+    """``decode_batch(mel[B,80,T]) -> waveform [B,1,(T+10)*256]`` (SpeechBrain HIFIGAN.decode_batch).
 
-    def __init__(self, weights=None, cfg=HifiganConfig, device=None, seed=0):
+    ``pipeline="tma"`` (default with zero padding): TMA-fed warp-specialised persistent conv kernel; LeakyReLU is
+    applied by the producing layer's epilogue.  ``pipeline="gather"``: first-generation kernel (operands gathered
+    with ordinary loads, activation on load) - required for reflect padding."""
+
+    def __init__(self, weights=None, cfg=HifiganConfig, device=None, seed=0, pipeline=None):
         self.cfg = cfg
         self.dev = device or ops._dev()
+        self.pipeline = pipeline or ("gather" if cfg.pad_reflect else "tma")
+        if self.pipeline == "tma" and cfg.pad_reflect:
+            raise ValueError("the TMA pipeline implements zero padding only")
         W = weights if weights is not None else init_weights(cfg, seed)
         self.master = W
         L = lambda name, dil=1: _Layer(W[name + ".weight"], W[name + ".bias"], dil, self.dev)
@@ -128,27 +139,39 @@ class HifiganGenerator:
         self.post_b = W["conv_post.bias"].float().to(self.dev)
         self.launches = 0
 
-    # one implicit-GEMM conv launch
-    def _conv(self, x, layer, B, L, pre_slope=1.0, resid=None, scale=1.0, reflect=None):
-        out = torch.empty((B, L, layer.cout), dtype=torch.bfloat16, device=self.dev)
-        check(lib().adv_conv1d_bf16(ptr(x), ptr(layer.w), ptr(layer.bias), ptr(resid), ptr(out), B, L, layer.cin,
-                                    layer.taps, layer.dil, layer.cout, layer.kpad,
-                                    int(self.cfg.pad_reflect if reflect is None else reflect),
-                                    float(pre_slope), float(scale), stream_ptr()), "adv_conv1d_bf16")
-        self.launches += 1
-        return out
+    def _buf(self, B, L, C):
+        return torch.empty((B, L, C), dtype=torch.bfloat16, device=self.dev)
 
-    @torch.no_grad()
-    def forward_padded(self, mel):
-        """mel [B, 80, T] fp32 -> waveform [B, (T + 2*pad) * prod(upsample_factors)] fp32."""
-        cfg = self.cfg
-        mel = mel.to(self.dev, torch.float32).contiguous()
-        B, C, T = mel.shape
-        pad = cfg.inference_padding
-        L = T + 2 * pad
-        x = torch.empty((B, L, C), dtype=torch.bfloat16, device=self.dev)
-        check(lib().adv_mel_to_channels_last(ptr(mel), B, C, T, pad, C, ptr(x), stream_ptr()), "adv_mel_to_channels_last")
-        o = self._conv(x, self.conv_pre, B, L)
+    # first-generation kernel: operands gathered with plain loads, optional LeakyReLU on load
+    def _conv(self, x, layer, B, L, pre_slope=1.0, resid=None, scale=1.0, reflect=None, want_raw=True, act_slope=None):
+        out = self._buf(B, L, layer.cout) if want_raw else None
+        act = self._buf(B, L, layer.cout) if act_slope is not None else None
+        check(lib().adv_conv1d_bf16(ptr(x), ptr(layer.w), ptr(layer.bias), ptr(resid), ptr(out), ptr(act), B, L,
+                                    layer.cin, layer.taps, layer.dil, layer.cout, layer.kpad,
+                                    int(self.cfg.pad_reflect if reflect is None else reflect), float(pre_slope),
+                                    float(act_slope if act_slope is not None else 1.0), float(scale), stream_ptr()),
+              "adv_conv1d_bf16")
+        self.launches += 1
+        return (out, act) if act_slope is not None else out
+
+    # production kernel: TMA + warp specialisation; input is used as stored
+    def _conv_tma(self, x, layer, B, L, resid=None, want_raw=True, act_slope=None):
+        out = self._buf(B, L, layer.cout) if want_raw else None
+        act = self._buf(B, L, layer.cout) if act_slope is not None else None
+        check(lib().adv_conv1d_bf16_tma(ptr(x), ptr(layer.w_tma), ptr(layer.bias), ptr(resid), ptr(out), ptr(act), B, L,
+                                        layer.cin, layer.taps, layer.dil, layer.cout,
+                                        float(act_slope if act_slope is not None else 1.0), 1.0, stream_ptr()),
+              "adv_conv1d_bf16_tma")
+        self.launches += 1
+        return out, act
+
+    def _avg3(self, outs, slope=1.0):
+        o = torch.empty_like(outs[0])
+        check(lib().adv_avg3_bf16(ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), outs[0].numel(), float(slope), ptr(o),
+                                  stream_ptr()), "adv_avg3_bf16")
+        return o
+
+    def _stages_gather(self, o, B, L):
         for (up, s), stage in zip(self.ups, self.blocks):
             # transposed convs never reflect: taps that fall outside the input contribute nothing
             o = self._conv(o, up, B, L, pre_slope=LRELU_SLOPE, reflect=False)   # [B][L][s*Cout] == [B][L*s][Cout]
@@ -161,9 +184,48 @@ class HifiganGenerator:
                     xt = self._conv(xb, c1, B, L, pre_slope=LRELU_SLOPE)
                     xb = self._conv(xt, c2, B, L, pre_slope=LRELU_SLOPE, resid=xb)
                 outs.append(xb)
-            o = torch.empty_like(outs[0])
-            check(lib().adv_avg3_bf16(ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), outs[0].numel(), ptr(o), stream_ptr()),
-                  "adv_avg3_bf16")
+            o = self._avg3(outs)
+        return o, L
+
+    def _stages_tma(self, o, B, L):
+        """``o`` = raw conv_pre output.  Every tensor a conv consumes was written already LeakyReLU'd by its
+        producer; raw copies exist only where a residual or the MRF average needs them."""
+        n_stage = len(self.ups)
+        o_act = None
+        for si, ((up, s), stage) in enumerate(zip(self.ups, self.blocks)):
+            if si == 0:   # input is conv_pre's raw output: activation on load, first-generation kernel
+                x_raw, x_act = self._conv(o, up, B, L, pre_slope=LRELU_SLOPE, reflect=False, act_slope=LRELU_SLOPE)
+            else:
+                x_raw, x_act = self._conv_tma(o_act, up, B, L, act_slope=LRELU_SLOPE)
+            L, ch = L * s, up.cout // s
+            x_raw, x_act = x_raw.view(B, L, ch), x_act.view(B, L, ch)
+            outs = []
+            for branch in stage:
+                xb_raw, xb_act = x_raw, x_act
+                for d, (c1, c2) in enumerate(branch):
+                    _, xt_act = self._conv_tma(xb_act, c1, B, L, want_raw=False, act_slope=LRELU_SLOPE)
+                    last = d == len(branch) - 1
+                    xb_raw, xb_act = self._conv_tma(xt_act, c2, B, L, resid=xb_raw,
+                                                    act_slope=None if last else LRELU_SLOPE)
+                outs.append(xb_raw)
+            if si == n_stage - 1:
+                o = self._avg3(outs)                       # raw: conv_post applies its own LeakyReLU(0.01)
+            else:
+                o_act = self._avg3(outs, LRELU_SLOPE)      # next stage's transposed conv reads it activated
+        return o, L
+
+    @torch.no_grad()
+    def forward_padded(self, mel):
+        """mel [B, 80, T] fp32 -> waveform [B, (T + 2*pad) * prod(upsample_factors)] fp32."""
+        cfg = self.cfg
+        mel = mel.to(self.dev, torch.float32).contiguous()
+        B, C, T = mel.shape
+        pad = cfg.inference_padding
+        L = T + 2 * pad
+        x = self._buf(B, L, C)
+        check(lib().adv_mel_to_channels_last(ptr(mel), B, C, T, pad, C, ptr(x), stream_ptr()), "adv_mel_to_channels_last")
+        o = self._conv(x, self.conv_pre, B, L)
+        o, L = (self._stages_tma if self.pipeline == "tma" else self._stages_gather)(o, B, L)
         wav = torch.empty((B, L), dtype=torch.float32, device=self.dev)
         check(lib().adv_post_conv_tanh(ptr(o), ptr(self.post_w), ptr(self.post_b), B, L, o.shape[2],
                                        self.post_w.shape[0], 0.01, int(cfg.pad_reflect), ptr(wav), stream_ptr()),
