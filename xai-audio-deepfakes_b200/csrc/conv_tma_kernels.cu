@@ -157,52 +157,76 @@ conv1d_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const long tl = tile / a.tiles_n;
             const int b = (int)(tl / a.tiles_l), l0 = (int)(tl % a.tiles_l) * 128;
             const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
-            bar_wait(&tfull[ab], aph);
-            fence_after_sync();
             const int l = l0 + quad * 32 + lane;
             const bool row_ok = l < a.L;
             const size_t rowoff = ((size_t)b * a.L + l) * a.N + (size_t)tn * BN;
+            const bool has_res = a.resid != nullptr && row_ok;
+            // the residual row does not depend on the MMAs: fetch its first 32 columns while they finish
+            int4 rnext[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                rnext[j] = has_res ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff) + j) : make_int4(0, 0, 0, 0);
+            bar_wait(&tfull[ab], aph);
+            fence_after_sync();
             const uint32_t trow = tmem_base + ab * BN + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 8) {
-                float v[8];
-                tmem_ld8(trow + c0, v);
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                int4 rcur[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+                if (c0 + 32 < BN) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        rnext[j] = has_res ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff + c0 + 32) + j)
+                                           : make_int4(0, 0, 0, 0);
+                }
+                float v[32];
+                tmem_ld32(trow + c0, v);
                 if (row_ok) {
                     const int n = tn * BN + c0;
                     if (a.bias != nullptr) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
-                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                    }
-                    if (a.resid != nullptr) {
-                        const int4 r = __ldg(reinterpret_cast<const int4*>(a.resid + rowoff + c0));
-                        const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = __bfloat1622float2(rp[j]);
-                            v[2 * j] += f.x;
-                            v[2 * j + 1] += f.y;
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n) + j);
+                            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+                        }
+                    }
+                    if (has_res) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rcur[q]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __bfloat1622float2(rp[j]);
+                                v[8 * q + 2 * j] += f.x;
+                                v[8 * q + 2 * j + 1] += f.y;
+                            }
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] *= a.out_scale;
+                    for (int j = 0; j < 32; ++j) v[j] *= a.out_scale;
                     if (a.out_raw != nullptr) {
-                        int4 o;
-                        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        *reinterpret_cast<int4*>(a.out_raw + rowoff + c0) = o;
+                        for (int q = 0; q < 4; ++q) {
+                            int4 o;
+                            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]);
+                            *(reinterpret_cast<int4*>(a.out_raw + rowoff + c0) + q) = o;
+                        }
                     }
                     if (a.out_act != nullptr) {
-                        int4 o;
-                        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float x0 = v[2 * j], x1 = v[2 * j + 1];
-                            op[j] = __floats2bfloat162_rn(x0 > 0.f ? x0 : x0 * a.act_slope, x1 > 0.f ? x1 : x1 * a.act_slope);
+                        for (int q = 0; q < 4; ++q) {
+                            int4 o;
+                            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float x0 = v[8 * q + 2 * j], x1 = v[8 * q + 2 * j + 1];
+                                op[j] = __floats2bfloat162_rn(x0 > 0.f ? x0 : x0 * a.act_slope, x1 > 0.f ? x1 : x1 * a.act_slope);
+                            }
+                            *(reinterpret_cast<int4*>(a.out_act + rowoff + c0) + q) = o;
                         }
-                        *reinterpret_cast<int4*>(a.out_act + rowoff + c0) = o;
                     }
                 }
             }
@@ -268,7 +292,12 @@ static int launch_conv_tma(const CUtensorMap& ma, const CUtensorMap& mw, ConvTma
     if (rc != ADV_OK) return rc;
     a.tiles_n = a.N / BN;
     const long tiles = (long)a.B * a.tiles_l * a.tiles_n;
-    const int per_sm = smem <= 110 * 1024 && 2 * BN <= 256 ? 2 : 1;
+    // co-resident CTAs per SM: bounded by shared memory, by TMEM columns (512) and by 4
+    int per_sm = (int)((220 * 1024) / smem);
+    const int by_tmem = 512 / (2 * BN < 32 ? 32 : 2 * BN);
+    if (per_sm > by_tmem) per_sm = by_tmem;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
     long grid = (long)num_sms() * per_sm;
     if (grid > tiles) grid = tiles;
     conv1d_tma_kernel<BN, BK, STAGES><<<(unsigned)grid, kConvThreads, smem, s>>>(ma, mw, a);
