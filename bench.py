@@ -283,6 +283,24 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * BATCH * e2e_steps / float(te)
+    # ---- vocoder side path (BASELINE configs[2] geometry, smaller batch): HiFi-GAN on the tcgen05 conv kernels
+    voc = None
+    try:
+        H = pkg.hifigan
+        gen_v = H.HifiganGenerator(H.init_weights(seed=0, std=0.01))
+        vb, vt = 32, 251
+        mel = -4 + 2 * torch.randn(vb, 80, vt, generator=gen, device="cuda")
+        gen_v.decode_batch(mel)
+        t_v = time_loop(lambda i: gen_v.decode_batch(mel), 2) / 2
+        fl = H.HifiganGenerator.flops_per_clip(vt) * vb
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
+        voc = {"workload": f"HiFi-GAN V1 generator, {vb} x 4 s clips (80 x {vt} mel -> 66816 samples), bf16",
+               "clips_per_s": vb / t_v, "tflops": fl / t_v / 1e12, "bound": "tensor", "peak": pk,
+               "frac": fl / t_v / 1e12 / pk, "launches_per_batch": 81}
+        del gen_v, mel
+    except Exception as e:  # the vocoder is a side path: never fail the headline bench on it
+        voc = {"error": repr(e)[:200]}
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -334,6 +352,7 @@ def main():
             "istft": {"GBps": BYTES_ISTFT * BATCH / t_istft / 1e9, "frac": BYTES_ISTFT * BATCH / t_istft / 1e9 / peak,
                       "us": t_istft * 1e6},
         },
+        "vocoder": voc,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "lmac_means": metrics,

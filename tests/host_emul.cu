@@ -116,9 +116,95 @@ int run() {
     return ierr > 2e-6 ? 1 : 0;
 }
 
+// wide 512-point unit (32 lanes x 16 values): same checks
+int run_w512() {
+    const int NF = 512, L = 32;
+    std::vector<float> xa(NF), xb(NF);
+    srand(99);
+    for (int i = 0; i < NF; ++i) {
+        xa[i] = (float)rand() / RAND_MAX - 0.5f;
+        xb[i] = (float)rand() / RAND_MAX - 0.5f;
+    }
+    std::vector<cd> RA(NF / 2 + 1), RB(NF / 2 + 1);
+    for (int k = 0; k <= NF / 2; ++k) {
+        cd sa = 0, sb = 0;
+        for (int n = 0; n < NF; ++n) {
+            cd w = std::polar(1.0, -2.0 * M_PI * (double)((long)k * n % NF) / NF);
+            sa += (double)xa[n] * w;
+            sb += (double)xb[n] * w;
+        }
+        RA[k] = sa;
+        RB[k] = sb;
+    }
+    std::vector<std::vector<float2>> tw(L, std::vector<float2>(16)), V(L, std::vector<float2>(16)), O(L, std::vector<float2>(16));
+    for (int l = 0; l < L; ++l)
+        for (int k1 = 0; k1 < 16; ++k1) {
+            double a = -2.0 * M_PI * (double)(l * k1) / NF;
+            tw[l][k1] = make_float2((float)cos(a), (float)sin(a));
+        }
+    std::vector<float> scratch(w512::SCRATCH);
+    for (int l = 0; l < L; ++l)
+        for (int n1 = 0; n1 < 16; ++n1) V[l][n1] = make_float2(xa[n1 * 32 + l], xb[n1 * 32 + l]);
+    for (int l = 0; l < L; ++l) w512::fwd_cols(V[l].data(), Tw{tw[l].data()});
+    for (int im = 0; im < 2; ++im) {
+        for (int l = 0; l < L; ++l) w512::scr_store_cols(V[l].data(), l, scratch.data(), im);
+        for (int l = 0; l < L; ++l) w512::scr_load_rows(V[l].data(), l, scratch.data(), im);
+    }
+    for (int l = 0; l < L; ++l) w512::fwd_rows_local(V[l].data());
+    O = V;
+    for (int l = 0; l < L; ++l) w512::fwd_rows_combine(V[l].data(), l, O[l ^ 1].data());
+    // split
+    std::vector<std::vector<float2>> send(L, std::vector<float2>(8)), XA(L, std::vector<float2>(9)), XB(L, std::vector<float2>(9));
+    for (int l = 0; l < L; ++l) w512::split_pre(V[l].data(), send[l].data());
+    for (int l = 0; l < L; ++l) w512::split_post(V[l].data(), l, send[w512::partner_row(l)].data(), XA[l].data(), XB[l].data());
+    double err = 0, mx = 0;
+    std::vector<int> seen(NF / 2 + 1, 0);
+    for (int l = 0; l < L; ++l)
+        for (int i = 0; i < 9; ++i) {
+            int b = w512::bin_of(l, i);
+            if (b < 0) continue;
+            if (b > NF / 2) { printf("w512 bin out of range %d (lane %d slot %d)\n", b, l, i); return 1; }
+            seen[b]++;
+            err = fmax(err, std::abs(cd(XA[l][i].x, XA[l][i].y) - RA[b]));
+            err = fmax(err, std::abs(cd(XB[l][i].x, XB[l][i].y) - RB[b]));
+            mx = fmax(mx, std::abs(RA[b]));
+        }
+    for (int k = 0; k <= NF / 2; ++k)
+        if (seen[k] != 1) { printf("w512 bin %d seen %d times\n", k, seen[k]); return 1; }
+    printf("W512 forward+split max err %.3e (max |X| %.3f)\n", err, mx);
+    if (err > 2e-5 * mx) return 1;
+    // merge + inverse
+    for (int l = 0; l < L; ++l)
+        for (int i = 0; i < 9; ++i) {
+            int b = w512::bin_of(l, i);
+            if (b == 0 || b == NF / 2) { XA[l][i].y = 123.0f; XB[l][i].y = -77.0f; }
+            if (b < 0) { XA[l][i] = make_float2(0, 0); XB[l][i] = make_float2(0, 0); }
+        }
+    for (int l = 0; l < L; ++l) w512::merge_pre(V[l].data(), l, XA[l].data(), XB[l].data(), send[l].data());
+    for (int l = 0; l < L; ++l) w512::merge_post(V[l].data(), l, send[w512::partner_row(l)].data());
+    O = V;
+    for (int l = 0; l < L; ++l) w512::inv_rows_combine(V[l].data(), l, O[l ^ 1].data());
+    for (int l = 0; l < L; ++l) w512::inv_rows_local(V[l].data());
+    for (int im = 0; im < 2; ++im) {
+        for (int l = 0; l < L; ++l) w512::scr_store_rows(V[l].data(), l, scratch.data(), im);
+        for (int l = 0; l < L; ++l) w512::scr_load_cols(V[l].data(), l, scratch.data(), im);
+    }
+    for (int l = 0; l < L; ++l) w512::inv_cols(V[l].data(), Tw{tw[l].data()});
+    double ierr = 0;
+    for (int l = 0; l < L; ++l)
+        for (int n1 = 0; n1 < 16; ++n1) {
+            int n = n1 * 32 + l;
+            ierr = fmax(ierr, fabs(V[l][n1].x / NF - xa[n]));
+            ierr = fmax(ierr, fabs(V[l][n1].y / NF - xb[n]));
+        }
+    printf("W512 merge+inverse round-trip max err %.3e\n", ierr);
+    return ierr > 2e-6 ? 1 : 0;
+}
+
 int main() {
     int rc = run<512>();
     rc |= run<1024>();
+    rc |= run_w512();
     printf(rc ? "FAIL\n" : "OK\n");
     return rc;
 }

@@ -364,4 +364,140 @@ ADV_HD void merge1024_post(float2* v, int l, const float2* recv) {
     }
 }
 
+// =============================================================================================
+// "Wide" 512-point unit: a full warp (32 lanes) per FFT, 16 complex values per lane.
+// Half the registers per thread of the 16-lane unit => twice the resident warps for the fused explain
+// kernel.  512 = 16 (in-register radix over n1, n = 32*n1 + lane) x 32 (rows): after the transpose two
+// lanes share a row (r = lane>>1; lane parity h picks the even / odd n2), each runs a radix-16, and one
+// butterfly across the lane pair (shuffle xor 1) finishes the 32-point row transform:
+//     lane (r, h) ends with Z[r + 16*(m + 16h)], m = 0..15.
+// Mirror bins (k, 512-k) live in lanes (r, 0) and (16-r, 1): the two-real-frames split / merge trades
+// 8 values with that partner and every lane ends up owning 8 one-sided bins (lane 1 also the Nyquist).
+// All exchange steps are split pre / post so tests/host_emul.cu can run them lane by lane.
+// =============================================================================================
+namespace w512 {
+constexpr int LANES = 32, E = 16, PITCH = 34, SCRATCH = 16 * PITCH;  // floats of scratch per unit
+constexpr int SLOTS = 9;                                             // one-sided bins per lane (8, +Nyquist on lane 1)
+
+ADV_HD int partner_row(int l) { return 2 * ((16 - (l >> 1)) & 15) + (1 - (l & 1)); }
+// one-sided bin of lane l, slot i (0..8); -1 when empty
+ADV_HD int bin_of(int l, int i) {
+    const int r = l >> 1, h = l & 1;
+    if (i < 8) return h == 0 ? r + 16 * i : ((16 - r) & 15) + 16 * (8 + i);
+    return l == 1 ? 256 : -1;
+}
+
+template <class TwFn>
+ADV_HD void fwd_cols(float2* v, TwFn tw) {
+    fft_inplace<16, -1>(v);
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], tw(k1));
+}
+template <class TwFn>
+ADV_HD void inv_cols(float2* v, TwFn tw) {
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmulc(v[k1], tw(k1));
+    fft_inplace<16, +1>(v);
+}
+ADV_HD void scr_store_cols(const float2* v, int l, float* scr, bool imag) {
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) scr[k1 * PITCH + l] = imag ? v[k1].y : v[k1].x;
+}
+ADV_HD void scr_load_cols(float2* v, int l, const float* scr, bool imag) {
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+        const float x = scr[k1 * PITCH + l];
+        if (imag) v[k1].y = x; else v[k1].x = x;
+    }
+}
+ADV_HD void scr_load_rows(float2* v, int l, const float* scr, bool imag) {
+    const float* p = scr + (l >> 1) * PITCH + (l & 1);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const float x = p[2 * m];
+        if (imag) v[m].y = x; else v[m].x = x;
+    }
+}
+ADV_HD void scr_store_rows(const float2* v, int l, float* scr, bool imag) {
+    float* p = scr + (l >> 1) * PITCH + (l & 1);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) p[2 * m] = imag ? v[m].y : v[m].x;
+}
+// forward rows: radix-16 on the lane's half row, then (with `other` = partner lane's values, xor 1)
+// the radix-2 across the pair
+ADV_HD void fwd_rows_local(float2* v) { fft_inplace<16, -1>(v); }
+ADV_HD void fwd_rows_combine(float2* v, int l, const float2* other) {
+    const bool h = l & 1;
+    static_for<0, 16>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        const float2 e = h ? other[m] : v[m];
+        const float2 o = h ? v[m] : other[m];
+        const float2 t = twmul<32, m, -1>(o);
+        v[m] = h ? csub(e, t) : cadd(e, t);
+    });
+}
+// inverse rows: undo the pair butterfly (needs the partner's values), then radix-16
+ADV_HD void inv_rows_combine(float2* v, int l, const float2* other) {
+    const bool h = l & 1;
+    static_for<0, 16>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        // h = 0: X[m] + X[m+16];  h = 1: (X[m] - X[m+16]) * W_32^{-m}
+        const float2 lo = h ? other[m] : v[m];
+        const float2 hi = h ? v[m] : other[m];
+        v[m] = h ? twmul<32, m, +1>(csub(lo, hi)) : cadd(lo, hi);
+    });
+}
+ADV_HD void inv_rows_local(float2* v) { fft_inplace<16, +1>(v); }
+
+// ---- split: Z (two packed real frames) -> 9 one-sided bins of each frame per lane ---------------------
+ADV_HD void split_pre(const float2* v, float2* send) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) send[j] = v[8 + j];
+}
+ADV_HD void split_post(const float2* v, int l, const float2* recv, float2* xa, float2* xb) {
+    const bool h = l & 1, z = (l >> 1) == 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float2 a, b;
+        if (!h) {  // lane (r,0): bins r + 16 i; mirror came from the partner
+            a = v[i];
+            b = z ? (i == 0 ? v[0] : recv[8 - i]) : recv[7 - i];
+        } else {   // lane (r,1): bins of the partner's row, k2 = 8 + i; own registers hold the mirrors
+            a = recv[i];
+            b = z ? v[8 - i] : v[7 - i];
+        }
+        split_pair(a, b, xa[i], xb[i]);
+    }
+    split_pair(v[0], v[0], xa[8], xb[8]);  // Nyquist: meaningful on lane 1 only
+}
+// ---- merge: two one-sided spectra -> inverse-FFT input layout (C2R semantics on DC / Nyquist) -------
+ADV_HD void merge_pre(float2* v, int l, const float2* ya, const float2* yb, float2* send) {
+    const bool h = l & 1, z = (l >> 1) == 0;
+    float2 za[9], zb[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) merge_pair(ya[i], yb[i], za[i], zb[i]);
+    if (!h) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = za[i];
+        if (z) v[0] = make_float2(ya[0].x, yb[0].x);  // DC
+#pragma unroll
+        for (int j = 0; j < 8; ++j) send[j] = z ? zb[(8 - j) & 7] : zb[7 - j];  // (z: j = 0 is unused)
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (z) v[8 - i] = zb[i]; else v[7 - i] = zb[i];
+        }
+        if (z) v[0] = make_float2(ya[8].x, yb[8].x);  // Nyquist
+#pragma unroll
+        for (int j = 0; j < 8; ++j) send[j] = za[j];
+    }
+}
+ADV_HD void merge_post(float2* v, int l, const float2* recv) {
+    const bool keep8 = (l == 1);  // lane (0,1) computed its own v[8] (mirror of its k2 = 8 bin)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (!(keep8 && j == 0)) v[8 + j] = recv[j];
+}
+}  // namespace w512
+
 }  // namespace adv

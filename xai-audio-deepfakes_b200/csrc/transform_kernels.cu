@@ -20,6 +20,7 @@
 // PRIVATE shared-memory strip (hop + window-support samples); after one CTA barrier each output
 // sample gathers the <= ceil(strip / 2hop)+1 strips that cover it, in a fixed order, multiplies by the
 // precomputed reciprocal window envelope and is stored coalesced.  No atomics anywhere.
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include "adv_internal.cuh"
@@ -106,6 +107,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // copy that lands asynchronously (complete on `bar`, phase 0); the caller overlaps its other loads and
 // then calls stage_wait().  Tiles that touch the clip edges (torch.stft's centre=True reflect padding)
 // or an unaligned row use plain loads.  `bulk` is CTA-uniform.
+template <int NT = kThreads>
 __device__ __forceinline__ int stage_segment(float* seg, int seglen, const float* __restrict__ row, int base,
                                              int n_in, uint64_t* bar, bool& bulk) {
     const int a0 = base & ~3;
@@ -120,7 +122,7 @@ __device__ __forceinline__ int stage_segment(float* seg, int seglen, const float
         }
         return shift;
     }
-    for (int i = threadIdx.x; i < seglen; i += kThreads) {
+    for (int i = threadIdx.x; i < seglen; i += NT) {
         int idx = base + i;
         if (idx < 0) idx = -idx;
         else if (idx >= n_in) idx = 2 * (n_in - 1) - idx;
@@ -139,20 +141,20 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 // Sum NQ doubles per thread over the CTA; result valid in thread 0.  red: >= NQ * 8 doubles of smem.
-template <int NQ>
+template <int NQ, int NT = kThreads>
 __device__ __forceinline__ void block_sum(double (&q)[NQ], double* red) {
     const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
 #pragma unroll
     for (int i = 0; i < NQ; ++i) {
         q[i] = warp_sum(q[i]);
-        if (ln == 0) red[i * (kThreads / 32) + w] = q[i];
+        if (ln == 0) red[i * (NT / 32) + w] = q[i];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
             double s = 0.0;
-            for (int k = 0; k < kThreads / 32; ++k) s += red[i * (kThreads / 32) + k];
+            for (int k = 0; k < NT / 32; ++k) s += red[i * (NT / 32) + k];
             q[i] = s;
         }
     }
@@ -615,6 +617,235 @@ explain_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t wav_
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused explain, n_fft = 512, "wide" units: 512 threads = 16 warps, one warp per FFT (fft_core.cuh w512).
+// Same tiling, staging, strips and gather as explain_kernel<512>; half the registers per thread, so
+// twice the warps are resident per SM (the narrow-unit kernel is FP32-issue / latency bound at 8 warps).
+// ------------------------------------------------------------------------------------------------
+constexpr int kWideThreads = 512;
+
+struct WideCfg {
+    static constexpr int UNITS = 16, FT = 32, MP = FT + 1, F = 257, NF = 512;
+    static __host__ __device__ int strip(int hop, int support) { return (hop + support + 3) & ~3; }
+    static __host__ __device__ size_t seg_floats(int hop) { return (size_t)(FT - 1) * hop + NF + 8; }
+    static __host__ __device__ size_t strips_bytes(int hop, int support, bool from_spec) {
+        size_t b = sizeof(float2) * UNITS * strip(hop, support);
+        if (!from_spec && b < sizeof(float) * seg_floats(hop)) b = sizeof(float) * seg_floats(hop);
+        return b;
+    }
+    static size_t bytes(int hop, int support, bool from_spec) {
+        return al16(sizeof(float2) * 512) + al16(sizeof(float) * UNITS * w512::SCRATCH) + al16(sizeof(float) * NF) +
+               al16(strips_bytes(hop, support, from_spec)) + al16(sizeof(double) * 4 * (kWideThreads / 32)) +
+               al16(sizeof(float) * F * MP) + 16;
+    }
+};
+
+struct TwWide {
+    const float2* p;  // [16 k1][32 lanes]
+    int l;
+    __device__ __forceinline__ float2 operator()(int k1) const { return p[k1 * 32 + l]; }
+};
+
+__device__ __forceinline__ void wide_fft_forward(float2* v, int l, TwWide tw, float* scr) {
+    w512::fwd_cols(v, tw);
+    __syncwarp();
+    w512::scr_store_cols(v, l, scr, false);
+    __syncwarp();
+    w512::scr_load_rows(v, l, scr, false);
+    __syncwarp();
+    w512::scr_store_cols(v, l, scr, true);
+    __syncwarp();
+    w512::scr_load_rows(v, l, scr, true);
+    w512::fwd_rows_local(v);
+    float2 other[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        other[m].x = __shfl_xor_sync(0xffffffffu, v[m].x, 1);
+        other[m].y = __shfl_xor_sync(0xffffffffu, v[m].y, 1);
+    }
+    w512::fwd_rows_combine(v, l, other);
+}
+__device__ __forceinline__ void wide_fft_inverse(float2* v, int l, TwWide tw, float* scr) {
+    float2 other[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        other[m].x = __shfl_xor_sync(0xffffffffu, v[m].x, 1);
+        other[m].y = __shfl_xor_sync(0xffffffffu, v[m].y, 1);
+    }
+    w512::inv_rows_combine(v, l, other);
+    w512::inv_rows_local(v);
+    __syncwarp();
+    w512::scr_store_rows(v, l, scr, false);
+    __syncwarp();
+    w512::scr_load_cols(v, l, scr, false);
+    __syncwarp();
+    w512::scr_store_rows(v, l, scr, true);
+    __syncwarp();
+    w512::scr_load_cols(v, l, scr, true);
+    w512::inv_cols(v, tw);
+}
+__device__ __forceinline__ void wide_exchange8(const float2* send, float2* recv, int src) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        recv[j].x = __shfl_sync(0xffffffffu, send[j].x, src);
+        recv[j].y = __shfl_sync(0xffffffffu, send[j].y, src);
+    }
+}
+
+template <int MODE, bool FROM_SPEC>
+__global__ void __launch_bounds__(kWideThreads, 1)
+explain_w512_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t wav_stride,
+                    const float2* __restrict__ X, int64_t sb, int64_t st, int64_t sf,
+                    const float* __restrict__ mask, int Fm, int Tm,
+                    float* __restrict__ rel, float* __restrict__ irr, double* __restrict__ stats) {
+    using C = WideCfg;
+    constexpr int UNITS = C::UNITS, FT = C::FT, MP = C::MP, F = C::F, NF = C::NF, NT = kWideThreads;
+    const int support = P.whi - P.wlo, lb = P.hop + support, strip = C::strip(P.hop, support);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(512);
+    float* scratch = cv.take<float>(UNITS * w512::SCRATCH);
+    float* win_s = cv.take<float>(NF);
+    float2* pb = reinterpret_cast<float2*>(cv.take<unsigned char>(C::strips_bytes(P.hop, support, FROM_SPEC)));
+    float* seg = reinterpret_cast<float*>(pb);
+    double* red = cv.take<double>(4 * (NT / 32));
+    float* mask_s = cv.take<float>(F * MP);
+    uint64_t* bar = cv.take<uint64_t>(1);
+
+    const int tid = threadIdx.x, b = blockIdx.y;
+    const TileGeom g = tile_geom<NF>(P, TL, blockIdx.x);
+    const int S = g.s1 - g.s0;
+    bool bulk = false;
+    int shift = 0;
+    if (!FROM_SPEC)
+        shift = stage_segment<NT>(seg, (FT - 1) * P.hop + NF, wav + (size_t)b * wav_stride, g.t_lo * P.hop - NF / 2,
+                                  P.n_in, bar, bulk);
+    {
+        const float* mrow = mask + (size_t)b * Fm * Tm;
+#pragma unroll 4
+        for (int e = tid; e < F * FT; e += NT) {
+            const int f = e / FT, c = e % FT;
+            const int t = g.t_lo + c;
+            mask_s[f * MP + c] = (f < Fm && t < Tm && t <= g.t_hi) ? __ldg(mrow + (size_t)f * Tm + t) : 0.0f;
+        }
+    }
+    // plan table is [32][16] (exp(-2 pi i a b / 512), symmetric in a, b): transpose to [16 k1][32 lanes]
+    if (tid < 512) tw_s[(tid & 15) * 32 + (tid >> 4)] = P.tw[tid];
+    for (int i = tid; i < NF; i += NT) win_s[i] = P.window[i];
+    __syncthreads();
+
+    const int u = tid >> 5, l = tid & 31;
+    float* my = scratch + u * w512::SCRATCH;
+    const TwWide tw{tw_s, l};
+    const int fa = g.t_lo + 2 * u;
+    const float* wl = win_s + l;
+    const int prt = w512::partner_row(l);
+
+    float2 v[16];
+    float2 xa[9], xb[9];
+    if (FROM_SPEC) {
+        const bool va = fa <= g.t_hi, vb = fa + 1 <= g.t_hi;
+        const float2* xa_p = X + (size_t)b * sb + (size_t)fa * st;
+        const float2* xb_p = xa_p + st;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int bin = w512::bin_of(l, i);
+            const float2 z = make_float2(0.f, 0.f);
+            xa[i] = (va && bin >= 0) ? __ldg(xa_p + (size_t)bin * sf) : z;
+            xb[i] = (vb && bin >= 0) ? __ldg(xb_p + (size_t)bin * sf) : z;
+        }
+    } else {
+        stage_wait(bar, bulk);
+        const float* sa = seg + shift + (2 * u) * P.hop + l;
+        const float* sbp = sa + P.hop;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const float w = wl[n1 * 32];
+            v[n1] = make_float2(sa[n1 * 32] * w, sbp[n1 * 32] * w);
+        }
+        __syncthreads();  // the segment's memory becomes the strips
+        wide_fft_forward(v, l, tw, my);
+        float2 send[8], recv[8];
+        w512::split_pre(v, send);
+        wide_exchange8(send, recv, prt);
+        w512::split_post(v, l, recv, xa, xb);
+    }
+
+    float2* pbu = pb + u * strip;
+    const int c0 = l - P.wlo, ovl = support - P.hop;
+    if (ovl < 0)
+        for (int k = support + l; k < P.hop; k += 32) pbu[k] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const int t = fa + half;
+        const bool valid = t <= g.t_hi;
+        const int col = 2 * u + half;
+        {
+            float2 yr[9], yi[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const int bin = w512::bin_of(l, i);
+                const bool live = bin >= 0 && valid;
+                const float m = live ? mask_s[bin * MP + col] : 0.0f;
+                float gr, gi;
+                mask_gains<MODE>(xa[i], m, gr, gi);
+                yr[i] = live ? make_float2(xa[i].x * gr, xa[i].y * gr) : make_float2(0.f, 0.f);
+                yi[i] = live ? make_float2(xa[i].x * gi, xa[i].y * gi) : make_float2(0.f, 0.f);
+            }
+            float2 send[8], recv[8];
+            w512::merge_pre(v, l, yr, yi, send);
+            wide_exchange8(send, recv, prt);
+            w512::merge_post(v, l, recv);
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) xa[i] = xb[i];
+        wide_fft_inverse(v, l, tw, my);
+        float2* dst = pbu + half * P.hop;
+        const int keep = half ? ovl : 0;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const int k = n1 * 32 + c0;
+            if ((unsigned)k < (unsigned)support) {
+                const float w = wl[n1 * 32];
+                float2 o = k < keep ? dst[k] : make_float2(0.f, 0.f);
+                o.x = fmaf(v[n1].x, w, o.x);
+                o.y = fmaf(v[n1].y, w, o.y);
+                dst[k] = o;
+            }
+        }
+        __syncwarp();  // frame a's strip stores are visible to the unit before frame b's read-modify-write
+    }
+    __syncthreads();
+
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    float* rrow = rel + (size_t)b * P.n_out + g.s0;
+    float* irow = irr + (size_t)b * P.n_out + g.s0;
+    const float* env = P.inv_env + g.s0;
+    const int two_hop = 2 * P.hop, x0 = g.p0 - (g.t_lo * P.hop + P.wlo);
+    const float inv_two_hop = 1.0f / (float)two_hop;
+    for (int q = tid; q < S; q += NT) {
+        const float e = __ldg(env + q);
+        const float2 o = gather2<UNITS>(pb, strip, lb, two_hop, inv_two_hop, x0 + q);
+        const float yr = o.x * e, yi = o.y * e;
+        rrow[q] = yr;
+        irow[q] = yi;
+        acc[0] += (double)yr;
+        acc[1] += (double)yr * (double)yr;
+        acc[2] += (double)yi;
+        acc[3] += (double)yi * (double)yi;
+    }
+    if (stats != nullptr) {
+        block_sum<4, NT>(acc, red);
+        if (tid == 0) {
+            double* srow = stats + ((size_t)b * TL.tiles + blockIdx.x) * 4;
+            srow[0] = acc[0];
+            srow[1] = acc[1];
+            srow[2] = acc[2];
+            srow[3] = acc[3];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
 // cudaFuncSetAttribute once per (kernel, size high-water mark): keeps the launch path free of
@@ -693,11 +924,33 @@ static int launch_explain_inst(const adv_plan* p, const Tiling& tl, const float*
     return ADV_OK;
 }
 
+template <int MODE, bool FROM_SPEC>
+static int launch_explain_wide(const adv_plan* p, const Tiling& tl, const float* wav, int64_t wav_stride,
+                               const float2* X, int64_t sb, int64_t st, int64_t sf, const float* mask, int Fm,
+                               int Tm, int batch, float* rel, float* irr, double* stats, cudaStream_t s) {
+    const size_t smem = WideCfg::bytes(p->d.hop, p->d.whi - p->d.wlo, FROM_SPEC);
+    int rc = set_smem(explain_w512_kernel<MODE, FROM_SPEC>, smem);
+    if (rc != ADV_OK) return rc;
+    dim3 grid(tl.tiles, batch);
+    explain_w512_kernel<MODE, FROM_SPEC><<<grid, kWideThreads, smem, s>>>(p->d, tl, wav, wav_stride, X, sb, st, sf,
+                                                                         mask, Fm, Tm, rel, irr, stats);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
 int launch_explain(const adv_plan* p, const float* wav, int64_t wav_stride, const float2* X, int64_t sb,
                    int64_t st, int64_t sf, const float* mask, int Fm, int Tm, int mode, int batch, float* rel,
                    float* irr, double* stats, cudaStream_t s) {
     const Tiling tl = choose_tiling(p, batch);
     const bool spec = (X != nullptr);
+    static const bool narrow = getenv("ADV_EXPLAIN_NARROW") != nullptr;  // keep the 16-lane-unit kernel reachable
+    if (p->d.n_fft == 512 && !narrow) {
+#define ADV_WIDE(MODE, SPEC) \
+    return launch_explain_wide<MODE, SPEC>(p, tl, wav, wav_stride, X, sb, st, sf, mask, Fm, Tm, batch, rel, irr, stats, s)
+        if (mode == ADV_MASK_LOG1P) { if (spec) ADV_WIDE(ADV_MASK_LOG1P, true); else ADV_WIDE(ADV_MASK_LOG1P, false); }
+        else { if (spec) ADV_WIDE(ADV_MASK_LINEAR, true); else ADV_WIDE(ADV_MASK_LINEAR, false); }
+#undef ADV_WIDE
+    }
 #define ADV_EXPLAIN(NF, MODE, SPEC) \
     return launch_explain_inst<NF, MODE, SPEC>(p, tl, wav, wav_stride, X, sb, st, sf, mask, Fm, Tm, batch, rel, irr, stats, s)
     if (p->d.n_fft == 512) {
