@@ -57,11 +57,33 @@ class TorchLogReg(nn.Module):
         return logits, torch.sigmoid(logits)
 
 
+class _NormalizeFn(torch.autograd.Function):
+    """Forward = our row_stats + normalize kernels.  Backward (gradient-attribution / training callers only,
+    outside the evaluation hot path) re-derives the gradient with torch ops from the saved input."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.normalize_(x.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        with torch.enable_grad():
+            xd = x.detach().to(g.device).requires_grad_(True)
+            y = (xd - xd.mean(dim=-1, keepdim=True)) / (xd.std(dim=-1, keepdim=True) + 1e-7)
+            (gx,) = torch.autograd.grad(y, xd, g)
+        return gx.to(x.device)
+
+
 def zero_mean_unit_var_norm(input_values):
     """classifier_embedder.py:59-63 over the last dim: (x - mean) / (std_unbiased + 1e-7).
-    Runs the row_stats + normalize kernels; returns a CUDA tensor of the input's shape."""
+    Runs the row_stats + normalize kernels; returns a CUDA tensor of the input's shape.  Differentiable
+    (the reference keeps this op in torch precisely so that gradients reach the waveform)."""
     shape = input_values.shape
     x = input_values.reshape(-1, shape[-1])
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _NormalizeFn.apply(x).reshape(shape)
     return ops.normalize_(x).reshape(shape)
 
 
