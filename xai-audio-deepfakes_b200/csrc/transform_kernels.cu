@@ -719,18 +719,29 @@ explain_w512_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t
     if (!FROM_SPEC)
         shift = stage_segment<NT>(seg, (FT - 1) * P.hop + NF, wav + (size_t)b * wav_stride, g.t_lo * P.hop - NF / 2,
                                   P.n_in, bar, bulk);
-    {
+    {   // mask tile [F][FT]: every load of the tile (17 per thread) is issued before the first use, so the
+        // tile costs one memory latency instead of one per loop trip
         const float* mrow = mask + (size_t)b * Fm * Tm;
-#pragma unroll 4
-        for (int e = tid; e < F * FT; e += NT) {
+        constexpr int kTrips = (F * FT + NT - 1) / NT;
+        float mreg[kTrips];
+        const float2 twv = P.tw[tid];
+        const float wv = P.window[tid];
+#pragma unroll
+        for (int j = 0; j < kTrips; ++j) {
+            const int e = tid + j * NT;
             const int f = e / FT, c = e % FT;
             const int t = g.t_lo + c;
-            mask_s[f * MP + c] = (f < Fm && t < Tm && t <= g.t_hi) ? __ldg(mrow + (size_t)f * Tm + t) : 0.0f;
+            mreg[j] = (e < F * FT && f < Fm && t < Tm && t <= g.t_hi) ? __ldg(mrow + (size_t)f * Tm + t) : 0.0f;
+        }
+        // plan table is [32][16] (exp(-2 pi i a b / 512), symmetric in a, b): transpose to [16 k1][32 lanes]
+        tw_s[(tid & 15) * 32 + (tid >> 4)] = twv;
+        win_s[tid] = wv;
+#pragma unroll
+        for (int j = 0; j < kTrips; ++j) {
+            const int e = tid + j * NT;
+            if (e < F * FT) mask_s[(e / FT) * MP + (e % FT)] = mreg[j];
         }
     }
-    // plan table is [32][16] (exp(-2 pi i a b / 512), symmetric in a, b): transpose to [16 k1][32 lanes]
-    if (tid < 512) tw_s[(tid & 15) * 32 + (tid >> 4)] = P.tw[tid];
-    for (int i = tid; i < NF; i += NT) win_s[i] = P.window[i];
     __syncthreads();
 
     const int u = tid >> 5, l = tid & 31;
