@@ -13,6 +13,7 @@ struct PlanDev {
     int n_fft, hop, T, n_in, n_out;
     int wlo, whi;          // window support [wlo, whi) inside n_fft (non-zero taps)
     int phases;            // ceil(support / hop): frames t and t+phases never overlap
+    int rect_full;         // window == 1 on all n_fft taps (torch's default when win_length == n_fft)
     const float* window;   // dev [n_fft], window centred in n_fft
     const float* inv_env;  // dev [n_out], 1 / (n_fft * sum_t w^2), 0 where no frame lands
     const float2* tw;      // dev [32][lanes], exp(-2*pi*i*l*k1/n_fft)

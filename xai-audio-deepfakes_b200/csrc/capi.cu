@@ -138,6 +138,9 @@ int adv_plan_create(adv_plan** out, int n_fft, int hop, int win_length, const fl
     p->d.wlo = wlo;
     p->d.whi = whi;
     p->d.phases = phases;
+    p->d.rect_full = 1;
+    for (int i = 0; i < n_fft; ++i)
+        if (win[i] != 1.0f) p->d.rect_full = 0;
     p->d.window = (const float*)p->dev_block;
     p->d.inv_env = (const float*)((char*)p->dev_block + o_env);
     p->d.tw = (const float2*)((char*)p->dev_block + o_tw);

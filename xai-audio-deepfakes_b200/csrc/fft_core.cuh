@@ -80,6 +80,36 @@ ADV_HD float2 twmul(float2 a) {
     }
 }
 
+// radix-2 butterfly with the twiddle folded into FMAs:  lo = e + W*o,  hi = e - W*o = 2e - lo
+// (6 FMA-pipe instructions for a general twiddle instead of 8; trivial twiddles stay pure adds)
+template <int N, int K, int DIR>
+ADV_HD void butterfly(float2 e, float2 o, float2& lo, float2& hi) {
+    if constexpr (K == 0 || 4 * K == N) {
+        const float2 t = twmul<N, K, DIR>(o);
+        lo = cadd(e, t);
+        hi = csub(e, t);
+    } else if constexpr (8 * K == N || 8 * K == 3 * N) {
+        constexpr float h = 0.70710678118654752f;
+        // W*o = h * (p, q) with p, q sums / differences of o's parts
+        float p, q;
+        if constexpr (8 * K == N) {
+            p = DIR < 0 ? o.x + o.y : o.x - o.y;
+            q = DIR < 0 ? o.y - o.x : o.x + o.y;
+        } else {
+            p = DIR < 0 ? o.y - o.x : -(o.x + o.y);
+            q = DIR < 0 ? -(o.x + o.y) : o.x - o.y;
+        }
+        lo = make_float2(fmaf(p, h, e.x), fmaf(q, h, e.y));
+        hi = make_float2(fmaf(-p, h, e.x), fmaf(-q, h, e.y));
+    } else {
+        constexpr int idx = K * (32 / N);
+        constexpr float c = kCos32[idx];
+        constexpr float s = (DIR < 0 ? -1.0f : 1.0f) * kSin32[idx];
+        lo = make_float2(fmaf(o.x, c, fmaf(-o.y, s, e.x)), fmaf(o.x, s, fmaf(o.y, c, e.y)));
+        hi = make_float2(fmaf(2.0f, e.x, -lo.x), fmaf(2.0f, e.y, -lo.y));
+    }
+}
+
 // N-point DFT of in[0], in[S], in[2S], ... -> out[0..N-1] (natural order), all in registers.
 template <int N, int DIR>
 struct FFTReg {
@@ -90,9 +120,7 @@ struct FFTReg {
         FFTReg<N / 2, DIR>::template run<2 * S>(in + S, o);
         static_for<0, N / 2>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            const float2 t = twmul<N, k, DIR>(o[k]);
-            out[k] = cadd(e[k], t);
-            out[k + N / 2] = csub(e[k], t);
+            butterfly<N, k, DIR>(e[k], o[k], out[k], out[k + N / 2]);
         });
     }
 };
@@ -432,8 +460,9 @@ ADV_HD void fwd_rows_combine(float2* v, int l, const float2* other) {
         constexpr int m = decltype(mc)::value;
         const float2 e = h ? other[m] : v[m];
         const float2 o = h ? v[m] : other[m];
-        const float2 t = twmul<32, m, -1>(o);
-        v[m] = h ? csub(e, t) : cadd(e, t);
+        float2 lo, hi;
+        butterfly<32, m, -1>(e, o, lo, hi);
+        v[m] = h ? hi : lo;
     });
 }
 // inverse rows: undo the pair butterfly (needs the partner's values), then radix-16

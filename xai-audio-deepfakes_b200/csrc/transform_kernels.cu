@@ -691,7 +691,7 @@ __device__ __forceinline__ void wide_exchange8(const float2* send, float2* recv,
     }
 }
 
-template <int MODE, bool FROM_SPEC>
+template <int MODE, bool FROM_SPEC, bool RECT>  // RECT: all-ones window over the whole frame (no window math)
 __global__ void __launch_bounds__(kWideThreads, 1)
 explain_w512_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t wav_stride,
                     const float2* __restrict__ X, int64_t sb, int64_t st, int64_t sf,
@@ -770,7 +770,7 @@ explain_w512_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t
         const float* sbp = sa + P.hop;
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
-            const float w = wl[n1 * 32];
+            const float w = RECT ? 1.0f : wl[n1 * 32];
             v[n1] = make_float2(sa[n1 * 32] * w, sbp[n1 * 32] * w);
         }
         __syncthreads();  // the segment's memory becomes the strips
@@ -812,15 +812,29 @@ explain_w512_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t
         wide_fft_inverse(v, l, tw, my);
         float2* dst = pbu + half * P.hop;
         const int keep = half ? ovl : 0;
+        if (RECT) {  // support == n_fft, w == 1: every sample lands, only the overlap test remains
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-            const int k = n1 * 32 + c0;
-            if ((unsigned)k < (unsigned)support) {
-                const float w = wl[n1 * 32];
-                float2 o = k < keep ? dst[k] : make_float2(0.f, 0.f);
-                o.x = fmaf(v[n1].x, w, o.x);
-                o.y = fmaf(v[n1].y, w, o.y);
+            for (int n1 = 0; n1 < 16; ++n1) {
+                const int k = n1 * 32 + l;
+                float2 o = v[n1];
+                if (k < keep) {
+                    const float2 prev = dst[k];
+                    o.x += prev.x;
+                    o.y += prev.y;
+                }
                 dst[k] = o;
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+                const int k = n1 * 32 + c0;
+                if ((unsigned)k < (unsigned)support) {
+                    const float w = wl[n1 * 32];
+                    float2 o = k < keep ? dst[k] : make_float2(0.f, 0.f);
+                    o.x = fmaf(v[n1].x, w, o.x);
+                    o.y = fmaf(v[n1].y, w, o.y);
+                    dst[k] = o;
+                }
             }
         }
         __syncwarp();  // frame a's strip stores are visible to the unit before frame b's read-modify-write
@@ -940,11 +954,17 @@ static int launch_explain_wide(const adv_plan* p, const Tiling& tl, const float*
                                const float2* X, int64_t sb, int64_t st, int64_t sf, const float* mask, int Fm,
                                int Tm, int batch, float* rel, float* irr, double* stats, cudaStream_t s) {
     const size_t smem = WideCfg::bytes(p->d.hop, p->d.whi - p->d.wlo, FROM_SPEC);
-    int rc = set_smem(explain_w512_kernel<MODE, FROM_SPEC>, smem);
-    if (rc != ADV_OK) return rc;
     dim3 grid(tl.tiles, batch);
-    explain_w512_kernel<MODE, FROM_SPEC><<<grid, kWideThreads, smem, s>>>(p->d, tl, wav, wav_stride, X, sb, st, sf,
-                                                                         mask, Fm, Tm, rel, irr, stats);
+    int rc;
+    if (p->d.rect_full) {
+        if ((rc = set_smem(explain_w512_kernel<MODE, FROM_SPEC, true>, smem)) != ADV_OK) return rc;
+        explain_w512_kernel<MODE, FROM_SPEC, true><<<grid, kWideThreads, smem, s>>>(p->d, tl, wav, wav_stride, X, sb, st,
+                                                                                   sf, mask, Fm, Tm, rel, irr, stats);
+    } else {
+        if ((rc = set_smem(explain_w512_kernel<MODE, FROM_SPEC, false>, smem)) != ADV_OK) return rc;
+        explain_w512_kernel<MODE, FROM_SPEC, false><<<grid, kWideThreads, smem, s>>>(p->d, tl, wav, wav_stride, X, sb, st,
+                                                                                    sf, mask, Fm, Tm, rel, irr, stats);
+    }
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }
