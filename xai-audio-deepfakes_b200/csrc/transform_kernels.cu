@@ -102,6 +102,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---- cp.async (LDGSTS): global -> shared without a register round trip ----------------------------
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// plan tables (twiddles, window): 16-byte async copies; wait + __syncthreads before the first use
+template <int NT>
+__device__ __forceinline__ void stage_tables(float2* tw_s, int n_tw, float* win_s, int n_win, const PlanDev& P) {
+    for (int i = threadIdx.x; i < n_tw / 2; i += NT) cp_async16(tw_s + 2 * i, P.tw + 2 * i);
+    for (int i = threadIdx.x; i < n_win / 4; i += NT) cp_async16(win_s + 4 * i, P.window + 4 * i);
+}
+// reciprocal-envelope tile for the epilogue: lands while the FFTs run
+template <int NT>
+__device__ __forceinline__ void stage_env(float* env_s, const float* __restrict__ env, int S) {
+    for (int i = threadIdx.x; i < S; i += NT) cp_async4(env_s + i, env + i);
+}
+
 // Stage `seglen` waveform samples starting at original index `base` into shared memory and return the
 // offset (0..3 floats) at which the data starts inside `seg`.  Interior tiles: thread 0 issues ONE bulk
 // copy that lands asynchronously (complete on `bar`, phase 0); the caller overlaps its other loads and
@@ -194,15 +214,16 @@ struct Cfg {
         return al16(sizeof(float2) * 32 * G::LANES) + al16(sizeof(float) * UNITS * G::SCRATCH) +
                al16(sizeof(float) * NF) + al16(sizeof(float) * seg_floats(hop)) + 16;
     }
-    static size_t istft_bytes(int hop, int support) {
+    static size_t istft_bytes(int hop, int support, int tile_samples) {
         return al16(sizeof(float2) * 32 * G::LANES) + al16(sizeof(float) * UNITS * G::SCRATCH) +
                al16(sizeof(float) * NF) + al16(sizeof(float) * UNITS * strip(hop, support)) +
-               al16(sizeof(double) * 2 * (kThreads / 32));
+               al16(sizeof(double) * 2 * (kThreads / 32)) + al16(sizeof(float) * tile_samples);
     }
-    static size_t explain_bytes(int hop, int support, bool from_spec) {
+    static size_t explain_bytes(int hop, int support, bool from_spec, int tile_samples) {
         return al16(sizeof(float2) * 32 * G::LANES) + al16(sizeof(float) * UNITS * G::SCRATCH) +
                al16(sizeof(float) * NF) + al16(strips_bytes(hop, support, from_spec)) +
-               al16(sizeof(double) * 4 * (kThreads / 32)) + al16(sizeof(float) * G::NBINS * MP) + 16;
+               al16(sizeof(double) * 4 * (kThreads / 32)) + al16(sizeof(float) * G::NBINS * MP) + 16 +
+               al16(sizeof(float) * tile_samples);
     }
 };
 
@@ -228,8 +249,8 @@ stft_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, float2
     bool bulk;
     const int shift = stage_segment(seg, (FT - 1) * P.hop + NF, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2,
                                     P.n_in, bar, bulk);
-    for (int i = tid; i < 32 * G::LANES; i += kThreads) tw_s[i] = P.tw[i];
-    for (int i = tid; i < NF; i += kThreads) win_s[i] = P.window[i];
+    stage_tables<kThreads>(tw_s, 32 * G::LANES, win_s, NF, P);
+    cp_async_wait_all();
     __syncthreads();
     stage_wait(bar, bulk);
 
@@ -333,10 +354,12 @@ istft_kernel(PlanDev P, Tiling TL, const float2* __restrict__ X, int64_t sb, int
     float* win_s = cv.take<float>(NF);
     float* pb = cv.take<float>(UNITS * strip);
     double* red = cv.take<double>(2 * (kThreads / 32));
+    float* env_s = cv.take<float>(TL.hops_per_tile * P.hop);
 
     const int tid = threadIdx.x, b = blockIdx.y;
     const TileGeom g = tile_geom<NF>(P, TL, blockIdx.x);
     const int S = g.s1 - g.s0;
+    stage_tables<kThreads>(tw_s, 32 * G::LANES, win_s, NF, P);
     const int u = tid / G::LANES, l = tid % G::LANES;
     const int fa = g.t_lo + 2 * u, fb = fa + 1;
     const bool va = fa <= g.t_hi, vb = fb <= g.t_hi;
@@ -353,9 +376,9 @@ istft_kernel(PlanDev P, Tiling TL, const float2* __restrict__ X, int64_t sb, int
             yb[i] = (vb && bin >= 0) ? __ldg(xb_p + (size_t)bin * sf) : z;
         }
     }
-    for (int i = tid; i < 32 * G::LANES; i += kThreads) tw_s[i] = P.tw[i];
-    for (int i = tid; i < NF; i += kThreads) win_s[i] = P.window[i];
+    cp_async_wait_all();
     __syncthreads();
+    stage_env<kThreads>(env_s, P.inv_env + g.s0, S);  // needed only by the epilogue
 
     float2 v[32];
     merge_regs<NF>(v, l, ya, yb);
@@ -384,15 +407,15 @@ istft_kernel(PlanDev P, Tiling TL, const float2* __restrict__ X, int64_t sb, int
             }
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     double acc[2] = {0.0, 0.0};
     float* orow = out + (size_t)b * P.n_out + g.s0;
-    const float* env = P.inv_env + g.s0;
     const int two_hop = 2 * P.hop, x0 = g.p0 - (g.t_lo * P.hop + P.wlo);
     const float inv_two_hop = 1.0f / (float)two_hop;
     for (int q = tid; q < S; q += kThreads) {
-        const float y = gather1<UNITS>(pb, strip, lb, two_hop, inv_two_hop, x0 + q) * __ldg(env + q);
+        const float y = gather1<UNITS>(pb, strip, lb, two_hop, inv_two_hop, x0 + q) * env_s[q];
         orow[q] = y;
         acc[0] += (double)y;
         acc[1] += (double)y * (double)y;
@@ -487,10 +510,12 @@ explain_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t wav_
     double* red = cv.take<double>(4 * (kThreads / 32));
     float* mask_s = cv.take<float>(F * MP);
     uint64_t* bar = cv.take<uint64_t>(1);
+    float* env_s = cv.take<float>(TL.hops_per_tile * P.hop);
 
     const int tid = threadIdx.x, b = blockIdx.y;
     const TileGeom g = tile_geom<NF>(P, TL, blockIdx.x);
     const int S = g.s1 - g.s0;
+    stage_env<kThreads>(env_s, P.inv_env + g.s0, S);  // needed only by the epilogue
     bool bulk = false;
     int shift = 0;
     if (!FROM_SPEC)
@@ -585,16 +610,16 @@ explain_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t wav_
             }
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     float* rrow = rel + (size_t)b * P.n_out + g.s0;
     float* irow = irr + (size_t)b * P.n_out + g.s0;
-    const float* env = P.inv_env + g.s0;
     const int two_hop = 2 * P.hop, x0 = g.p0 - (g.t_lo * P.hop + P.wlo);
     const float inv_two_hop = 1.0f / (float)two_hop;
     for (int q = tid; q < S; q += kThreads) {
-        const float e = __ldg(env + q);
+        const float e = env_s[q];
         const float2 o = gather2<UNITS>(pb, strip, lb, two_hop, inv_two_hop, x0 + q);
         const float yr = o.x * e, yi = o.y * e;
         rrow[q] = yr;
@@ -632,10 +657,10 @@ struct WideCfg {
         if (!from_spec && b < sizeof(float) * seg_floats(hop)) b = sizeof(float) * seg_floats(hop);
         return b;
     }
-    static size_t bytes(int hop, int support, bool from_spec) {
+    static size_t bytes(int hop, int support, bool from_spec, int tile_samples) {
         return al16(sizeof(float2) * 512) + al16(sizeof(float) * UNITS * w512::SCRATCH) + al16(sizeof(float) * NF) +
                al16(strips_bytes(hop, support, from_spec)) + al16(sizeof(double) * 4 * (kWideThreads / 32)) +
-               al16(sizeof(float) * F * MP) + 16;
+               al16(sizeof(float) * F * MP) + 16 + al16(sizeof(float) * tile_samples);
     }
 };
 
@@ -710,10 +735,12 @@ explain_w512_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t
     double* red = cv.take<double>(4 * (NT / 32));
     float* mask_s = cv.take<float>(F * MP);
     uint64_t* bar = cv.take<uint64_t>(1);
+    float* env_s = cv.take<float>(TL.hops_per_tile * P.hop);
 
     const int tid = threadIdx.x, b = blockIdx.y;
     const TileGeom g = tile_geom<NF>(P, TL, blockIdx.x);
     const int S = g.s1 - g.s0;
+    stage_env<NT>(env_s, P.inv_env + g.s0, S);  // needed only by the epilogue
     bool bulk = false;
     int shift = 0;
     if (!FROM_SPEC)
@@ -839,16 +866,16 @@ explain_w512_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t
         }
         __syncwarp();  // frame a's strip stores are visible to the unit before frame b's read-modify-write
     }
+    cp_async_wait_all();
     __syncthreads();
 
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     float* rrow = rel + (size_t)b * P.n_out + g.s0;
     float* irow = irr + (size_t)b * P.n_out + g.s0;
-    const float* env = P.inv_env + g.s0;
     const int two_hop = 2 * P.hop, x0 = g.p0 - (g.t_lo * P.hop + P.wlo);
     const float inv_two_hop = 1.0f / (float)two_hop;
     for (int q = tid; q < S; q += NT) {
-        const float e = __ldg(env + q);
+        const float e = env_s[q];
         const float2 o = gather2<UNITS>(pb, strip, lb, two_hop, inv_two_hop, x0 + q);
         const float yr = o.x * e, yi = o.y * e;
         rrow[q] = yr;
@@ -920,7 +947,7 @@ template <int NF>
 static int launch_istft_nf(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch,
                            float* out, double* stats, cudaStream_t s) {
     const Tiling tl = choose_tiling(p, batch);
-    const size_t smem = Cfg<NF>::istft_bytes(p->d.hop, p->d.whi - p->d.wlo);
+    const size_t smem = Cfg<NF>::istft_bytes(p->d.hop, p->d.whi - p->d.wlo, tl.hops_per_tile * p->d.hop);
     int rc = set_smem(istft_kernel<NF>, smem);
     if (rc != ADV_OK) return rc;
     dim3 grid(tl.tiles, batch);
@@ -939,7 +966,7 @@ template <int NF, int MODE, bool FROM_SPEC>
 static int launch_explain_inst(const adv_plan* p, const Tiling& tl, const float* wav, int64_t wav_stride,
                                const float2* X, int64_t sb, int64_t st, int64_t sf, const float* mask, int Fm,
                                int Tm, int batch, float* rel, float* irr, double* stats, cudaStream_t s) {
-    const size_t smem = Cfg<NF>::explain_bytes(p->d.hop, p->d.whi - p->d.wlo, FROM_SPEC);
+    const size_t smem = Cfg<NF>::explain_bytes(p->d.hop, p->d.whi - p->d.wlo, FROM_SPEC, tl.hops_per_tile * p->d.hop);
     int rc = set_smem(explain_kernel<NF, MODE, FROM_SPEC>, smem);
     if (rc != ADV_OK) return rc;
     dim3 grid(tl.tiles, batch);
@@ -953,7 +980,7 @@ template <int MODE, bool FROM_SPEC>
 static int launch_explain_wide(const adv_plan* p, const Tiling& tl, const float* wav, int64_t wav_stride,
                                const float2* X, int64_t sb, int64_t st, int64_t sf, const float* mask, int Fm,
                                int Tm, int batch, float* rel, float* irr, double* stats, cudaStream_t s) {
-    const size_t smem = WideCfg::bytes(p->d.hop, p->d.whi - p->d.wlo, FROM_SPEC);
+    const size_t smem = WideCfg::bytes(p->d.hop, p->d.whi - p->d.wlo, FROM_SPEC, tl.hops_per_tile * p->d.hop);
     dim3 grid(tl.tiles, batch);
     int rc;
     if (p->d.rect_full) {
