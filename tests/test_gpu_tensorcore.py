@@ -68,6 +68,10 @@ TMA_CASES = [
     (2, 90, 256, 2048, 3, 1, False),      # phase-stacked transposed conv (8 N tiles share each A tile)
     (5, 128, 64, 32, 3, 1, False),
     (40, 700, 64, 64, 7, 1, True),        # more tiles than CTAs: persistent loop + both TMEM buffers
+    (2, 500, 64, 64, 11, 5, True),        # slab kernel: 178-row slab, 11 row-shifted descriptors (128-byte swizzle)
+    (2, 500, 32, 32, 7, 3, True),         # slab kernel, 64-byte swizzle, odd row shifts
+    (1, 300, 32, 32, 3, 1, False),
+    (3, 1000, 64, 64, 3, 3, True),
 ]
 
 

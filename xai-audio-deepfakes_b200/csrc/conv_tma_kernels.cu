@@ -19,6 +19,7 @@
 //   to / instead of the raw one), so consumers load pure TMA tiles.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include "adv_internal.cuh"
@@ -68,6 +69,94 @@ __device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
     d |= (uint64_t)1 << 46;                              // Blackwell descriptor version
     d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;     // SWIZZLE_128B / SWIZZLE_64B
     return d;
+}
+
+// Epilogue of one 128 x BN tile for one warp (TMEM lanes 32*quad ..): +bias, +residual, *scale, raw and / or
+// LeakyReLU'd bf16 stores.  The residual row is fetched before the accumulator is waited for.
+struct EpiArgs {
+    const float* bias;
+    const __nv_bfloat16* resid;
+    __nv_bfloat16* out_raw;
+    __nv_bfloat16* out_act;
+    int L, N;
+    float act_slope, out_scale;
+};
+template <int BN>
+__device__ __forceinline__ void conv_epilogue(const EpiArgs& a, int b, int l0, int tn, uint32_t tmem_acc, int quad,
+                                              int lane, uint64_t* tfull_bar, uint32_t parity) {
+    const int l = l0 + quad * 32 + lane;
+    const bool row_ok = l < a.L;
+    const size_t rowoff = ((size_t)b * a.L + l) * a.N + (size_t)tn * BN;
+    const bool has_res = a.resid != nullptr && row_ok;
+    // the residual row does not depend on the MMAs: fetch its first 32 columns while they finish
+    int4 rnext[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        rnext[j] = has_res ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff) + j) : make_int4(0, 0, 0, 0);
+    bar_wait(tfull_bar, parity);
+    fence_after_sync();
+    const uint32_t trow = tmem_acc + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        int4 rcur[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+        if (c0 + 32 < BN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                rnext[j] = has_res ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff + c0 + 32) + j)
+                                   : make_int4(0, 0, 0, 0);
+        }
+        float v[32];
+        tmem_ld32(trow + c0, v);
+        if (row_ok) {
+            const int n = tn * BN + c0;
+            if (a.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n) + j);
+                    v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+                }
+            }
+            if (has_res) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rcur[q]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __bfloat1622float2(rp[j]);
+                        v[8 * q + 2 * j] += f.x;
+                        v[8 * q + 2 * j + 1] += f.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= a.out_scale;
+            if (a.out_raw != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int4 o;
+                    __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]);
+                    *(reinterpret_cast<int4*>(a.out_raw + rowoff + c0) + q) = o;
+                }
+            }
+            if (a.out_act != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int4 o;
+                    __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float x0 = v[8 * q + 2 * j], x1 = v[8 * q + 2 * j + 1];
+                        op[j] = __floats2bfloat162_rn(x0 > 0.f ? x0 : x0 * a.act_slope, x1 > 0.f ? x1 : x1 * a.act_slope);
+                    }
+                    *(reinterpret_cast<int4*>(a.out_act + rowoff + c0) + q) = o;
+                }
+            }
+        }
+    }
 }
 
 template <int BN, int BK, int STAGES>
@@ -157,79 +246,115 @@ conv1d_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const long tl = tile / a.tiles_n;
             const int b = (int)(tl / a.tiles_l), l0 = (int)(tl % a.tiles_l) * 128;
             const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
-            const int l = l0 + quad * 32 + lane;
-            const bool row_ok = l < a.L;
-            const size_t rowoff = ((size_t)b * a.L + l) * a.N + (size_t)tn * BN;
-            const bool has_res = a.resid != nullptr && row_ok;
-            // the residual row does not depend on the MMAs: fetch its first 32 columns while they finish
-            int4 rnext[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                rnext[j] = has_res ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff) + j) : make_int4(0, 0, 0, 0);
-            bar_wait(&tfull[ab], aph);
-            fence_after_sync();
-            const uint32_t trow = tmem_base + ab * BN + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                int4 rcur[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-                if (c0 + 32 < BN) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        rnext[j] = has_res ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff + c0 + 32) + j)
-                                           : make_int4(0, 0, 0, 0);
-                }
-                float v[32];
-                tmem_ld32(trow + c0, v);
-                if (row_ok) {
-                    const int n = tn * BN + c0;
-                    if (a.bias != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n) + j);
-                            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-                        }
-                    }
-                    if (has_res) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rcur[q]);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 f = __bfloat1622float2(rp[j]);
-                                v[8 * q + 2 * j] += f.x;
-                                v[8 * q + 2 * j + 1] += f.y;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= a.out_scale;
-                    if (a.out_raw != nullptr) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            int4 o;
-                            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]);
-                            *(reinterpret_cast<int4*>(a.out_raw + rowoff + c0) + q) = o;
-                        }
-                    }
-                    if (a.out_act != nullptr) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            int4 o;
-                            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float x0 = v[8 * q + 2 * j], x1 = v[8 * q + 2 * j + 1];
-                                op[j] = __floats2bfloat162_rn(x0 > 0.f ? x0 : x0 * a.act_slope, x1 > 0.f ? x1 : x1 * a.act_slope);
-                            }
-                            *(reinterpret_cast<int4*>(a.out_act + rowoff + c0) + q) = o;
-                        }
-                    }
-                }
+            const EpiArgs ea{a.bias, a.resid, a.out_raw, a.out_act, a.L, a.N, a.act_slope, a.out_scale};
+            conv_epilogue<BN>(ea, b, l0, tn, tmem_base + ab * BN, quad, lane, &tfull[ab], aph);
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) bar_arrive(&tempty[ab]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kCols);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Narrow-channel variant (C_in = C_out = C in {32, 64}: the MRF stages that are memory-, not tensor-bound).
+// The general kernel re-fetches a shifted 128-row A tile per tap (up to 11x the activation through L2) and
+// the weight tile per K-block.  Here a persistent CTA keeps ALL weights resident in shared memory and
+// fetches, per tile, ONE slab of 128 + 2*halo activation rows; tap j is the same slab read through a
+// descriptor whose start address is advanced by j*dil rows (the swizzle phase follows the address).
+// ---------------------------------------------------------------------------------------------------
+struct SlabArgs {
+    EpiArgs e;
+    int B, taps, dil, halo, rows;  // rows = 128 + 2*halo (TMA box height)
+    int tiles_l;
+};
+
+// Row-shifted start addresses need nothing special in the descriptor: measured on B200, the swizzle XOR is
+// taken from the absolute shared-memory address bits (base_offset stays 0; setting it to (addr >> 7) & 7
+// breaks the result), for both the 128-byte and the 64-byte modes and for odd row shifts.
+
+template <int C, int STAGES>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, SlabArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kRow = C * 2, kWTile = C * kRow;
+    const int slab_stride = (a.rows * kRow + 1023) & ~1023;
+    unsigned char* wsm = smem;                               // [taps][C x C] weights, resident
+    unsigned char* slabs = smem + a.taps * kWTile;           // [STAGES][slab_stride]
+    uint64_t* full = reinterpret_cast<uint64_t*>(slabs + STAGES * slab_stride);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    constexpr uint32_t kCols = 2 * C;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            bar_init(&full[s], 1);
+            bar_init(&empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            bar_init(&tfull[i], 1);
+            bar_init(&tempty[i], 4);
+        }
+        bar_init(wbar, 1);
+        bar_init_fence();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kCols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const long total_tiles = (long)a.B * a.tiles_l;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            bar_expect_tx(wbar, a.taps * kWTile);
+            for (int tap = 0; tap < a.taps; ++tap) tma_load_2d(wsm + tap * kWTile, &map_w, wbar, tap * C, 0);
+            uint32_t it = 0;
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int b = (int)(tile / a.tiles_l), l0 = (int)(tile % a.tiles_l) * 128;
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                bar_wait(&empty[s], ph ^ 1);
+                bar_expect_tx(&full[s], a.rows * kRow);
+                tma_load_3d(slabs + s * slab_stride, &map_a, &full[s], 0, l0 - a.halo, b);
             }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, C);
+            bar_wait(wbar, 0);
+            uint32_t it = 0;
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                bar_wait(&tempty[ab], aph ^ 1);
+                bar_wait(&full[s], ph);
+                fence_after_sync();
+                const uint32_t tmem_d = tmem_base + ab * C;
+                const uint32_t slab = smem_addr(slabs + s * slab_stride);
+                for (int tap = 0; tap < a.taps; ++tap) {
+                    const uint64_t da = make_desc_k<C>(slab + tap * a.dil * kRow);
+                    const uint64_t db = make_desc_k<C>(smem_addr(wsm + tap * kWTile));
+#pragma unroll
+                    for (int k = 0; k < C / 16; ++k) mma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (tap | k) != 0);
+                }
+                mma_commit(&empty[s]);
+                mma_commit(&tfull[ab]);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        uint32_t it = 0;
+        for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int b = (int)(tile / a.tiles_l), l0 = (int)(tile % a.tiles_l) * 128;
+            const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+            conv_epilogue<C>(a.e, b, l0, 0, tmem_base + ab * C, quad, lane, &tfull[ab], aph);
             fence_before_sync();
             __syncwarp();
             if (lane == 0) bar_arrive(&tempty[ab]);
@@ -305,6 +430,26 @@ static int launch_conv_tma(const CUtensorMap& ma, const CUtensorMap& mw, ConvTma
     return ADV_OK;
 }
 
+template <int C>
+static int launch_conv_slab(const CUtensorMap& ma, const CUtensorMap& mw, const SlabArgs& a, cudaStream_t s) {
+    constexpr int STAGES = 3;
+    const size_t slab_stride = ((size_t)a.rows * C * 2 + 1023) & ~size_t(1023);
+    const size_t smem = (size_t)a.taps * C * C * 2 + STAGES * slab_stride + 256 + 1024;
+    int rc = set_smem_attr2(conv1d_slab_kernel<C, STAGES>, smem);
+    if (rc != ADV_OK) return rc;
+    int per_sm = (int)((220 * 1024) / smem);
+    const int by_tmem = 512 / (2 * C);
+    if (per_sm > by_tmem) per_sm = by_tmem;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    const long tiles = (long)a.B * a.tiles_l;
+    long grid = (long)num_sms() * per_sm;
+    if (grid > tiles) grid = tiles;
+    conv1d_slab_kernel<C, STAGES><<<(unsigned)grid, kConvThreads, smem, s>>>(ma, mw, a);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
 }  // namespace adv
 
 using namespace adv;
@@ -340,6 +485,37 @@ extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* b
                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return ADV_ERR_INVALID;
+    }
+    static const bool no_slab = getenv("ADV_NO_SLAB") != nullptr;
+    if (!no_slab && Cin == N && (Cin == 32 || Cin == 64)) {
+        const int halo = ((taps - 1) / 2) * dil, rows = 128 + 2 * halo;
+        if (rows <= 256) {
+            CUtensorMap ms;  // slab map: box = all C channels x (128 + 2 halo) rows x 1 clip
+            cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)L, (cuuint64_t)batch};
+            cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)L * Cin * 2};
+            cuuint32_t box[3] = {(cuuint32_t)Cin, (cuuint32_t)rows, 1};
+            cuuint32_t estr[3] = {1, 1, 1};
+            if (enc(&ms, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(in), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return ADV_ERR_INVALID;
+            CUtensorMap mws;  // one tap of the weights: box = C (k) x C (n)
+            cuuint64_t wd[2] = {(cuuint64_t)taps * Cin, (cuuint64_t)N};
+            cuuint64_t wst[1] = {(cuuint64_t)taps * Cin * 2};
+            cuuint32_t wb[2] = {(cuuint32_t)Cin, (cuuint32_t)N};
+            cuuint32_t we[2] = {1, 1};
+            if (enc(&mws, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), wd, wst, wb, we,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return ADV_ERR_INVALID;
+            SlabArgs sa;
+            sa.e = EpiArgs{bias, (const __nv_bfloat16*)resid, (__nv_bfloat16*)out_raw, (__nv_bfloat16*)out_act, L, N,
+                           act_slope, out_scale};
+            sa.B = batch; sa.taps = taps; sa.dil = dil; sa.halo = halo; sa.rows = rows;
+            sa.tiles_l = (L + 127) / 128;
+            return Cin == 64 ? launch_conv_slab<64>(ms, mws, sa, (cudaStream_t)stream)
+                             : launch_conv_slab<32>(ms, mws, sa, (cudaStream_t)stream);
+        }
     }
     ConvTmaArgs a;
     a.bias = bias;
