@@ -72,6 +72,9 @@ TMA_CASES = [
     (2, 500, 32, 32, 7, 3, True),         # slab kernel, 64-byte swizzle, odd row shifts
     (1, 300, 32, 32, 3, 1, False),
     (3, 1000, 64, 64, 3, 3, True),
+    (2, 700, 256, 256, 7, 3, True),       # slab2 kernel: tile pairs, two channel groups, streamed weights
+    (1, 513, 128, 128, 11, 5, True),      # slab2: 306-row slab in two TMA boxes, ragged last pair
+    (3, 300, 512, 256, 3, 1, False),      # slab2: four channel groups, two N tiles
 ]
 
 

@@ -366,6 +366,140 @@ conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Wide-channel variant (C_in % 128 == 0, N % 128 == 0: upsample + MRF stages with 128 / 256 channels).
+// With the general kernel these stages are L2 -> SM bandwidth bound: per 128-row tile it re-fetches a shifted
+// A tile per tap AND the full weight matrix.  Here one work item is a PAIR of tiles (256 positions) x 128
+// output channels: the activation slab (256 + 2*halo rows, two 64-channel blocks at a time) is fetched once
+// and read through row-shifted descriptors, and every streamed 128x64 weight block feeds both tiles
+// (two M = 128 MMAs into two TMEM accumulators), halving weight traffic per output.  Slab chunks and weight
+// blocks ride separate mbarrier rings; accumulators are double-buffered (4 x 128 = 512 TMEM columns).
+// ---------------------------------------------------------------------------------------------------
+struct Slab2Args {
+    EpiArgs e;
+    int B, Cin, taps, dil, halo;
+    int rb;                       // TMA box height: the slab (256 + 2*halo rows) arrives as two boxes
+    int pairs_l, tiles_n, groups; // tile pairs per clip, 128-wide N tiles, channel groups of 128
+};
+
+template <int WSTAGES>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, Slab2Args a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kRow = 128, kWTile = 128 * kRow;           // 64 channels bf16 per row; 128 x 64 weight block
+    const int part = (2 * a.rb * kRow + 1023) & ~1023;       // one 64-channel block of the slab
+    unsigned char* slabs = smem;                             // [2 buffers][2 channel blocks][part]
+    unsigned char* wring = smem + 4 * part;                  // [WSTAGES][kWTile]
+    uint64_t* sfull = reinterpret_cast<uint64_t*>(wring + WSTAGES * kWTile);
+    uint64_t* sempty = sfull + 2;
+    uint64_t* wfull = sempty + 2;
+    uint64_t* wempty = wfull + WSTAGES;
+    uint64_t* tfull = wempty + WSTAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            bar_init(&sfull[i], 1);
+            bar_init(&sempty[i], 1);
+            bar_init(&tfull[i], 1);
+            bar_init(&tempty[i], 4);
+        }
+        for (int s = 0; s < WSTAGES; ++s) {
+            bar_init(&wfull[s], 1);
+            bar_init(&wempty[s], 1);
+        }
+        bar_init_fence();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const long items = (long)a.B * a.pairs_l * a.tiles_n;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t ci = 0, wi = 0;
+            for (long item = blockIdx.x; item < items; item += gridDim.x) {
+                const int tn = (int)(item % a.tiles_n);
+                const long pr = item / a.tiles_n;
+                const int b = (int)(pr / a.pairs_l), l0 = (int)(pr % a.pairs_l) * 256;
+                for (int g = 0; g < a.groups; ++g, ++ci) {
+                    const int sb = ci & 1, sph = (ci >> 1) & 1;
+                    bar_wait(&sempty[sb], sph ^ 1);
+                    bar_expect_tx(&sfull[sb], 4 * a.rb * kRow);
+                    for (int c = 0; c < 2; ++c)
+                        for (int hf = 0; hf < 2; ++hf)
+                            tma_load_3d(slabs + (2 * sb + c) * part + hf * a.rb * kRow, &map_a, &sfull[sb],
+                                        (2 * g + c) * 64, l0 - a.halo + hf * a.rb, b);
+                    for (int tap = 0; tap < a.taps; ++tap)
+                        for (int c = 0; c < 2; ++c, ++wi) {
+                            const int ws = wi % WSTAGES, wph = (wi / WSTAGES) & 1;
+                            bar_wait(&wempty[ws], wph ^ 1);
+                            bar_expect_tx(&wfull[ws], kWTile);
+                            tma_load_2d(wring + ws * kWTile, &map_w, &wfull[ws], tap * a.Cin + (2 * g + c) * 64, tn * 128);
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, 128);
+            uint32_t ci = 0, wi = 0, tcount = 0;
+            for (long item = blockIdx.x; item < items; item += gridDim.x, ++tcount) {
+                const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+                bar_wait(&tempty[ab], aph ^ 1);
+                fence_after_sync();
+                const uint32_t acc0 = tmem_base + ab * 256, acc1 = acc0 + 128;
+                uint32_t first = 1;
+                for (int g = 0; g < a.groups; ++g, ++ci) {
+                    const int sb = ci & 1, sph = (ci >> 1) & 1;
+                    bar_wait(&sfull[sb], sph);
+                    fence_after_sync();
+                    for (int tap = 0; tap < a.taps; ++tap)
+                        for (int c = 0; c < 2; ++c, ++wi) {
+                            const int ws = wi % WSTAGES, wph = (wi / WSTAGES) & 1;
+                            bar_wait(&wfull[ws], wph);
+                            fence_after_sync();
+                            const uint32_t sa = smem_addr(slabs + (2 * sb + c) * part) + tap * a.dil * kRow;
+                            const uint64_t da0 = make_desc_k<64>(sa), da1 = make_desc_k<64>(sa + 128 * kRow);
+                            const uint64_t db = make_desc_k<64>(smem_addr(wring + ws * kWTile));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                mma_f16(acc0, da0 + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                                mma_f16(acc1, da1 + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                            }
+                            first = 0;
+                            mma_commit(&wempty[ws]);
+                        }
+                    mma_commit(&sempty[sb]);
+                }
+                mma_commit(&tfull[ab]);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        uint32_t tcount = 0;
+        for (long item = blockIdx.x; item < items; item += gridDim.x, ++tcount) {
+            const int tn = (int)(item % a.tiles_n);
+            const long pr = item / a.tiles_n;
+            const int b = (int)(pr / a.pairs_l), l0 = (int)(pr % a.pairs_l) * 256;
+            const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+            conv_epilogue<128>(a.e, b, l0, tn, tmem_base + ab * 256, quad, lane, &tfull[ab], aph);
+            conv_epilogue<128>(a.e, b, l0 + 128, tn, tmem_base + ab * 256 + 128, quad, lane, &tfull[ab], aph);
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) bar_arrive(&tempty[ab]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -515,6 +649,46 @@ extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* b
             sa.tiles_l = (L + 127) / 128;
             return Cin == 64 ? launch_conv_slab<64>(ms, mws, sa, (cudaStream_t)stream)
                              : launch_conv_slab<32>(ms, mws, sa, (cudaStream_t)stream);
+        }
+    }
+    static const bool no_slab2 = getenv("ADV_NO_SLAB2") != nullptr;
+    if (!no_slab && !no_slab2 && Cin % 128 == 0 && N % 128 == 0) {
+        const int halo = ((taps - 1) / 2) * dil, rows = 256 + 2 * halo, rb = (rows + 1) / 2;
+        if (rb <= 256) {
+            CUtensorMap ms, mws;
+            cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)L, (cuuint64_t)batch};
+            cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)L * Cin * 2};
+            cuuint32_t box[3] = {64, (cuuint32_t)rb, 1};
+            cuuint32_t estr[3] = {1, 1, 1};
+            if (enc(&ms, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(in), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return ADV_ERR_INVALID;
+            cuuint64_t wd[2] = {(cuuint64_t)taps * Cin, (cuuint64_t)N};
+            cuuint64_t wst[1] = {(cuuint64_t)taps * Cin * 2};
+            cuuint32_t wb[2] = {64, 128};
+            cuuint32_t we[2] = {1, 1};
+            if (enc(&mws, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), wd, wst, wb, we,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return ADV_ERR_INVALID;
+            Slab2Args sa;
+            sa.e = EpiArgs{bias, (const __nv_bfloat16*)resid, (__nv_bfloat16*)out_raw, (__nv_bfloat16*)out_act, L, N,
+                           act_slope, out_scale};
+            sa.B = batch; sa.Cin = Cin; sa.taps = taps; sa.dil = dil; sa.halo = halo; sa.rb = rb;
+            sa.pairs_l = (L + 255) / 256; sa.tiles_n = N / 128; sa.groups = Cin / 128;
+            constexpr int WS = 3;
+            const size_t part = ((size_t)2 * rb * 128 + 1023) & ~size_t(1023);
+            const size_t smem = 4 * part + (size_t)WS * 128 * 128 + 256 + 1024;
+            int rc = set_smem_attr2(conv1d_slab2_kernel<WS>, smem);
+            if (rc == ADV_OK) {
+                const long items = (long)batch * sa.pairs_l * sa.tiles_n;
+                long grid = num_sms();
+                if (grid > items) grid = items;
+                conv1d_slab2_kernel<WS><<<(unsigned)grid, kConvThreads, smem, (cudaStream_t)stream>>>(ms, mws, sa);
+                ADV_CUDA_CHECK(cudaGetLastError());
+                return ADV_OK;
+            }
         }
     }
     ConvTmaArgs a;
