@@ -188,15 +188,12 @@ class HifiganGenerator:
         return o, L
 
     def _stages_tma(self, o, B, L):
-        """``o`` = raw conv_pre output.  Every tensor a conv consumes was written already LeakyReLU'd by its
-        producer; raw copies exist only where a residual or the MRF average needs them."""
+        """``o`` = conv_pre output, already LeakyReLU'd.  Every tensor a conv consumes was written activated by
+        its producer; raw copies exist only where a residual or the MRF average needs them."""
         n_stage = len(self.ups)
-        o_act = None
+        o_act = o
         for si, ((up, s), stage) in enumerate(zip(self.ups, self.blocks)):
-            if si == 0:   # input is conv_pre's raw output: activation on load, first-generation kernel
-                x_raw, x_act = self._conv(o, up, B, L, pre_slope=LRELU_SLOPE, reflect=False, act_slope=LRELU_SLOPE)
-            else:
-                x_raw, x_act = self._conv_tma(o_act, up, B, L, act_slope=LRELU_SLOPE)
+            x_raw, x_act = self._conv_tma(o_act, up, B, L, act_slope=LRELU_SLOPE)
             L, ch = L * s, up.cout // s
             x_raw, x_act = x_raw.view(B, L, ch), x_act.view(B, L, ch)
             outs = []
@@ -224,8 +221,11 @@ class HifiganGenerator:
         L = T + 2 * pad
         x = self._buf(B, L, C)
         check(lib().adv_mel_to_channels_last(ptr(mel), B, C, T, pad, C, ptr(x), stream_ptr()), "adv_mel_to_channels_last")
-        o = self._conv(x, self.conv_pre, B, L)
-        o, L = (self._stages_tma if self.pipeline == "tma" else self._stages_gather)(o, B, L)
+        if self.pipeline == "tma":   # conv_pre (C_in = 80) runs on the gather kernel and hands over lrelu(o)
+            _, o = self._conv(x, self.conv_pre, B, L, want_raw=False, act_slope=LRELU_SLOPE)
+            o, L = self._stages_tma(o, B, L)
+        else:
+            o, L = self._stages_gather(self._conv(x, self.conv_pre, B, L), B, L)
         wav = torch.empty((B, L), dtype=torch.float32, device=self.dev)
         check(lib().adv_post_conv_tanh(ptr(o), ptr(self.post_w), ptr(self.post_b), B, L, o.shape[2],
                                        self.post_w.shape[0], 0.01, int(cfg.pad_reflect), ptr(wav), stream_ptr()),
