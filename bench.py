@@ -46,6 +46,7 @@ F = CFG["n_fft"] // 2 + 1
 BYTES_EXPLAIN = 4 * N + 4 * F * T + 2 * 4 * N
 BYTES_STFT = 4 * N + 8 * F * T
 BYTES_ISTFT = 8 * F * T + 4 * N
+METRIC = "explained clips/s (4s@16kHz) STFT-mask-iSTFT+LMAC metrics"
 POOL = 16  # rotating input/output sets: 16 x 75.6 MB = 1.2 GB >> 126 MB L2
 
 
@@ -138,7 +139,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / steps
     val = BATCH / dt
     line = {
-        "impl": "reference", "metric": "explained clips/s", "value": val, "unit": "clips/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: 64 x 4 s clips @16 kHz, n_fft 512 hop 160, mask -> iSTFT x2 -> "
@@ -166,7 +167,7 @@ def time_loop(fn, iters):
 def main():
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--gpus", type=int, default=1)
-    ap_.add_argument("--steps", type=int, default=2000)
+    ap_.add_argument("--steps", type=int, default=5000)
     ap_.add_argument("--warmup", type=int, default=50)
     ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap_.add_argument("--no-cpu-baseline", action="store_true")
@@ -351,7 +352,7 @@ def main():
         traffic = json.load(open(tpath)).get("explain_kernel_bytes_per_launch")
 
     line = {
-        "metric": "explained clips/s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps,
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps,
         "warmup": done, "ms_per_step": elapsed / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: 64 x 4 s clips @16 kHz per GPU-step, n_fft 512 hop 160 win 512, "

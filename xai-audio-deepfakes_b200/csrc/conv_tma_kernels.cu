@@ -544,6 +544,24 @@ static int set_smem_attr2(K kernel, size_t bytes) {
     return ADV_OK;
 }
 
+// resident CTAs per SM for a persistent launch (registers, shared memory and TMEM columns all bound it)
+template <class K>
+static int resident_ctas(K kernel, size_t smem, int tmem_cols) {
+    static std::mutex mu;
+    static std::unordered_map<size_t, int> cache;
+    const size_t key = reinterpret_cast<size_t>(kernel) ^ (smem * 1315423911u);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    int n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kConvThreads, smem) != cudaSuccess || n < 1) n = 1;
+    const int by_tmem = 512 / (tmem_cols < 32 ? 32 : tmem_cols);
+    if (n > by_tmem) n = by_tmem;
+    if (n > 4) n = 4;
+    cache[key] = n;
+    return n;
+}
+
 template <int BN, int BK, int STAGES>
 static int launch_conv_tma(const CUtensorMap& ma, const CUtensorMap& mw, ConvTmaArgs& a, cudaStream_t s) {
     constexpr size_t smem = (size_t)STAGES * (128 * BK * 2 + BN * BK * 2) + 256 + 1024;
@@ -551,12 +569,7 @@ static int launch_conv_tma(const CUtensorMap& ma, const CUtensorMap& mw, ConvTma
     if (rc != ADV_OK) return rc;
     a.tiles_n = a.N / BN;
     const long tiles = (long)a.B * a.tiles_l * a.tiles_n;
-    // co-resident CTAs per SM: bounded by shared memory, by TMEM columns (512) and by 4
-    int per_sm = (int)((220 * 1024) / smem);
-    const int by_tmem = 512 / (2 * BN < 32 ? 32 : 2 * BN);
-    if (per_sm > by_tmem) per_sm = by_tmem;
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) per_sm = 1;
+    const int per_sm = resident_ctas(conv1d_tma_kernel<BN, BK, STAGES>, smem, 2 * BN);
     long grid = (long)num_sms() * per_sm;
     if (grid > tiles) grid = tiles;
     conv1d_tma_kernel<BN, BK, STAGES><<<(unsigned)grid, kConvThreads, smem, s>>>(ma, mw, a);
@@ -571,11 +584,7 @@ static int launch_conv_slab(const CUtensorMap& ma, const CUtensorMap& mw, const 
     const size_t smem = (size_t)a.taps * C * C * 2 + STAGES * slab_stride + 256 + 1024;
     int rc = set_smem_attr2(conv1d_slab_kernel<C, STAGES>, smem);
     if (rc != ADV_OK) return rc;
-    int per_sm = (int)((220 * 1024) / smem);
-    const int by_tmem = 512 / (2 * C);
-    if (per_sm > by_tmem) per_sm = by_tmem;
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) per_sm = 1;
+    const int per_sm = resident_ctas(conv1d_slab_kernel<C, STAGES>, smem, 2 * C);
     const long tiles = (long)a.B * a.tiles_l;
     long grid = (long)num_sms() * per_sm;
     if (grid > tiles) grid = tiles;
