@@ -16,7 +16,7 @@ struct PlanDev {
     int rect_full;         // window == 1 on all n_fft taps (torch's default when win_length == n_fft)
     const float* window;   // dev [n_fft], window centred in n_fft
     const float* inv_env;  // dev [n_out], 1 / (n_fft * sum_t w^2), 0 where no frame lands
-    const float2* tw;      // dev [32][lanes], exp(-2*pi*i*l*k1/n_fft)
+    const float2* tw;      // dev [2][32][lanes]: exp(-2*pi*i*l*k1/n_fft), then the row-rotated variant
 };
 
 // Tiling of the output (sample) axis for the overlap-add kernels.

@@ -108,12 +108,16 @@ int adv_plan_create(adv_plan** out, int n_fft, int hop, int win_length, const fl
     }
 
     const int lanes = n_fft / 32;
-    std::vector<float2> tw((size_t)32 * lanes);
-    for (int k1 = 0; k1 < 32; ++k1)
-        for (int l = 0; l < lanes; ++l) {
-            const double a = -2.0 * M_PI * (double)((k1 * l) % n_fft) / (double)n_fft;
-            tw[(size_t)k1 * lanes + l] = make_float2((float)cos(a), (float)sin(a));
-        }
+    // [0]: exp(-2 pi i l k1 / n_fft); [1]: the same times exp(-2 pi i k1 / 32), the table of a unit that reads
+    // its samples rotated by one radix-32 row (stft_w_kernel's bank-conflict avoidance)
+    std::vector<float2> tw((size_t)2 * 32 * lanes);
+    for (int r = 0; r < 2; ++r)
+        for (int k1 = 0; k1 < 32; ++k1)
+            for (int l = 0; l < lanes; ++l) {
+                const long num = ((long)k1 * l + (long)r * k1 * (n_fft / 32)) % n_fft;
+                const double a = -2.0 * M_PI * (double)num / (double)n_fft;
+                tw[((size_t)r * 32 + k1) * lanes + l] = make_float2((float)cos(a), (float)sin(a));
+            }
 
     adv_plan* p = (adv_plan*)calloc(1, sizeof(adv_plan));
     if (!p) return ADV_ERR_INVALID;

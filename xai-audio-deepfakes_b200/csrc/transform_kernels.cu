@@ -110,6 +110,35 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// ---- bulk-async store (TMA 1-D, shared -> global) of a unit's finished rows ---------------------------
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// `nbytes` (multiple of 4) staged at stage + (g & 15) go to global address g: the 16-byte aligned body by one
+// bulk copy issued by the elected lane, the <= 3 words before / after it by lanes 0..2 of the unit.  Call after
+// every writer lane has executed fence_async_smem() and the unit has synchronised.
+__device__ __forceinline__ void unit_store_bulk(const unsigned char* stage, unsigned char* g, uint32_t nbytes, int l,
+                                                bool elected) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
+    uint32_t head = mis ? 16 - mis : 0;
+    if (head > nbytes) head = nbytes;
+    const uint32_t body = (nbytes - head) & ~15u, tail = nbytes - head - body;
+    const float* sw = reinterpret_cast<const float*>(stage + mis);
+    float* gw = reinterpret_cast<float*>(g);
+    if ((uint32_t)l < head / 4) gw[l] = sw[l];
+    if ((uint32_t)l < tail / 4) gw[(head + body) / 4 + l] = sw[(head + body) / 4 + l];
+    if (elected && body) {
+        bulk_s2g(g + head, stage + mis + head, body);
+        bulk_commit();
+    }
+}
 // plan tables (twiddles, window): 16-byte async copies; wait + __syncthreads before the first use
 template <int NT>
 __device__ __forceinline__ void stage_tables(float2* tw_s, int n_tw, float* win_s, int n_win, const PlanDev& P) {
@@ -287,6 +316,333 @@ stft_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, float2
 }
 
 // ------------------------------------------------------------------------------------------------
+// STFT, persistent + software-pipelined (the production forward kernel)
+//
+// grid = min(tiles, resident CTAs); every CTA walks the tile list with stride gridDim.x.  The waveform
+// segment of tile i+1 is requested (one bulk-async copy completing on an mbarrier) as soon as every
+// thread holds tile i's samples in registers, so it lands while tile i's FFTs run: after the first tile
+// no global-load latency is exposed, and the plan tables are staged once per CTA instead of once per
+// tile.  Clip edges (torch.stft's centre=True reflect padding) and the <= 3 samples either side of the
+// 16-byte aligned bulk range are filled with plain loads into the same buffer.
+// ------------------------------------------------------------------------------------------------
+// Request samples [base, base + seglen) of `row` (reflect-padded outside [0, n_in)) into seg; sample
+// idx lands at seg[idx - base + shift], shift = base mod 4 (returned).  Thread 0 arms `bar` with the
+// bulk byte count (possibly 0) - one phase per call.  All threads must call it.
+template <int NT>
+__device__ __forceinline__ int stage_segment_async(float* seg, int seglen, const float* __restrict__ row, int base,
+                                                   int n_in, uint64_t* bar, int gtid = -1) {
+    if (gtid < 0) gtid = threadIdx.x;  // index inside the cooperating group of NT threads (CTA or warp)
+    const int shift = base & 3;
+    const int lo = max(base, 0), hi = min(base + seglen, n_in);
+    int a0 = (lo + 3) & ~3, a1 = hi & ~3;
+    if ((reinterpret_cast<uintptr_t>(row) & 15) != 0 || a1 <= a0) a0 = a1 = base;  // no bulk part
+    if (gtid == 0) {
+        const uint32_t bytes = (uint32_t)(a1 - a0) * 4u;
+        mbar_expect_tx(bar, bytes);
+        if (bytes) bulk_g2s(seg + (a0 - base + shift), row + a0, bytes, bar);
+    }
+    const int nL = a0 - base, nP = nL + (base + seglen - a1);
+    for (int i = gtid; i < nP; i += NT) {
+        const int pos = i < nL ? base + i : a1 + (i - nL);
+        int idx = pos;
+        if (idx < 0) idx = -idx;
+        else if (idx >= n_in) idx = 2 * (n_in - 1) - idx;
+        seg[pos - base + shift] = (idx >= 0 && idx < n_in) ? __ldg(row + idx) : 0.0f;
+    }
+    return shift;
+}
+
+// atan2 for the phase output: odd minimax polynomial on [0, 1] (max abs error 1.3e-7 rad before the
+// quadrant fix-up, i.e. fp32 round-off of a result up to pi) - a third of libm atan2f's instructions
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+    const float s = a * a;
+    float p = -0.004355369135737419f;
+    p = fmaf(p, s, 0.023040004074573517f);
+    p = fmaf(p, s, -0.0577734000980854f);
+    p = fmaf(p, s, 0.09794221073389053f);
+    p = fmaf(p, s, -0.13976576924324036f);
+    p = fmaf(p, s, 0.19962702691555023f);
+    p = fmaf(p, s, -0.3333165943622589f);
+    float r = fmaf(p * s, a, a);
+    if (ay > ax) r = 1.57079632679489662f - r;
+    if (x < 0.0f) r = 3.14159265358979324f - r;
+    return copysignf(r, y);
+}
+
+template <int NF>
+struct PCfg {  // shared-memory carve-up of the persistent kernels
+    using G = Geo<NF>;
+    static constexpr int UNITS = kThreads / G::LANES, FT = 2 * UNITS;
+    static __host__ __device__ size_t seg_floats(int hop) { return (size_t)(FT - 1) * hop + NF + 8; }
+    static size_t stft_bytes(int hop) {
+        return al16(sizeof(float2) * 32 * G::LANES) + al16(sizeof(float) * UNITS * GeoV<NF>::SCRATCH) +
+               al16(sizeof(float) * NF) + al16(sizeof(float) * seg_floats(hop)) + 16;
+    }
+};
+
+template <int NF, bool MAG, bool PHASE, bool RECT>
+__global__ void __launch_bounds__(kThreads, 2)
+stft_p_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int total_tiles, int tiles_per_clip,
+              float2* __restrict__ X, float* __restrict__ mag, float* __restrict__ phase) {
+    using G = Geo<NF>;
+    using C = PCfg<NF>;
+    constexpr int UNITS = C::UNITS, FT = C::FT, F = G::NBINS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(32 * G::LANES);
+    float* scratch = cv.take<float>(UNITS * GeoV<NF>::SCRATCH);
+    float* win_s = cv.take<float>(NF);
+    float* seg = cv.take<float>(C::seg_floats(P.hop));
+    uint64_t* bar = cv.take<uint64_t>(1);
+
+    const int tid = threadIdx.x, u = tid / G::LANES, l = tid % G::LANES;
+    const int seglen = (FT - 1) * P.hop + NF;
+    int tile = blockIdx.x;
+    if (tid == 0) mbar_init(bar, 1);
+    stage_tables<kThreads>(tw_s, 32 * G::LANES, win_s, NF, P);
+    __syncthreads();  // barrier initialised before anyone arms or polls it
+    int b = tile / tiles_per_clip, t0 = (tile - b * tiles_per_clip) * FT;
+    int shift = stage_segment_async<kThreads>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar);
+    cp_async_wait_all();
+
+    float* my = scratch + u * GeoV<NF>::SCRATCH;
+    const TwSmem<G::LANES> tw{tw_s, l};
+    for (uint32_t it = 0;; ++it) {
+        __syncthreads();  // plain-load part of the segment (and, first time round, the tables) visible
+        mbar_wait(bar, it & 1);
+        float2 v[32];
+        {
+            const float* sa = seg + shift + (2 * u) * P.hop + l;
+            const float* sb = sa + P.hop;
+            const float* wl = win_s + l;
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                if (RECT) {
+                    v[n1] = make_float2(sa[n1 * G::R2], sb[n1 * G::R2]);
+                } else {
+                    const float w = wl[n1 * G::R2];
+                    v[n1] = make_float2(sa[n1 * G::R2] * w, sb[n1 * G::R2] * w);
+                }
+            }
+        }
+        const int cur_b = b, fa = t0 + 2 * u;
+        const int next = tile + gridDim.x;
+        __syncthreads();  // every thread holds its samples: the buffer is free for the next tile
+        if (next < total_tiles) {
+            b = next / tiles_per_clip;
+            t0 = (next - b * tiles_per_clip) * FT;
+            shift = stage_segment_async<kThreads>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2,
+                                                  P.n_in, bar);
+        }
+        unit_fft_forward_v<NF>(v, l, tw, my);
+        float2 xa[17], xb[17];
+        split_regs<NF>(v, l, xa, xb);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int t = fa + half;
+            if (t >= P.T) continue;
+            const float2* x = half ? xb : xa;
+            const size_t row = ((size_t)cur_b * P.T + t) * F;
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+                const int bin = bin_of<NF>(l, i);
+                if (bin < 0) continue;
+                X[row + bin] = x[i];
+                if (MAG) {
+                    const float r2 = fmaf(x[i].x, x[i].x, x[i].y * x[i].y);
+                    mag[row + bin] = sqrtf(r2);
+                }
+                if (PHASE) phase[row + bin] = fast_atan2f(x[i].y, x[i].x);
+            }
+        }
+        if (next >= total_tiles) break;
+        tile = next;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// STFT, warp-autonomous: every warp owns its frames (4 for n_fft 512, 2 for 1024), its slice of the
+// waveform, its mbarrier and its place in the item list - no CTA barrier in steady state, so the warps of
+// an SM drift into different phases (shared-memory loads / FMA butterflies / global stores) and the three
+// pipes overlap instead of being hammered in lock-step.
+// n_fft 512: the two units of a warp read slices whose starts differ by 2*hop samples; when that is a
+// multiple of 32 floats their loads would collide bank for bank, so the odd unit reads its samples rotated
+// by one radix-32 row (sample n1+1 where the even unit reads n1) and uses a twiddle table that carries the
+// compensating phase exp(-2 pi i k1 / 32) (second half of PlanDev::tw) - conflict-free at no cost.
+// ------------------------------------------------------------------------------------------------
+template <int NF>
+struct WCfg {
+    using G = Geo<NF>;
+    static constexpr int WARPS = kThreads / 32, UPW = 32 / G::LANES, FW = 2 * UPW;  // units, frames per warp
+    static __host__ __device__ size_t seg_floats(int hop) { return ((size_t)(FW - 1) * hop + NF + 8 + 3) & ~size_t(3); }
+    // per-unit scratch in floats: the transposes need GeoV::SCRATCH; with BULK stores the unit's two finished
+    // rows (2 * NBINS complex + 16 bytes of alignment slack) are staged in the same memory.  Stride = 16 mod 32
+    // floats so that the two units of a warp sit in opposite bank halves.
+    static constexpr int unit_floats(bool bulk) {
+        int n = GeoV<NF>::SCRATCH;
+        const int need = 4 * G::NBINS + 4;
+        if (bulk && need > n) n = need;
+        return ((n + 15) / 32) * 32 + 16;
+    }
+    static size_t stft_bytes(int hop, bool bulk) {
+        return al16(sizeof(float2) * 2 * 32 * G::LANES) + al16(sizeof(float) * WARPS * UPW * unit_floats(bulk)) +
+               al16(sizeof(float) * NF) + al16(sizeof(float) * WARPS * seg_floats(hop)) + al16(8 * WARPS);
+    }
+};
+
+template <int NF, bool MAG, bool PHASE, bool RECT, bool BULK>
+__global__ void __launch_bounds__(kThreads, 2)
+stft_w_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int total_items, int items_per_clip,
+              float2* __restrict__ X, float* __restrict__ mag, float* __restrict__ phase) {
+    using G = Geo<NF>;
+    using C = WCfg<NF>;
+    constexpr int F = G::NBINS, FW = C::FW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(2 * 32 * G::LANES);
+    constexpr int UF = C::unit_floats(BULK);
+    float* scratch = cv.take<float>(C::WARPS * C::UPW * UF);
+    float* win_s = cv.take<float>(NF);
+    float* seg_all = cv.take<float>(C::WARPS * C::seg_floats(P.hop));
+    uint64_t* bars = cv.take<uint64_t>(C::WARPS);
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int uw = lane / G::LANES, l = lane % G::LANES;  // unit inside the warp, lane inside the unit
+    float* seg = seg_all + (size_t)w * C::seg_floats(P.hop);
+    uint64_t* bar = bars + w;
+    const int seglen = (FW - 1) * P.hop + NF;
+    const int stride = gridDim.x * C::WARPS;
+    int item = blockIdx.x * C::WARPS + w;
+
+    if (lane == 0) mbar_init(bar, 1);
+    for (int i = tid; i < 32 * G::LANES; i += kThreads) cp_async16(tw_s + 2 * i, P.tw + 2 * i);  // both tables
+    for (int i = tid; i < NF / 4; i += kThreads) cp_async16(win_s + 4 * i, P.window + 4 * i);
+    cp_async_wait_all();
+    __syncthreads();  // tables staged, barriers initialised
+    if (item >= total_items) return;
+
+    // bank rotation of the odd unit (see above): only when the units' slices start on the same bank
+    const int rot = (G::LANES == 16 && ((2 * P.hop) & 31) == 0) ? uw : 0;
+    float* my = scratch + (w * C::UPW + uw) * UF;
+    const bool elected = (l == 0);
+    const TwSmem<G::LANES> tw{tw_s + rot * 32 * G::LANES, l};
+    int b = item / items_per_clip, t0 = (item - b * items_per_clip) * FW;
+    int shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar, lane);
+
+    for (uint32_t it = 0;; ++it) {
+        __syncwarp();  // plain-load part of the slice visible to the warp
+        mbar_wait(bar, it & 1);
+        float2 v[32];
+        {
+            const float* sa = seg + shift + (2 * uw) * P.hop + l + rot * G::R2;
+            const float* sb = sa + P.hop;
+            const float* wl = win_s + l + rot * G::R2;
+            const int wrap = rot * NF;  // the rotated unit's last row is row 0
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const int o = n1 * G::R2 - (n1 == 31 ? wrap : 0);
+                if (RECT) {
+                    v[n1] = make_float2(sa[o], sb[o]);
+                } else {
+                    const float ww = wl[o];
+                    v[n1] = make_float2(sa[o] * ww, sb[o] * ww);
+                }
+            }
+        }
+        const int cur_b = b, fa = t0 + 2 * uw;
+        const int next = item + stride;
+        __syncwarp();  // every lane holds its samples: the slice buffer is free for the next item
+        if (next < total_items) {
+            b = next / items_per_clip;
+            t0 = (next - b * items_per_clip) * FW;
+            shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar,
+                                            lane);
+        }
+        if (BULK) {  // the previous item's rows have left the staging memory (it doubles as transpose scratch)
+            if (elected) bulk_wait_read();
+        }
+        unit_fft_forward_v<NF>(v, l, tw, my);
+        float2 xa[17], xb[17];
+        split_regs<NF>(v, l, xa, xb);
+        if (BULK) {
+            // rows fa, fa+1 of one clip are adjacent in X / mag / phase: stage both and hand each array to one
+            // bulk-async store (full-line writes, no per-lane store traffic through the LSU)
+            const int nrows = min(2, P.T - fa);
+            if (nrows > 0) {
+                const size_t row = ((size_t)cur_b * P.T + fa) * F;
+                unsigned char* stage = reinterpret_cast<unsigned char*>(my);
+                {
+                    unsigned char* g = reinterpret_cast<unsigned char*>(X + row);
+                    float2* st = reinterpret_cast<float2*>(stage + (reinterpret_cast<uintptr_t>(g) & 15));
+                    __syncwarp();  // transposes of this unit done with the scratch
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) {
+                        const int bin = bin_of<NF>(l, i);
+                        if (bin < 0) continue;
+                        st[bin] = xa[i];
+                        st[F + bin] = xb[i];
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    unit_store_bulk(stage, g, (uint32_t)nrows * F * 8u, l, elected);
+                }
+                if (MAG || PHASE) {
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) {  // (re, im) -> (|X|, angle X) in place
+                        const float2 a = xa[i], c = xb[i];
+                        xa[i] = make_float2(sqrtf(fmaf(a.x, a.x, a.y * a.y)), PHASE ? fast_atan2f(a.y, a.x) : 0.0f);
+                        xb[i] = make_float2(sqrtf(fmaf(c.x, c.x, c.y * c.y)), PHASE ? fast_atan2f(c.y, c.x) : 0.0f);
+                    }
+                    if (elected) bulk_wait_read();
+                    __syncwarp();
+                    // first half of the staging area: magnitudes, second half: phases (each 2 rows of F floats)
+                    unsigned char* gm = reinterpret_cast<unsigned char*>(mag + row);
+                    unsigned char* gp = reinterpret_cast<unsigned char*>(phase + row);
+                    unsigned char* stage_p = stage + ((2 * F * 4 + 16 + 15) & ~15);
+                    float* sm_ = reinterpret_cast<float*>(stage + (MAG ? (reinterpret_cast<uintptr_t>(gm) & 15) : 0));
+                    float* sp_ = reinterpret_cast<float*>(stage_p + (PHASE ? (reinterpret_cast<uintptr_t>(gp) & 15) : 0));
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) {
+                        const int bin = bin_of<NF>(l, i);
+                        if (bin < 0) continue;
+                        if (MAG) { sm_[bin] = xa[i].x; sm_[F + bin] = xb[i].x; }
+                        if (PHASE) { sp_[bin] = xa[i].y; sp_[F + bin] = xb[i].y; }
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (MAG) unit_store_bulk(stage, gm, (uint32_t)nrows * F * 4u, l, elected);
+                    if (PHASE) unit_store_bulk(stage_p, gp, (uint32_t)nrows * F * 4u, l, elected);
+                }
+            }
+        } else {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int t = fa + half;
+            if (t >= P.T) continue;
+            const float2* x = half ? xb : xa;
+            const size_t row = ((size_t)cur_b * P.T + t) * F;
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+                const int bin = bin_of<NF>(l, i);
+                if (bin < 0) continue;
+                X[row + bin] = x[i];
+                if (MAG) mag[row + bin] = sqrtf(fmaf(x[i].x, x[i].x, x[i].y * x[i].y));
+                if (PHASE) phase[row + bin] = fast_atan2f(x[i].y, x[i].x);
+            }
+        }
+        }
+        if (next >= total_items) break;
+        item = next;
+    }
+    if (BULK) {  // shared memory must outlive the reads of the last bulk stores
+        if (elected) bulk_wait_read();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // shared pieces of the overlap-add kernels
 // ------------------------------------------------------------------------------------------------
 struct TileGeom {
@@ -427,6 +783,208 @@ istft_kernel(PlanDev P, Tiling TL, const float2* __restrict__ X, int64_t sb, int
             srow[0] = acc[0];
             srow[1] = acc[1];
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// iSTFT, persistent + software-pipelined (the production inverse kernel)
+//
+// grid = min(tiles, resident CTAs); every CTA walks the tile list.  Differences to istft_kernel:
+//   * the next tile's spectrum rows are requested (plain loads into registers that are dead between the
+//     strip write and the next merge) BEFORE the barrier and the gather epilogue of the current tile, so
+//     their DRAM latency is covered by the epilogue instead of being exposed at tile start;
+//   * the gather epilogue handles VEC consecutive samples per step (128-/64-bit strip loads and output
+//     stores; strip index arithmetic once per group) - it was a third of the old kernel's instructions;
+//   * the strip origin is the window-support start rounded DOWN to a multiple of VEC (the extra leading
+//     taps are exact zeros of the window table), which keeps every strip access VEC-aligned;
+//   * plan tables are staged once per CTA; the reciprocal envelope is read straight from L2.
+// CONTIG: spectrum rows are contiguous (bin stride 1): offsets become immediates.
+// ------------------------------------------------------------------------------------------------
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using T = float; };
+template <> struct VecT<2> { using T = float2; };
+template <> struct VecT<4> { using T = float4; };
+__device__ __forceinline__ void vadd(float& a, float b) { a += b; }
+__device__ __forceinline__ void vadd(float2& a, float2 b) { a.x += b.x; a.y += b.y; }
+__device__ __forceinline__ void vadd(float4& a, float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ float vmul_stats(float& a, float e, float& sq) { a *= e; sq = a * a; return a; }
+__device__ __forceinline__ float vmul_stats(float2& a, float2 e, float& sq) {
+    a.x *= e.x; a.y *= e.y;
+    sq = fmaf(a.x, a.x, a.y * a.y);
+    return a.x + a.y;
+}
+__device__ __forceinline__ float vmul_stats(float4& a, float4 e, float& sq) {
+    a.x *= e.x; a.y *= e.y; a.z *= e.z; a.w *= e.w;
+    sq = fmaf(a.x, a.x, a.y * a.y) + fmaf(a.z, a.z, a.w * a.w);
+    return (a.x + a.y) + (a.z + a.w);
+}
+template <class V> __device__ __forceinline__ V vzero();
+template <> __device__ __forceinline__ float vzero<float>() { return 0.0f; }
+template <> __device__ __forceinline__ float2 vzero<float2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ float4 vzero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+template <int NF>
+struct IPCfg {
+    using G = Geo<NF>;
+    static constexpr int UNITS = kThreads / G::LANES;
+    // strip pitch: hop + support (support measured from the VEC-aligned origin, <= 3 more taps), padded like Cfg
+    static __host__ __device__ int strip(int hop, int support) { return Cfg<NF>::strip(hop, support + 4); }
+    static size_t bytes(int hop, int support, int tile_samples) {
+        return al16(sizeof(float2) * 32 * G::LANES) + al16(sizeof(float) * UNITS * GeoV<NF>::SCRATCH) +
+               al16(sizeof(float) * NF) + al16(sizeof(float) * UNITS * strip(hop, support)) +
+               al16(sizeof(double) * 2 * (kThreads / 32)) + al16(sizeof(float) * tile_samples);
+    }
+};
+
+template <int NF, int VEC, bool CONTIG>
+__global__ void __launch_bounds__(kThreads, 2)
+istft_p_kernel(PlanDev P, Tiling TL, int total_tiles, const float2* __restrict__ X, int64_t sb, int64_t st, int64_t sf,
+               float* __restrict__ out, double* __restrict__ stats) {
+    using G = Geo<NF>;
+    using C = IPCfg<NF>;
+    using V = typename VecT<VEC>::T;
+    constexpr int UNITS = C::UNITS;
+    const int wlo = P.wlo & ~(VEC - 1);
+    const int support = P.whi - wlo, lb = P.hop + support, strip = C::strip(P.hop, P.whi - P.wlo);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(32 * G::LANES);
+    float* scratch = cv.take<float>(UNITS * GeoV<NF>::SCRATCH);
+    float* win_s = cv.take<float>(NF);
+    float* pb = cv.take<float>(UNITS * strip);
+    double* red = cv.take<double>(2 * (kThreads / 32));
+    float* env_s = cv.take<float>(TL.hops_per_tile * P.hop);
+
+    const int tid = threadIdx.x, u = tid / G::LANES, l = tid % G::LANES;
+    stage_tables<kThreads>(tw_s, 32 * G::LANES, win_s, NF, P);
+    int tile = blockIdx.x;
+    int b = tile / TL.tiles;
+    TileGeom g = tile_geom<NF>(P, TL, tile - b * TL.tiles);
+    float* my = scratch + u * GeoV<NF>::SCRATCH;
+    // lane-private slots inside the unit's transpose scratch (dead between the last transpose read and the
+    // next tile's first transpose write): frame a's bins arrive there by cp.async, frame b's in registers
+    float2* slot = reinterpret_cast<float2*>(my) + l * 17;
+    static_assert(17 * 8 * G::LANES <= GeoV<NF>::SCRATCH * 4, "row staging must fit the transpose scratch");
+
+    float2 yb[17];
+    bool va_cur = false;
+    auto load_rows = [&](int bb, const TileGeom& gg) -> bool {
+        const int fa = gg.t_lo + 2 * u;
+        const bool va = fa <= gg.t_hi, vb = fa + 1 <= gg.t_hi;
+        const float2* xa_p = X + (size_t)bb * sb + (size_t)fa * st;
+        const float2* xb_p = xa_p + st;
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+            const int bin = bin_of<NF>(l, i);
+            const float2 z = make_float2(0.f, 0.f);
+            const size_t o = CONTIG ? (size_t)bin : (size_t)bin * sf;
+            if (va && bin >= 0)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(slot + i)), "l"(xa_p + o) : "memory");
+            yb[i] = (vb && bin >= 0) ? __ldg(xb_p + o) : z;
+        }
+        return va;
+    };
+    va_cur = load_rows(b, g);
+    stage_env<kThreads>(env_s, P.inv_env + g.s0, g.s1 - g.s0);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+
+    float* pbu = pb + u * strip;
+    const TwSmem<G::LANES> tw{tw_s, l};
+    const float* wl = win_s + l;
+    const int c0 = l - wlo, ovl = support - P.hop, two_hop = 2 * P.hop;
+    for (;;) {
+        float2 v[32];
+        {
+            float2 ya[17];
+#pragma unroll
+            for (int i = 0; i < 17; ++i)
+                ya[i] = (va_cur && bin_of<NF>(l, i) >= 0) ? slot[i] : make_float2(0.f, 0.f);
+            merge_regs<NF>(v, l, ya, yb);
+        }
+        unit_fft_inverse_v<NF>(v, l, tw, my);  // (starts with a __syncwarp: the unit's slot reads are done)
+        const int next = tile + gridDim.x;
+        const int cur_b = b, cur_tile = tile - b * TL.tiles;
+        const TileGeom cg = g;
+        // private strip of the unit: frame a at [0, support), frame b at [hop, hop + support)
+        // (the previous tile's epilogue finished reading the strips: barrier at the loop end)
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const int k = n1 * G::R2 + c0;
+            if ((unsigned)k < (unsigned)support) pbu[k] = v[n1].x * wl[n1 * G::R2];
+        }
+        if (ovl < 0)  // degenerate (hop > support, only legal for single-frame plans): clear the gap
+            for (int k = support + l; k < P.hop; k += G::LANES) pbu[k] = 0.0f;
+        __syncwarp();
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const int k = n1 * G::R2 + c0;
+            if ((unsigned)k < (unsigned)support) {
+                const float old = k < ovl ? pbu[P.hop + k] : 0.0f;
+                pbu[P.hop + k] = fmaf(v[n1].y, wl[n1 * G::R2], old);
+            }
+        }
+        if (next < total_tiles) {  // next tile's rows: in flight across the barrier and the epilogue
+            b = next / TL.tiles;
+            g = tile_geom<NF>(P, TL, next - b * TL.tiles);
+            __syncwarp();  // every lane of the unit is past its last transpose read
+            va_cur = load_rows(b, g);
+            cp_async_commit();
+            cp_async_wait_group<1>();  // this tile's envelope (older group) has landed; the rows may still fly
+        } else {
+            cp_async_wait_all();
+        }
+        __syncthreads();
+
+        // gather: VEC samples per step; strips covering offset x are u = x / two_hop, u-1, ... while k < lb
+        const int S = cg.s1 - cg.s0;
+        const int x0 = cg.p0 - (cg.t_lo * P.hop + wlo);
+        float* orow = out + (size_t)cur_b * P.n_out + cg.s0;
+        double acc0 = 0.0, acc1 = 0.0;
+        const float inv_two_hop = 1.0f / (float)two_hop;
+        for (int q = tid * VEC; q < S; q += kThreads * VEC) {
+            const int x = x0 + q;
+            int uu = min(UNITS - 1, (int)(((float)x + 0.5f) * inv_two_hop));  // exact: x < 2^20
+            int k = x - uu * two_hop;
+            V a = vzero<V>();
+            while (uu >= 0 && k < lb) {
+                vadd(a, *reinterpret_cast<const V*>(pb + uu * strip + k));
+                --uu;
+                k += two_hop;
+            }
+            if (VEC == 1 || q + VEC <= S) {
+                const V e = *reinterpret_cast<const V*>(env_s + q);
+                float sq;
+                const float sm = vmul_stats(a, e, sq);
+                *reinterpret_cast<V*>(orow + q) = a;
+                acc0 += (double)sm;
+                acc1 += (double)sq;
+            } else {  // ragged end of the clip (n_out not a multiple of VEC): element by element
+                const float* af = reinterpret_cast<const float*>(&a);
+                for (int j = 0; j < VEC && q + j < S; ++j) {
+                    const float y = af[j] * env_s[q + j];
+                    orow[q + j] = y;
+                    acc0 += (double)y;
+                    acc1 += (double)y * (double)y;
+                }
+            }
+        }
+        if (stats != nullptr) {
+            double acc[2] = {acc0, acc1};
+            block_sum<2>(acc, red);
+            if (tid == 0) {
+                double* srow = stats + ((size_t)cur_b * TL.tiles + cur_tile) * 2;
+                srow[0] = acc[0];
+                srow[1] = acc[1];
+            }
+        }
+        if (next >= total_tiles) break;
+        tile = next;
+        __syncthreads();  // strips, envelope tile and reduction scratch are free again
+        stage_env<kThreads>(env_s, P.inv_env + g.s0, g.s1 - g.s0);  // lands during the FFTs
+        cp_async_commit();
+        cp_async_wait_group<1>();  // own row copies (issued before the epilogue, long since landed)
     }
 }
 
@@ -937,10 +1495,96 @@ static int launch_stft_nf(const adv_plan* p, const float* wav, int64_t wav_strid
     return ADV_OK;
 }
 
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int NF, bool RECT>
+static int launch_stft_p(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
+                         float* phase, cudaStream_t s) {
+    constexpr int FT = PCfg<NF>::FT;
+    const size_t smem = PCfg<NF>::stft_bytes(p->d.hop);
+    const int tiles_per_clip = (p->d.T + FT - 1) / FT;
+    const long total = (long)tiles_per_clip * batch;
+    if (total > 0x7fffffffL) return ADV_ERR_UNSUPPORTED;
+    const int grid = (int)(total < 2L * sm_count() ? total : 2L * sm_count());
+    int rc;
+#define ADV_LAUNCH_STFT(M, PH)                                                                              \
+    do {                                                                                                    \
+        if ((rc = set_smem(stft_p_kernel<NF, M, PH, RECT>, smem)) != ADV_OK) return rc;                     \
+        stft_p_kernel<NF, M, PH, RECT><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total,      \
+                                                                     tiles_per_clip, X, mag, phase);        \
+    } while (0)
+    if (mag && phase) ADV_LAUNCH_STFT(true, true);
+    else if (mag) ADV_LAUNCH_STFT(true, false);
+    else if (phase) ADV_LAUNCH_STFT(false, true);
+    else ADV_LAUNCH_STFT(false, false);
+#undef ADV_LAUNCH_STFT
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+template <int NF, bool RECT>
+static int launch_stft_w(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
+                         float* phase, cudaStream_t s) {
+    using C = WCfg<NF>;
+    // bulk-async output staging where two CTAs per SM still fit (n_fft 512)
+    constexpr bool BULK = (NF == 512);
+    static const bool want_bulk = getenv("ADV_STFT_BULK") != nullptr;  // measured slower (22.3 vs 17.2 us): off
+    const bool bulk = BULK && want_bulk;
+    const size_t smem = C::stft_bytes(p->d.hop, bulk);
+    const int items_per_clip = (p->d.T + C::FW - 1) / C::FW;
+    const long total = (long)items_per_clip * batch;
+    if (total > 0x7fffffffL) return ADV_ERR_UNSUPPORTED;
+    const long ctas = (total + C::WARPS - 1) / C::WARPS;
+    const int grid = (int)(ctas < 2L * sm_count() ? ctas : 2L * sm_count());
+    int rc;
+#define ADV_LAUNCH_STFT(M, PH)                                                                              \
+    do {                                                                                                    \
+        if (bulk) {                                                                                         \
+            if ((rc = set_smem(stft_w_kernel<NF, M, PH, RECT, BULK>, smem)) != ADV_OK) return rc;           \
+            stft_w_kernel<NF, M, PH, RECT, BULK><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total, \
+                                                                           items_per_clip, X, mag, phase);  \
+        } else {                                                                                            \
+            if ((rc = set_smem(stft_w_kernel<NF, M, PH, RECT, false>, smem)) != ADV_OK) return rc;          \
+            stft_w_kernel<NF, M, PH, RECT, false><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total, \
+                                                                            items_per_clip, X, mag, phase); \
+        }                                                                                                   \
+    } while (0)
+    if (mag && phase) ADV_LAUNCH_STFT(true, true);
+    else if (mag) ADV_LAUNCH_STFT(true, false);
+    else if (phase) ADV_LAUNCH_STFT(false, true);
+    else ADV_LAUNCH_STFT(false, false);
+#undef ADV_LAUNCH_STFT
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
 int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
                 float* phase, cudaStream_t s) {
-    return p->d.n_fft == 512 ? launch_stft_nf<512>(p, wav, wav_stride, batch, X, mag, phase, s)
-                             : launch_stft_nf<1024>(p, wav, wav_stride, batch, X, mag, phase, s);
+    static const char* var = getenv("ADV_STFT");  // A/B switch: "v2" one tile per CTA, "p" persistent CTA tiles
+    const int which = var == nullptr ? 0 : (var[0] == 'v' ? 2 : (var[0] == 'p' ? 1 : 0));
+    if (which == 2)
+        return p->d.n_fft == 512 ? launch_stft_nf<512>(p, wav, wav_stride, batch, X, mag, phase, s)
+                                 : launch_stft_nf<1024>(p, wav, wav_stride, batch, X, mag, phase, s);
+    if (which == 1) {
+        if (p->d.n_fft == 512)
+            return p->d.rect_full ? launch_stft_p<512, true>(p, wav, wav_stride, batch, X, mag, phase, s)
+                                  : launch_stft_p<512, false>(p, wav, wav_stride, batch, X, mag, phase, s);
+        return p->d.rect_full ? launch_stft_p<1024, true>(p, wav, wav_stride, batch, X, mag, phase, s)
+                              : launch_stft_p<1024, false>(p, wav, wav_stride, batch, X, mag, phase, s);
+    }
+    if (p->d.n_fft == 512)
+        return p->d.rect_full ? launch_stft_w<512, true>(p, wav, wav_stride, batch, X, mag, phase, s)
+                              : launch_stft_w<512, false>(p, wav, wav_stride, batch, X, mag, phase, s);
+    return p->d.rect_full ? launch_stft_w<1024, true>(p, wav, wav_stride, batch, X, mag, phase, s)
+                          : launch_stft_w<1024, false>(p, wav, wav_stride, batch, X, mag, phase, s);
 }
 
 template <int NF>
@@ -956,10 +1600,51 @@ static int launch_istft_nf(const adv_plan* p, const float2* X, int64_t sb, int64
     return ADV_OK;
 }
 
+template <int NF, int VEC>
+static int launch_istft_p(const adv_plan* p, const Tiling& tl, const float2* X, int64_t sb, int64_t st, int64_t sf,
+                          int batch, float* out, double* stats, cudaStream_t s) {
+    const size_t smem = IPCfg<NF>::bytes(p->d.hop, p->d.whi - p->d.wlo, tl.hops_per_tile * p->d.hop);
+    const long total = (long)tl.tiles * batch;
+    if (total > 0x7fffffffL) return ADV_ERR_UNSUPPORTED;
+    const int grid = (int)(total < 2L * sm_count() ? total : 2L * sm_count());
+    int rc;
+    if (sf == 1) {
+        if ((rc = set_smem(istft_p_kernel<NF, VEC, true>, smem)) != ADV_OK) return rc;
+        istft_p_kernel<NF, VEC, true><<<grid, kThreads, smem, s>>>(p->d, tl, (int)total, X, sb, st, sf, out, stats);
+    } else {
+        if ((rc = set_smem(istft_p_kernel<NF, VEC, false>, smem)) != ADV_OK) return rc;
+        istft_p_kernel<NF, VEC, false><<<grid, kThreads, smem, s>>>(p->d, tl, (int)total, X, sb, st, sf, out, stats);
+    }
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+template <int NF>
+static int launch_istft_pv(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch,
+                           float* out, double* stats, cudaStream_t s) {
+    const Tiling tl = choose_tiling(p, batch);
+    // widest gather the geometry allows: hop, row pitch and base address must keep VEC-sample groups aligned
+    const uintptr_t base = reinterpret_cast<uintptr_t>(out);
+    int vec = 1;
+    if (p->d.hop % 4 == 0 && p->d.n_out % 4 == 0 && base % 16 == 0) vec = 4;
+    else if (p->d.hop % 2 == 0 && p->d.n_out % 2 == 0 && base % 8 == 0) vec = 2;
+    if (vec == 4) return launch_istft_p<NF, 4>(p, tl, X, sb, st, sf, batch, out, stats, s);
+    if (vec == 2) return launch_istft_p<NF, 2>(p, tl, X, sb, st, sf, batch, out, stats, s);
+    return launch_istft_p<NF, 1>(p, tl, X, sb, st, sf, batch, out, stats, s);
+}
+
 int launch_istft(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
                  double* stats, cudaStream_t s) {
-    return p->d.n_fft == 512 ? launch_istft_nf<512>(p, X, sb, st, sf, batch, out, stats, s)
-                             : launch_istft_nf<1024>(p, X, sb, st, sf, batch, out, stats, s);
+    static const bool v2 = getenv("ADV_ISTFT_V2") != nullptr;  // A/B switch: the one-tile-per-CTA kernel
+    if (v2)
+        return p->d.n_fft == 512 ? launch_istft_nf<512>(p, X, sb, st, sf, batch, out, stats, s)
+                                 : launch_istft_nf<1024>(p, X, sb, st, sf, batch, out, stats, s);
+    // n_fft 1024 (one unit per warp, 8 units per CTA): the persistent kernel measured slower than the
+    // one-tile-per-CTA kernel (51 vs 47 us on 64 x 5 s clips) - it spills around the row prefetch
+    static const bool p1024 = getenv("ADV_ISTFT_P1024") != nullptr;
+    if (p->d.n_fft == 512) return launch_istft_pv<512>(p, X, sb, st, sf, batch, out, stats, s);
+    return p1024 ? launch_istft_pv<1024>(p, X, sb, st, sf, batch, out, stats, s)
+                 : launch_istft_nf<1024>(p, X, sb, st, sf, batch, out, stats, s);
 }
 
 template <int NF, int MODE, bool FROM_SPEC>
