@@ -153,6 +153,18 @@ int run_w512() {
     for (int l = 0; l < L; ++l) w512::fwd_rows_local(V[l].data());
     O = V;
     for (int l = 0; l < L; ++l) w512::fwd_rows_combine(V[l].data(), l, O[l ^ 1].data());
+    {   // lean pair butterfly (twiddle on the odd lane, then v = other + sg v) must agree with the reference form
+        auto T = O, U = O;
+        for (int l = 0; l < L; ++l) w512::fwd_rows_tw(T[l].data(), l);
+        U = T;
+        for (int l = 0; l < L; ++l) w512::rows_bfly(T[l].data(), l, U[l ^ 1].data());
+        double d = 0;
+        for (int l = 0; l < L; ++l)
+            for (int m = 0; m < 16; ++m)
+                d = fmax(d, hypot((double)T[l][m].x - V[l][m].x, (double)T[l][m].y - V[l][m].y));
+        printf("W512 lean forward butterfly vs reference form: %.3e\n", d);
+        if (d > 1e-4) return 1;
+    }
     // split
     std::vector<std::vector<float2>> send(L, std::vector<float2>(8)), XA(L, std::vector<float2>(9)), XB(L, std::vector<float2>(9));
     for (int l = 0; l < L; ++l) w512::split_pre(V[l].data(), send[l].data());
@@ -184,6 +196,17 @@ int run_w512() {
     for (int l = 0; l < L; ++l) w512::merge_post(V[l].data(), l, send[w512::partner_row(l)].data());
     O = V;
     for (int l = 0; l < L; ++l) w512::inv_rows_combine(V[l].data(), l, O[l ^ 1].data());
+    {
+        auto T = O;
+        for (int l = 0; l < L; ++l) w512::rows_bfly(T[l].data(), l, O[l ^ 1].data());
+        for (int l = 0; l < L; ++l) w512::inv_rows_tw(T[l].data(), l);
+        double d = 0;
+        for (int l = 0; l < L; ++l)
+            for (int m = 0; m < 16; ++m)
+                d = fmax(d, hypot((double)T[l][m].x - V[l][m].x, (double)T[l][m].y - V[l][m].y));
+        printf("W512 lean inverse butterfly vs reference form: %.3e\n", d);
+        if (d > 1e-3) return 1;
+    }
     for (int l = 0; l < L; ++l) w512::inv_rows_local(V[l].data());
     for (int im = 0; im < 2; ++im) {
         for (int l = 0; l < L; ++l) w512::scr_store_rows(V[l].data(), l, scratch.data(), im);

@@ -45,8 +45,35 @@ static constexpr float kSin32[16] = {
     1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f,
     0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f};
 
+// Complex add / subtract / scaled add as ONE packed instruction on sm_100a (FADD2 / FFMA2 work on an aligned
+// 64-bit register pair).  Measured on B200: a packed instruction occupies the FMA pipe for two cycles, i.e. the
+// same lane throughput as two scalar ones, but takes a single issue slot - and these kernels are issue-bound
+// with more than half of their instructions outside the FMA pipe.  Bit-identical to the scalar forms.
+#if defined(__CUDA_ARCH__) && !defined(ADV_NO_F32X2)
+#define ADV_U64(v) (*reinterpret_cast<const unsigned long long*>(&(v)))
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    float2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r)) : "l"(ADV_U64(a)), "l"(ADV_U64(b)));
+    return r;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    float2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r)) : "l"(ADV_U64(a)), "l"(ADV_U64(b)));
+    return r;
+}
+// a * (s, s) + c
+__device__ __forceinline__ float2 cfma(float2 a, float2 s, float2 c) {
+    float2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+        : "l"(ADV_U64(a)), "l"(ADV_U64(s)), "l"(ADV_U64(c)));
+    return r;
+}
+#else
 ADV_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 ADV_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+ADV_HD float2 cfma(float2 a, float2 s, float2 c) { return make_float2(fmaf(a.x, s.x, c.x), fmaf(a.y, s.y, c.y)); }
+#endif
 ADV_HD float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -99,14 +126,15 @@ ADV_HD void butterfly(float2 e, float2 o, float2& lo, float2& hi) {
             p = DIR < 0 ? o.y - o.x : -(o.x + o.y);
             q = DIR < 0 ? -(o.x + o.y) : o.x - o.y;
         }
-        lo = make_float2(fmaf(p, h, e.x), fmaf(q, h, e.y));
-        hi = make_float2(fmaf(-p, h, e.x), fmaf(-q, h, e.y));
+        const float2 pq = make_float2(p, q);
+        lo = cfma(pq, make_float2(h, h), e);
+        hi = cfma(pq, make_float2(-h, -h), e);
     } else {
         constexpr int idx = K * (32 / N);
         constexpr float c = kCos32[idx];
         constexpr float s = (DIR < 0 ? -1.0f : 1.0f) * kSin32[idx];
         lo = make_float2(fmaf(o.x, c, fmaf(-o.y, s, e.x)), fmaf(o.x, s, fmaf(o.y, c, e.y)));
-        hi = make_float2(fmaf(2.0f, e.x, -lo.x), fmaf(2.0f, e.y, -lo.y));
+        hi = cfma(e, make_float2(2.0f, 2.0f), make_float2(-lo.x, -lo.y));
     }
 }
 
@@ -556,6 +584,33 @@ ADV_HD void inv_rows_combine(float2* v, int l, const float2* other) {
     });
 }
 ADV_HD void inv_rows_local(float2* v) { fft_inplace<16, +1>(v); }
+
+// Lean pair butterfly (same results as fwd_rows_combine / inv_rows_combine up to round-off, a third of the
+// instructions: no per-value selects).  Forward: the odd lane multiplies its half-row transform by W_32^m
+// BEFORE the exchange, then both lanes do  v = other + sg * v  (sg = +1 even lane, -1 odd lane).
+// Inverse: the same butterfly first, then the odd lane multiplies by W_32^{-m}.
+ADV_HD void fwd_rows_tw(float2* v, int l) {
+    if (l & 1) {
+        static_for<1, 16>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            v[m] = twmul<32, m, -1>(v[m]);
+        });
+    }
+}
+ADV_HD void rows_bfly(float2* v, int l, const float2* other) {
+    const float sg = (l & 1) ? -1.0f : 1.0f;
+    const float2 sg2 = make_float2(sg, sg);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = cfma(v[m], sg2, other[m]);
+}
+ADV_HD void inv_rows_tw(float2* v, int l) {
+    if (l & 1) {
+        static_for<1, 16>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            v[m] = twmul<32, m, +1>(v[m]);
+        });
+    }
+}
 
 // ---- split: Z (two packed real frames) -> 9 one-sided bins of each frame per lane ---------------------
 ADV_HD void split_pre(const float2* v, float2* send) {

@@ -1456,6 +1456,292 @@ explain_w512_kernel(PlanDev P, Tiling TL, const float* __restrict__ wav, int64_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused explain, n_fft = 512, persistent + software-pipelined (the production kernel of the hot path)
+//
+// One CTA per SM (512 threads = 16 wide units) walks the tile list.  While tile i is being transformed the
+// loads of tile i+1 are in flight and none of them passes through registers:
+//   * waveform segment: one bulk-async copy on an mbarrier (the buffer is free as soon as every thread holds
+//     its samples), reflect-padded clip edges by plain loads;
+//   * mask tile [257][32]: 4-byte cp.async with zero fill straight into the transposed shared-memory tile of
+//     the OTHER parity (two tiles), so the mask is never staged in registers;
+//   * plan tables once per CTA.
+// The overlap-add gather handles four consecutive samples per step (two 128-bit strip loads per covering
+// strip, 128-bit output stores, one index computation per group), the reciprocal envelope of those groups is
+// fetched into registers before the barrier, and the lane-pair radix-2 of the wide FFT is the lean form
+// (fft_core.cuh: twiddle on the odd lane, one FMA per component) instead of six selects per value.
+// Requires hop % 4 == 0, n_out % 4 == 0 and 16-byte aligned output rows (the launcher falls back to
+// explain_w512_kernel otherwise).
+// ------------------------------------------------------------------------------------------------
+struct PWideCfg {
+    static constexpr int UNITS = 16, FT = 32, MP = FT + 1, F = 257, NF = 512;
+    static __host__ __device__ int strip(int hop, int support) { return (hop + support + 4 + 3) & ~3; }
+    static __host__ __device__ size_t seg_floats(int hop) { return (size_t)(FT - 1) * hop + NF + 8; }
+    static size_t bytes(int hop, int support) {
+        return al16(sizeof(float2) * 512) + al16(sizeof(float) * UNITS * w512::SCRATCH) + al16(sizeof(float) * NF) +
+               al16(sizeof(float2) * UNITS * strip(hop, support)) + al16(sizeof(float) * seg_floats(hop)) +
+               al16(sizeof(double) * 4 * (kWideThreads / 32)) + 2 * al16(sizeof(float) * F * MP) + 16;
+    }
+};
+
+__device__ __forceinline__ void lean_fft_forward(float2* v, int l, TwWide tw, float* scr) {
+    w512::fwd_cols(v, tw);
+    __syncwarp();
+    w512::scr_store_cols(v, l, scr, false);
+    __syncwarp();
+    w512::scr_load_rows(v, l, scr, false);
+    __syncwarp();
+    w512::scr_store_cols(v, l, scr, true);
+    __syncwarp();
+    w512::scr_load_rows(v, l, scr, true);
+    w512::fwd_rows_local(v);
+    w512::fwd_rows_tw(v, l);
+    float2 other[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        other[m].x = __shfl_xor_sync(0xffffffffu, v[m].x, 1);
+        other[m].y = __shfl_xor_sync(0xffffffffu, v[m].y, 1);
+    }
+    w512::rows_bfly(v, l, other);
+}
+__device__ __forceinline__ void lean_fft_inverse(float2* v, int l, TwWide tw, float* scr) {
+    float2 other[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        other[m].x = __shfl_xor_sync(0xffffffffu, v[m].x, 1);
+        other[m].y = __shfl_xor_sync(0xffffffffu, v[m].y, 1);
+    }
+    w512::rows_bfly(v, l, other);
+    w512::inv_rows_tw(v, l);
+    w512::inv_rows_local(v);
+    __syncwarp();
+    w512::scr_store_rows(v, l, scr, false);
+    __syncwarp();
+    w512::scr_load_cols(v, l, scr, false);
+    __syncwarp();
+    w512::scr_store_rows(v, l, scr, true);
+    __syncwarp();
+    w512::scr_load_cols(v, l, scr, true);
+    w512::inv_cols(v, tw);
+}
+
+template <int MODE, bool RECT>
+__global__ void __launch_bounds__(kWideThreads, 1)
+explain_p512_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restrict__ wav, int64_t wav_stride,
+                    const float* __restrict__ mask, int Fm, int Tm, float* __restrict__ rel, float* __restrict__ irr,
+                    double* __restrict__ stats) {
+    using C = PWideCfg;
+    constexpr int UNITS = C::UNITS, FT = C::FT, MP = C::MP, F = C::F, NF = C::NF, NT = kWideThreads;
+    const int wlo = P.wlo & ~3;  // strip origin rounded down to a multiple of 4 (extra taps are exact zeros)
+    const int support = P.whi - wlo, lb = P.hop + support, strip = C::strip(P.hop, P.whi - P.wlo);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(512);
+    float* scratch = cv.take<float>(UNITS * w512::SCRATCH);
+    float* win_s = cv.take<float>(NF);
+    float2* pb = cv.take<float2>(UNITS * strip);
+    float* seg = cv.take<float>(C::seg_floats(P.hop));
+    double* red = cv.take<double>(4 * (NT / 32));
+    float* mask_all = cv.take<float>(2 * ((F * MP + 3) & ~3));
+    uint64_t* bar = cv.take<uint64_t>(1);
+    constexpr int kMaskTile = (F * MP + 3) & ~3;
+
+    const int tid = threadIdx.x, u = tid >> 5, l = tid & 31;
+    const int seglen = (FT - 1) * P.hop + NF;
+    int tile = blockIdx.x;
+    int b = tile / TL.tiles;
+    TileGeom g = tile_geom<NF>(P, TL, tile - b * TL.tiles);
+
+    // every load of a tile that can be requested ahead of time: segment (bulk + plain edges), mask tile
+    auto request_tile = [&](int bb, const TileGeom& gg, float* mask_dst) {
+        stage_segment_async<NT>(seg, seglen, wav + (size_t)bb * wav_stride, gg.t_lo * P.hop - NF / 2, P.n_in, bar);
+        const float* mrow = mask + (size_t)bb * Fm * Tm;
+        constexpr int kTrips = (F * FT + NT - 1) / NT;
+#pragma unroll
+        for (int j = 0; j < kTrips; ++j) {
+            const int e = tid + j * NT;
+            if (e < F * FT) {
+                const int f = e >> 5, c = e & 31;
+                const int t = gg.t_lo + c;
+                const bool ok = f < Fm && t < Tm && t <= gg.t_hi;
+                const float* src = ok ? mrow + (size_t)f * Tm + t : mrow;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(mask_dst + f * MP + c)), "l"(src),
+                             "r"(ok ? 4 : 0)
+                             : "memory");
+            }
+        }
+        cp_async_commit();
+    };
+
+    if (tid == 0) mbar_init(bar, 1);
+    {   // plan table is [32][16] (exp(-2 pi i a b / 512), symmetric in a, b): transpose to [16 k1][32 lanes]
+        tw_s[(tid & 15) * 32 + (tid >> 4)] = P.tw[tid];
+        win_s[tid] = P.window[tid];
+    }
+    __syncthreads();
+    request_tile(b, g, mask_all);
+    const int shift0 = (g.t_lo * P.hop - NF / 2) & 3;
+    int shift = shift0;
+
+    float* my = scratch + u * w512::SCRATCH;
+    const TwWide tw{tw_s, l};
+    const float* wl = win_s + l;
+    const int prt = w512::partner_row(l);
+    float2* pbu = pb + u * strip;
+    const int c0 = l - wlo, ovl = support - P.hop, two_hop = 2 * P.hop;
+    const float inv_two_hop = 1.0f / (float)two_hop;
+
+    for (uint32_t it = 0;; ++it) {
+        const float* mask_s = mask_all + (it & 1) * kMaskTile;
+        cp_async_wait_all();
+        __syncthreads();  // mask tile + plain part of the segment visible; the previous epilogue is over
+        mbar_wait(bar, it & 1);
+        float2 v[16];
+        {
+            const float* sa = seg + shift + (2 * u) * P.hop + l;
+            const float* sbp = sa + P.hop;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+                const float w = RECT ? 1.0f : wl[n1 * 32];
+                v[n1] = make_float2(sa[n1 * 32] * w, sbp[n1 * 32] * w);
+            }
+        }
+        const int cur_b = b, cur_tile = tile - b * TL.tiles;
+        const TileGeom cg = g;
+        const int next = tile + gridDim.x;
+        __syncthreads();  // every thread holds its samples: the segment buffer is free
+        if (next < total_tiles) {
+            b = next / TL.tiles;
+            g = tile_geom<NF>(P, TL, next - b * TL.tiles);
+            request_tile(b, g, mask_all + ((it + 1) & 1) * kMaskTile);
+            shift = (g.t_lo * P.hop - NF / 2) & 3;
+        }
+
+        float2 xa[9], xb[9];
+        lean_fft_forward(v, l, tw, my);
+        {
+            float2 send[8], recv[8];
+            w512::split_pre(v, send);
+            wide_exchange8(send, recv, prt);
+            w512::split_post(v, l, recv, xa, xb);
+        }
+        const int fa = cg.t_lo + 2 * u;
+        if (ovl < 0)
+            for (int k = support + l; k < P.hop; k += 32) pbu[k] = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const bool valid = fa + half <= cg.t_hi;
+            const int col = 2 * u + half;
+            {
+                float2 yr[9], yi[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    const int bin = w512::bin_of(l, i);
+                    const bool live = bin >= 0 && valid;
+                    const float m = live ? mask_s[bin * MP + col] : 0.0f;
+                    float gr, gi;
+                    mask_gains<MODE>(xa[i], m, gr, gi);
+                    yr[i] = live ? make_float2(xa[i].x * gr, xa[i].y * gr) : make_float2(0.f, 0.f);
+                    yi[i] = live ? make_float2(xa[i].x * gi, xa[i].y * gi) : make_float2(0.f, 0.f);
+                }
+                float2 send[8], recv[8];
+                w512::merge_pre(v, l, yr, yi, send);
+                wide_exchange8(send, recv, prt);
+                w512::merge_post(v, l, recv);
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) xa[i] = xb[i];
+            lean_fft_inverse(v, l, tw, my);
+            float2* dst = pbu + half * P.hop;
+            const int keep = half ? ovl : 0;
+            if (RECT) {
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    const int k = n1 * 32 + l;
+                    float2 o = v[n1];
+                    if (k < keep) {
+                        const float2 prev = dst[k];
+                        o.x += prev.x;
+                        o.y += prev.y;
+                    }
+                    dst[k] = o;
+                }
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    const int k = n1 * 32 + c0;
+                    if ((unsigned)k < (unsigned)support) {
+                        const float w = wl[n1 * 32];
+                        float2 o = k < keep ? dst[k] : make_float2(0.f, 0.f);
+                        o.x = fmaf(v[n1].x, w, o.x);
+                        o.y = fmaf(v[n1].y, w, o.y);
+                        dst[k] = o;
+                    }
+                }
+            }
+            __syncwarp();  // frame a's strip stores are visible to the unit before frame b's read-modify-write
+        }
+
+        // reciprocal envelope of this thread's first groups: requested before the barrier
+        const int S = cg.s1 - cg.s0;
+        const float* erow = P.inv_env + cg.s0;
+        constexpr int kEnvRegs = 3;
+        float4 e4[kEnvRegs];
+#pragma unroll
+        for (int j = 0; j < kEnvRegs; ++j) {
+            const int q = (tid + j * NT) * 4;
+            e4[j] = q + 4 <= S ? __ldg(reinterpret_cast<const float4*>(erow + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        float* rrow = rel + (size_t)cur_b * P.n_out + cg.s0;
+        float* irow = irr + (size_t)cur_b * P.n_out + cg.s0;
+        const int x0 = cg.p0 - (cg.t_lo * P.hop + wlo);
+        auto group = [&](int q, float4 e) {
+            const int x = x0 + q;
+            int uu = min(UNITS - 1, (int)(((float)x + 0.5f) * inv_two_hop));
+            int k = x - uu * two_hop;
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f), ir = r;
+            while (uu >= 0 && k < lb) {
+                const float4* p = reinterpret_cast<const float4*>(pb + uu * strip + k);
+                const float4 a = p[0], c = p[1];
+                r.x += a.x; ir.x += a.y; r.y += a.z; ir.y += a.w;
+                r.z += c.x; ir.z += c.y; r.w += c.z; ir.w += c.w;
+                --uu;
+                k += two_hop;
+            }
+            r.x *= e.x; r.y *= e.y; r.z *= e.z; r.w *= e.w;
+            ir.x *= e.x; ir.y *= e.y; ir.z *= e.z; ir.w *= e.w;
+            *reinterpret_cast<float4*>(rrow + q) = r;
+            *reinterpret_cast<float4*>(irow + q) = ir;
+            acc[0] += (double)((r.x + r.y) + (r.z + r.w));
+            acc[1] += (double)(fmaf(r.x, r.x, r.y * r.y) + fmaf(r.z, r.z, r.w * r.w));
+            acc[2] += (double)((ir.x + ir.y) + (ir.z + ir.w));
+            acc[3] += (double)(fmaf(ir.x, ir.x, ir.y * ir.y) + fmaf(ir.z, ir.z, ir.w * ir.w));
+        };
+#pragma unroll
+        for (int j = 0; j < kEnvRegs; ++j) {
+            const int q = (tid + j * NT) * 4;
+            if (q + 4 <= S) group(q, e4[j]);
+        }
+        for (int q = (tid + kEnvRegs * NT) * 4; q + 4 <= S; q += NT * 4)  // (tiles longer than 6144 samples)
+            group(q, __ldg(reinterpret_cast<const float4*>(erow + q)));
+        if (stats != nullptr) {
+            block_sum<4, NT>(acc, red);
+            if (tid == 0) {
+                double* srow = stats + ((size_t)cur_b * TL.tiles + cur_tile) * 4;
+                srow[0] = acc[0];
+                srow[1] = acc[1];
+                srow[2] = acc[2];
+                srow[3] = acc[3];
+            }
+        }
+        if (next >= total_tiles) break;
+        tile = next;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
 // cudaFuncSetAttribute once per (kernel, size high-water mark): keeps the launch path free of
@@ -1687,6 +1973,28 @@ int launch_explain(const adv_plan* p, const float* wav, int64_t wav_stride, cons
     const Tiling tl = choose_tiling(p, batch);
     const bool spec = (X != nullptr);
     static const bool narrow = getenv("ADV_EXPLAIN_NARROW") != nullptr;  // keep the 16-lane-unit kernel reachable
+    static const bool oldwide = getenv("ADV_EXPLAIN_W512") != nullptr;   // A/B: the one-tile-per-CTA wide kernel
+    if (p->d.n_fft == 512 && !narrow && !oldwide && !spec && p->d.hop % 4 == 0 && p->d.n_out % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(rel) & 15) == 0 && (reinterpret_cast<uintptr_t>(irr) & 15) == 0 &&
+        (tl.hops_per_tile * p->d.hop) % 4 == 0) {
+        const size_t smem = PWideCfg::bytes(p->d.hop, p->d.whi - p->d.wlo);
+        const long total = (long)tl.tiles * batch;
+        if (smem <= 227 * 1024 && total <= 0x7fffffffL) {
+            const int grid = (int)(total < sm_count() ? total : sm_count());
+            int rc;
+#define ADV_PWIDE(MODE, RECT)                                                                                   \
+    do {                                                                                                        \
+        if ((rc = set_smem(explain_p512_kernel<MODE, RECT>, smem)) != ADV_OK) return rc;                        \
+        explain_p512_kernel<MODE, RECT><<<grid, kWideThreads, smem, s>>>(p->d, tl, (int)total, wav, wav_stride,  \
+                                                                         mask, Fm, Tm, rel, irr, stats);        \
+    } while (0)
+            if (mode == ADV_MASK_LOG1P) { if (p->d.rect_full) ADV_PWIDE(ADV_MASK_LOG1P, true); else ADV_PWIDE(ADV_MASK_LOG1P, false); }
+            else { if (p->d.rect_full) ADV_PWIDE(ADV_MASK_LINEAR, true); else ADV_PWIDE(ADV_MASK_LINEAR, false); }
+#undef ADV_PWIDE
+            ADV_CUDA_CHECK(cudaGetLastError());
+            return ADV_OK;
+        }
+    }
     if (p->d.n_fft == 512 && !narrow) {
 #define ADV_WIDE(MODE, SPEC) \
     return launch_explain_wide<MODE, SPEC>(p, tl, wav, wav_stride, X, sb, st, sf, mask, Fm, Tm, batch, rel, irr, stats, s)
