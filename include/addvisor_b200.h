@@ -159,6 +159,13 @@ int adv_conv1d_bf16(const void* in, const void* w, const float* bias, const void
 int adv_conv1d_bf16_tma(const void* in, const void* w, const float* bias, const void* resid, void* out_raw,
                         void* out_act, int batch, int L, int Cin, int taps, int dil, int N, float act_slope,
                         float out_scale, void* stream);
+/* Fused residual unit of a HiFi-GAN ResBlock1 (hifigan.py:180 via SpeechBrain's generator), C = 32 or 64 channels:
+ *   out = conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 + x,  conv1 dilation `dil`, conv2 dilation 1, both `taps` wide,
+ * zero "same" padding.  x / out dev bf16 [B][L][C]; w1 / w2 dev bf16 [C][taps*C] (K index = tap*C + ci); biases fp32.
+ * One persistent tcgen05 kernel: the intermediate never leaves the SM.  ADV_ERR_UNSUPPORTED when both weight sets do
+ * not fit in shared memory (C = 64 with 11 taps): run the two convs with adv_conv1d_bf16_tma instead. */
+int adv_resunit_bf16(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, void* out, int batch,
+                     int L, int C, int taps, int dil, float slope, void* stream);
 /* mel [B][C][T] fp32 -> channels-last bf16 [B][T+2*pad][Cpad], replicate-padded in time (inference_padding) */
 int adv_mel_to_channels_last(const float* mel, int batch, int C, int T, int pad, int Cpad, void* out, void* stream);
 /* MRF average of the three resblock outputs (bf16, n elements), then LeakyReLU(act_slope) (1 = identity) */

@@ -95,6 +95,52 @@ def test_conv1d_tma_matches_torch(pkg, H, B, L, Cin, Cout, k, dil, use_resid):
     assert rel_l2(act.float().cpu().transpose(1, 2), F.leaky_relu(ref, 0.1)) < 4e-3
 
 
+RESUNIT_CASES = [
+    # B, L, C, k, dil
+    (2, 500, 64, 3, 1),
+    (3, 257, 64, 7, 5),      # 158-row slab, ragged L, tiles of 122 outputs
+    (2, 1000, 64, 3, 5),
+    (2, 300, 32, 11, 5),     # 64-byte swizzle: intermediate written with the 2-bit XOR pattern
+    (40, 700, 32, 7, 3),     # more tiles than resident CTAs: barrier phases over many iterations
+    (1, 100, 32, 3, 1),      # single partial tile
+    (2, 131, 64, 7, 1),
+]
+
+
+@pytest.mark.parametrize("B,L,C,k,dil", RESUNIT_CASES)
+def test_fused_resunit_matches_torch(pkg, H, B, L, C, k, dil):
+    """conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 + x in one kernel vs torch fp32 with the bf16 roundings of the
+    unfused path modelled (activated input and intermediate are bf16)."""
+    from importlib import import_module
+    L_ = import_module("xai-audio-deepfakes_b200._lib")
+    g = torch.Generator().manual_seed(B * L + C + k + dil)
+    x = bf16r(torch.randn(B, C, L, generator=g))
+    w1 = bf16r(0.1 * torch.randn(C, C, k, generator=g))
+    w2 = bf16r(0.1 * torch.randn(C, C, k, generator=g))
+    b1 = 0.1 * torch.randn(C, generator=g)
+    b2 = 0.1 * torch.randn(C, generator=g)
+    xt = bf16r(F.leaky_relu(V._conv(bf16r(F.leaky_relu(x, 0.1)), w1, b1, dil, False), 0.1))
+    ref = V._conv(xt, w2, b2, 1, False) + x
+    x_cl = x.transpose(1, 2).contiguous().to(torch.bfloat16).cuda()
+    gw = lambda w: w.permute(0, 2, 1).reshape(C, -1).to(torch.bfloat16).contiguous().cuda()
+    out = torch.empty_like(x_cl)
+    w1g, w2g, b1g, b2g = gw(w1), gw(w2), b1.cuda(), b2.cuda()
+    L_.check(L_.lib().adv_resunit_bf16(L_.ptr(x_cl), L_.ptr(w1g), L_.ptr(b1g), L_.ptr(w2g), L_.ptr(b2g), L_.ptr(out),
+                                       B, L, C, k, dil, 0.1, L_.stream_ptr()), "adv_resunit_bf16")
+    assert rel_l2(out.float().cpu().transpose(1, 2), ref) < 4e-3
+
+
+def test_fused_resunit_rejects_oversized(pkg):
+    from importlib import import_module
+    L_ = import_module("xai-audio-deepfakes_b200._lib")
+    x = torch.zeros(1, 200, 64, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(64, 11 * 64, dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros(64, device="cuda")
+    rc = L_.lib().adv_resunit_bf16(L_.ptr(x), L_.ptr(w), L_.ptr(b), L_.ptr(w), L_.ptr(b), L_.ptr(x), 1, 200, 64, 11, 1,
+                                   0.1, L_.stream_ptr())
+    assert rc == L_.ADV_ERR_UNSUPPORTED   # two 11-tap weight sets of 64 channels exceed shared memory
+
+
 CONV_CASES = [
     # B, L, Cin, Cout, k, dil, reflect, pre_slope, resid
     (2, 300, 64, 64, 3, 1, False, 1.0, False),
@@ -186,4 +232,7 @@ def test_hifigan_generator_matches_oracle(pkg, H, reflect, pipeline):
     # vs the oracle with bf16 storage of activations modelled: tighter
     refq = V.generator(mel, Wq, reflect=reflect, quantize=bf16r)
     assert rel_l2(wav, refq) < 1e-2, rel_l2(wav, refq)
-    assert gen.launches == 1 + 4 * (1 + 18)   # conv_pre + 4 x (upsample + 3 resblocks x 3 x 2 convs)
+    if pipeline == "tma":   # 64- and 32-channel stages: fused residual units (k 11 at 64 channels stays unfused)
+        assert gen.launches == 1 + 2 * (1 + 18) + (1 + 3 + 3 + 6) + (1 + 9)
+    else:
+        assert gen.launches == 1 + 4 * (1 + 18)   # conv_pre + 4 x (upsample + 3 resblocks x 3 x 2 convs)

@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libaddvisor_sm100.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "transform_kernels.cu", "pointwise_kernels.cu", "gemm_kernels.cu", "conv_tma_kernels.cu"]
+SOURCES = ["capi.cu", "transform_kernels.cu", "pointwise_kernels.cu", "gemm_kernels.cu", "conv_tma_kernels.cu",
+           "resunit_kernels.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC"]
 
@@ -93,6 +94,8 @@ _SIGS.update({
                                   C.c_void_p]),
     "adv_conv1d_bf16_tma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "adv_resunit_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "adv_mel_to_channels_last": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                            C.c_void_p]),
     "adv_avg3_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),

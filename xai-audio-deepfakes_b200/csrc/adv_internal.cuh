@@ -48,6 +48,30 @@ int launch_explain(const adv_plan* p, const float* wav, int64_t wav_stride, cons
                    float* irr, double* stats, cudaStream_t s);
 }  // namespace adv
 
+// Co-resident CTAs per SM of a persistent kernel, from the resources themselves (registers as compiled, dynamic +
+// static + 1 KB reserved shared memory per CTA out of 228 KB, TMEM columns out of 512).  The occupancy API was
+// measured to answer 1 for these large-dynamic-shared-memory kernels on this driver, which halved the grids.
+template <class K>
+static inline int adv_resident_ctas(K kernel, int threads, size_t dyn_smem, int tmem_cols, int cap) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return 1;
+    const int warps = (threads + 31) / 32;
+    const int regs_per_warp = ((fa.numRegs + 7) / 8) * 8 * 32;
+    int n = regs_per_warp > 0 ? 65536 / (regs_per_warp * warps) : cap;
+    const size_t per_cta = dyn_smem + fa.sharedSizeBytes + 1024;
+    const int by_smem = (int)((size_t)228 * 1024 / per_cta);
+    if (n > by_smem) n = by_smem;
+    if (tmem_cols > 0) {
+        int cols = 32;
+        while (cols < tmem_cols) cols <<= 1;
+        if (n > 512 / cols) n = 512 / cols;
+    }
+    const int by_threads = 2048 / (warps * 32);
+    if (n > by_threads) n = by_threads;
+    if (n > cap) n = cap;
+    return n < 1 ? 1 : n;
+}
+
 #define ADV_CUDA_CHECK(expr)                         \
     do {                                             \
         cudaError_t _e = (expr);                     \

@@ -553,11 +553,7 @@ static int resident_ctas(K kernel, size_t smem, int tmem_cols) {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
-    int n = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kConvThreads, smem) != cudaSuccess || n < 1) n = 1;
-    const int by_tmem = 512 / (tmem_cols < 32 ? 32 : tmem_cols);
-    if (n > by_tmem) n = by_tmem;
-    if (n > 4) n = 4;
+    const int n = adv_resident_ctas(kernel, kConvThreads, smem, tmem_cols, 4);
     cache[key] = n;
     return n;
 }

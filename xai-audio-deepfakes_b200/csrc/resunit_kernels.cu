@@ -1,0 +1,395 @@
+// Fused HiFi-GAN residual unit for the narrow MRF stages (C = 32 / 64 channels), sm_100a:
+//
+//     y = conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 + x          (one (convs1[d], convs2[d]) pair of a ResBlock1)
+//
+// Reference call site: hifi_gan.decode_batch, hifigan.py:180 (SpeechBrain HifiganGenerator ResBlock1).
+//
+// Run as two conv kernels these layers are HBM-bound, not tensor-bound: per output position conv1 reads the
+// activated input and writes the activated intermediate, conv2 reads it back plus the raw residual and
+// writes a raw and an activated copy - 6 tensor passes for 2 convs.  Here ONE persistent kernel reads the raw
+// input once and writes the raw output once; everything in between stays on the SM:
+//   * warp 0 (producer): both weight sets resident in shared memory (TMA, once), then per tile one TMA slab of
+//     128 + (k-1)*dil raw rows (out-of-range rows zero-filled = the conv's padding), double-buffered;
+//   * warps 2-5 (128 threads): LeakyReLU pass slab -> activated slab (same swizzled addresses, so the layout
+//     does not matter), then epilogue 1 (TMEM -> +b1 -> LeakyReLU -> bf16 -> the canonical K-major swizzled
+//     intermediate slab, rows outside [0, L) zeroed = conv2's padding) and epilogue 2 (TMEM -> +b2 -> +residual
+//     taken from the raw slab already in shared memory -> global);
+//   * warp 1 (MMA issuer): conv1 = taps x C/16 tcgen05.mma over row-shifted descriptors of the activated slab
+//     (tap j = start address + j*dil rows), conv2 the same over the intermediate slab (dil 1).
+// A tile yields 128 - (k-1) output positions: conv1 computes exactly the 128 intermediate rows conv2 needs;
+// conv2 runs M = 128 and its last k-1 rows (which would read past the intermediate) are discarded.
+// Schedule: conv2(i) overlaps the LeakyReLU pass of tile i+1, conv1(i+1) overlaps epilogue 2 of tile i; two
+// CTAs per SM where shared memory allows cover the rest.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+#include "adv_internal.cuh"
+#include "umma.cuh"
+
+namespace adv {
+
+using namespace umma;
+
+namespace {
+
+constexpr int kRuThreads = 192;
+
+struct ResUnitArgs {
+    const float* b1;
+    const float* b2;
+    __nv_bfloat16* out;  // [B][L][C]
+    int B, L, taps, dil;
+    int h2, halo1, rows;  // (taps-1)/2, h2*dil, 128 + 2*halo1 (TMA box height)
+    int TO, tiles_l;      // outputs per tile = 128 - (taps-1); tiles per clip
+    int nbuf;             // raw-slab buffers: 2, or 1 when that lets a second CTA share the SM
+    float slope;
+};
+
+__device__ __forceinline__ void ru_tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void ru_tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void ru_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ru_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+template <int C>
+__device__ __forceinline__ uint64_t ru_desc(uint32_t saddr) {
+    constexpr uint32_t row_bytes = C * 2;
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;  // SWIZZLE_128B / SWIZZLE_64B
+    return d;
+}
+// byte offset of (row, 16-byte chunk) in a K-major swizzled slab whose base is 1024-byte aligned: the
+// hardware XORs the chunk bits with address bits [7, 10) (128-byte rows) / [7, 9) (64-byte rows)
+template <int C>
+__device__ __forceinline__ uint32_t ru_off(int row, int chunk) {
+    if (C == 64) return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+    return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ float lrelu(float x, float s) { return x > 0.0f ? x : x * s; }
+
+// The per-tile chain TMA -> LeakyReLU pass -> conv1 -> epilogue 1 -> conv2 -> epilogue 2 is a sequence of
+// mbarrier hand-offs (measured: ~4.5 us per tile per CTA whatever the tap count), so throughput comes from
+// co-resident CTAs: registers are capped so that 4 (C = 32) / 2 (C = 64) CTAs fit an SM when shared memory allows.
+template <int C>
+__global__ void __launch_bounds__(kRuThreads, C == 32 ? 4 : 2)
+resunit_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+               const __grid_constant__ CUtensorMap map_w2, ResUnitArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kRow = C * 2, kWTile = C * kRow, kChunks = kRow / 16;
+    const int slab_bytes = (a.rows * kRow + 1023) & ~1023;
+    const int mid_bytes = ((128 + a.taps - 1) * kRow + 1023) & ~1023;
+    unsigned char* w1s = smem;                              // [taps][C x C]
+    unsigned char* w2s = w1s + a.taps * kWTile;
+    unsigned char* raw = w2s + a.taps * kWTile;             // [2][slab_bytes]
+    unsigned char* act = raw + a.nbuf * slab_bytes;
+    unsigned char* mid = act + slab_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(mid + mid_bytes);
+    uint64_t* wbar = bars;                                  // weights resident
+    uint64_t* raw_full = bars + 1;                          // [2]
+    uint64_t* raw_empty = bars + 3;                         // [2]
+    uint64_t* act_full = bars + 5;
+    uint64_t* acc1_full = bars + 6;
+    uint64_t* mid_full = bars + 7;
+    uint64_t* acc2_full = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    constexpr uint32_t kCols = 2 * C < 32 ? 32 : 2 * C;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        bar_init(wbar, 1);
+        for (int i = 0; i < 2; ++i) {
+            bar_init(&raw_full[i], 1);
+            bar_init(&raw_empty[i], 4);
+        }
+        bar_init(act_full, 4);
+        bar_init(acc1_full, 1);
+        bar_init(mid_full, 4);
+        bar_init(acc2_full, 1);
+        bar_init_fence();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kCols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const long total_tiles = (long)a.B * a.tiles_l;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            ru_expect_tx(wbar, 2 * a.taps * kWTile);
+            for (int tap = 0; tap < a.taps; ++tap) {
+                ru_tma_load_2d(w1s + tap * kWTile, &map_w1, wbar, tap * C, 0);
+                ru_tma_load_2d(w2s + tap * kWTile, &map_w2, wbar, tap * C, 0);
+            }
+            uint32_t it = 0;
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int b = (int)(tile / a.tiles_l), o0 = (int)(tile % a.tiles_l) * a.TO;
+                const int s = a.nbuf == 2 ? (it & 1) : 0, ph = a.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+                bar_wait(&raw_empty[s], ph ^ 1);
+                ru_expect_tx(&raw_full[s], a.rows * kRow);
+                ru_tma_load_3d(raw + s * slab_bytes, &map_x, &raw_full[s], 0, o0 - a.h2 - a.halo1, b);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, C);
+            const uint32_t acc1 = tmem_base, acc2 = tmem_base + C;
+            const uint32_t act_a = smem_addr(act), mid_a = smem_addr(mid);
+            bar_wait(wbar, 0);
+            uint32_t it = 0;
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t ph = it & 1;
+                bar_wait(act_full, ph);
+                fence_after_sync();
+                for (int tap = 0; tap < a.taps; ++tap) {
+                    const uint64_t da = ru_desc<C>(act_a + tap * a.dil * kRow);
+                    const uint64_t db = ru_desc<C>(smem_addr(w1s + tap * kWTile));
+#pragma unroll
+                    for (int k = 0; k < C / 16; ++k) mma_f16(acc1, da + 2 * k, db + 2 * k, idesc, (tap | k) != 0);
+                }
+                mma_commit(acc1_full);
+                bar_wait(mid_full, ph);
+                fence_after_sync();
+                for (int tap = 0; tap < a.taps; ++tap) {
+                    const uint64_t da = ru_desc<C>(mid_a + tap * kRow);
+                    const uint64_t db = ru_desc<C>(smem_addr(w2s + tap * kWTile));
+#pragma unroll
+                    for (int k = 0; k < C / 16; ++k) mma_f16(acc2, da + 2 * k, db + 2 * k, idesc, (tap | k) != 0);
+                }
+                mma_commit(acc2_full);
+            }
+        }
+    } else {
+        // ------------------------------ activation + epilogues (4 warps) ------------------------------
+        const int quad = warp & 3;            // TMEM lanes 32*quad .. +31 belong to this warp
+        const int et = threadIdx.x - 64;      // 0..127
+        const int r = quad * 32 + lane;       // accumulator row of this thread
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int n16 = a.rows * kChunks;     // 16-byte chunks of a slab
+
+        auto act_pass = [&](uint32_t it) {
+            const int s = a.nbuf == 2 ? (it & 1) : 0, ph = a.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+            bar_wait(&raw_full[s], ph);
+            const int4* src = reinterpret_cast<const int4*>(raw + s * slab_bytes);
+            int4* dst = reinterpret_cast<int4*>(act);
+            for (int i = et; i < n16; i += 128) {
+                int4 v = src[i];
+                __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(p[j]);
+                    p[j] = __floats2bfloat162_rn(lrelu(f.x, a.slope), lrelu(f.y, a.slope));
+                }
+                dst[i] = v;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) ru_arrive(act_full);
+        };
+
+        uint32_t it = 0;
+        if ((long)blockIdx.x < total_tiles) act_pass(0);
+        for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int b = (int)(tile / a.tiles_l), o0 = (int)(tile % a.tiles_l) * a.TO;
+            const uint32_t ph = it & 1;
+            // ---- epilogue 1: intermediate row r <-> position o0 - h2 + r ----
+            {
+                const int m = o0 - a.h2 + r;
+                const bool inside = m >= 0 && m < a.L;
+                bar_wait(acc1_full, ph);
+                fence_after_sync();
+#pragma unroll 1
+                for (int c0 = 0; c0 < C; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(trow + c0, v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        int4 o = make_int4(0, 0, 0, 0);
+                        if (inside) {
+                            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+                            const float4 ba = __ldg(reinterpret_cast<const float4*>(a.b1 + c0 + 8 * q));
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(a.b1 + c0 + 8 * q) + 1);
+                            op[0] = __floats2bfloat162_rn(lrelu(v[8 * q] + ba.x, a.slope), lrelu(v[8 * q + 1] + ba.y, a.slope));
+                            op[1] = __floats2bfloat162_rn(lrelu(v[8 * q + 2] + ba.z, a.slope), lrelu(v[8 * q + 3] + ba.w, a.slope));
+                            op[2] = __floats2bfloat162_rn(lrelu(v[8 * q + 4] + bb.x, a.slope), lrelu(v[8 * q + 5] + bb.y, a.slope));
+                            op[3] = __floats2bfloat162_rn(lrelu(v[8 * q + 6] + bb.z, a.slope), lrelu(v[8 * q + 7] + bb.w, a.slope));
+                        }
+                        *reinterpret_cast<int4*>(mid + ru_off<C>(r, c0 / 8 + q)) = o;
+                    }
+                }
+                fence_async_smem();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ru_arrive(mid_full);
+            }
+            // ---- next tile's LeakyReLU pass runs while conv2 of this tile is on the tensor core (with a single
+            //      raw buffer the slab is still needed for this tile's residual: the pass follows epilogue 2) ----
+            if (a.nbuf == 2 && tile + gridDim.x < total_tiles) act_pass(it + 1);
+            // ---- epilogue 2: output row r <-> position o0 + r (r < TO), residual from the raw slab ----
+            {
+                const int s = a.nbuf == 2 ? (it & 1) : 0;
+                const int l = o0 + r;
+                const bool ok = r < a.TO && l < a.L;
+                const unsigned char* rs = raw + s * slab_bytes;
+                const int rr = r + a.h2 + a.halo1;
+                bar_wait(acc2_full, ph);
+                fence_after_sync();
+                __nv_bfloat16* orow = a.out + ((size_t)b * a.L + l) * C;
+#pragma unroll 1
+                for (int c0 = 0; c0 < C; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(trow + C + c0, v);
+                    if (ok) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int4 rv = *reinterpret_cast<const int4*>(rs + ru_off<C>(rr, c0 / 8 + q));
+                            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                            const float4 ba = __ldg(reinterpret_cast<const float4*>(a.b2 + c0 + 8 * q));
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(a.b2 + c0 + 8 * q) + 1);
+                            const float2 r0 = __bfloat1622float2(rp[0]), r1 = __bfloat1622float2(rp[1]);
+                            const float2 r2 = __bfloat1622float2(rp[2]), r3 = __bfloat1622float2(rp[3]);
+                            int4 o;
+                            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+                            op[0] = __floats2bfloat162_rn(v[8 * q] + ba.x + r0.x, v[8 * q + 1] + ba.y + r0.y);
+                            op[1] = __floats2bfloat162_rn(v[8 * q + 2] + ba.z + r1.x, v[8 * q + 3] + ba.w + r1.y);
+                            op[2] = __floats2bfloat162_rn(v[8 * q + 4] + bb.x + r2.x, v[8 * q + 5] + bb.y + r2.y);
+                            op[3] = __floats2bfloat162_rn(v[8 * q + 6] + bb.z + r3.x, v[8 * q + 7] + bb.w + r3.y);
+                            *(reinterpret_cast<int4*>(orow + c0) + q) = o;
+                        }
+                    }
+                }
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ru_arrive(&raw_empty[s]);
+            }
+            if (a.nbuf == 1 && tile + gridDim.x < total_tiles) act_pass(it + 1);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kCols);
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn ru_encode_fn() {
+    static EncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(p);
+    });
+    return fn;
+}
+
+size_t resunit_smem(int C, int taps, int dil, int nbuf = 2) {
+    const int kRow = C * 2, rows = 128 + (taps - 1) * dil;
+    const size_t slab = ((size_t)rows * kRow + 1023) & ~size_t(1023);
+    const size_t mid = ((size_t)(128 + taps - 1) * kRow + 1023) & ~size_t(1023);
+    return (size_t)2 * taps * C * kRow + (nbuf + 1) * slab + mid + 256 + 1024;
+}
+
+template <int C>
+int launch_resunit(const CUtensorMap& mx, const CUtensorMap& m1, const CUtensorMap& m2, ResUnitArgs a, cudaStream_t s) {
+    static std::mutex mu;
+    static size_t high = 0;
+    static int sms = 0;
+    const size_t smem2 = resunit_smem(C, a.taps, a.dil, 2), smem1 = resunit_smem(C, a.taps, a.dil, 1);
+    if (smem2 > 227 * 1024) return ADV_ERR_UNSUPPORTED;
+    int occ2 = 1, occ1 = 1;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem2 > high) {
+            ADV_CUDA_CHECK(cudaFuncSetAttribute(resunit_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            high = smem2;
+        }
+        if (sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        }
+        occ2 = adv_resident_ctas(resunit_kernel<C>, kRuThreads, smem2, 2 * C, 4);
+        occ1 = adv_resident_ctas(resunit_kernel<C>, kRuThreads, smem1, 2 * C, 4);
+    }
+    // a second (third ...) co-resident CTA is worth more than the second raw-slab buffer
+    a.nbuf = occ1 > occ2 ? 1 : 2;
+    int per_sm = a.nbuf == 1 ? occ1 : occ2;
+    const size_t smem = a.nbuf == 1 ? smem1 : smem2;
+    const long tiles = (long)a.B * a.tiles_l;
+    long grid = (long)sms * per_sm;
+    if (grid > tiles) grid = tiles;
+    resunit_kernel<C><<<(unsigned)grid, kRuThreads, smem, s>>>(mx, m1, m2, a);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+}  // namespace
+}  // namespace adv
+
+using namespace adv;
+
+extern "C" int adv_resunit_bf16(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, void* out,
+                                int batch, int L, int C, int taps, int dil, float slope, void* stream) {
+    if (!x || !w1 || !w2 || !b1 || !b2 || !out || batch <= 0 || L <= 0 || taps <= 0 || dil <= 0) return ADV_ERR_INVALID;
+    if ((taps & 1) == 0 || !(C == 32 || C == 64)) return ADV_ERR_SHAPE;
+    const int h2 = (taps - 1) / 2, halo1 = h2 * dil, rows = 128 + 2 * halo1;
+    if (rows > 256 || taps > 64 || resunit_smem(C, taps, dil) > 227 * 1024) return ADV_ERR_UNSUPPORTED;
+    EncodeFn enc = ru_encode_fn();
+    if (!enc) return ADV_ERR_UNSUPPORTED;
+    const CUtensorMapSwizzle swz = C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUtensorMap mx, m1, m2;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)batch};
+        cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)L * C * 2};
+        cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)rows, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return ADV_ERR_INVALID;
+    }
+    for (int i = 0; i < 2; ++i) {
+        cuuint64_t wd[2] = {(cuuint64_t)taps * C, (cuuint64_t)C};
+        cuuint64_t wst[1] = {(cuuint64_t)taps * C * 2};
+        cuuint32_t wb[2] = {(cuuint32_t)C, (cuuint32_t)C};
+        cuuint32_t we[2] = {1, 1};
+        if (enc(i ? &m2 : &m1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(i ? w2 : w1), wd, wst, wb, we,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return ADV_ERR_INVALID;
+    }
+    ResUnitArgs a;
+    a.b1 = b1; a.b2 = b2; a.out = (__nv_bfloat16*)out;
+    a.B = batch; a.L = L; a.taps = taps; a.dil = dil;
+    a.h2 = h2; a.halo1 = halo1; a.rows = rows;
+    a.TO = 128 - (taps - 1);
+    a.tiles_l = (L + a.TO - 1) / a.TO;
+    a.slope = slope;
+    a.nbuf = 2;
+    return C == 64 ? launch_resunit<64>(mx, m1, m2, a, (cudaStream_t)stream)
+                   : launch_resunit<32>(mx, m1, m2, a, (cudaStream_t)stream);
+}

@@ -114,8 +114,9 @@ class HifiganGenerator:
     applied by the producing layer's epilogue.  ``pipeline="gather"``: first-generation kernel (operands gathered
     with ordinary loads, activation on load) - required for reflect padding."""
 
-    def __init__(self, weights=None, cfg=HifiganConfig, device=None, seed=0, pipeline=None):
+    def __init__(self, weights=None, cfg=HifiganConfig, device=None, seed=0, pipeline=None, fuse=True):
         self.cfg = cfg
+        self.fuse = fuse  # fused residual units on the narrow stages (False: every conv is its own launch)
         self.dev = device or ops._dev()
         self.pipeline = pipeline or ("gather" if cfg.pad_reflect else "tma")
         if self.pipeline == "tma" and cfg.pad_reflect:
@@ -187,19 +188,43 @@ class HifiganGenerator:
             o = self._avg3(outs)
         return o, L
 
+    # fused residual unit (conv1 -> LeakyReLU -> conv2 -> + x in one kernel): narrow stages whose two weight sets
+    # fit in shared memory next to the slabs
+    @staticmethod
+    def _fusable(c1, c2):
+        if c1.cin != c1.cout or c1.cin not in (32, 64) or c2.dil != 1 or c1.taps != c2.taps:
+            return False
+        row, rows = c1.cin * 2, 128 + (c1.taps - 1) * c1.dil
+        r1k = lambda v: (v + 1023) // 1024 * 1024
+        smem = 2 * c1.taps * c1.cin * row + 3 * r1k(rows * row) + r1k((128 + c1.taps - 1) * row) + 1280
+        return rows <= 256 and smem <= 227 * 1024
+
+    def _resunit(self, x_raw, c1, c2, B, L):
+        out = self._buf(B, L, c1.cout)
+        check(lib().adv_resunit_bf16(ptr(x_raw), ptr(c1.w_tma), ptr(c1.bias), ptr(c2.w_tma), ptr(c2.bias), ptr(out), B, L,
+                                     c1.cin, c1.taps, c1.dil, LRELU_SLOPE, stream_ptr()), "adv_resunit_bf16")
+        self.launches += 1
+        return out
+
     def _stages_tma(self, o, B, L):
-        """``o`` = conv_pre output, already LeakyReLU'd.  Every tensor a conv consumes was written activated by
-        its producer; raw copies exist only where a residual or the MRF average needs them."""
+        """``o`` = conv_pre output, already LeakyReLU'd.  Every tensor an (unfused) conv consumes was written
+        activated by its producer; raw copies exist only where a residual, a fused unit or the MRF average needs
+        them."""
         n_stage = len(self.ups)
         o_act = o
         for si, ((up, s), stage) in enumerate(zip(self.ups, self.blocks)):
-            x_raw, x_act = self._conv_tma(o_act, up, B, L, act_slope=LRELU_SLOPE)
+            fused = [self.fuse and all(self._fusable(c1, c2) for c1, c2 in branch) for branch in stage]
+            x_raw, x_act = self._conv_tma(o_act, up, B, L, act_slope=None if all(fused) else LRELU_SLOPE)
             L, ch = L * s, up.cout // s
-            x_raw, x_act = x_raw.view(B, L, ch), x_act.view(B, L, ch)
+            x_raw = x_raw.view(B, L, ch)
+            x_act = None if x_act is None else x_act.view(B, L, ch)
             outs = []
-            for branch in stage:
+            for branch, fz in zip(stage, fused):
                 xb_raw, xb_act = x_raw, x_act
                 for d, (c1, c2) in enumerate(branch):
+                    if fz:
+                        xb_raw = self._resunit(xb_raw, c1, c2, B, L)
+                        continue
                     _, xt_act = self._conv_tma(xb_act, c1, B, L, want_raw=False, act_slope=LRELU_SLOPE)
                     last = d == len(branch) - 1
                     xb_raw, xb_act = self._conv_tma(xt_act, c2, B, L, resid=xb_raw,
