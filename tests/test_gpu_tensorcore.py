@@ -214,13 +214,14 @@ def test_mel_against_reference_golden(pkg):
     assert np.abs(got - g["mel"]).max() / np.abs(g["mel"]).max() < 1e-4
 
 
-@pytest.mark.parametrize("reflect,pipeline", [(False, "tma"), (False, "gather"), (True, "gather")])
-def test_hifigan_generator_matches_oracle(pkg, H, reflect, pipeline):
+@pytest.mark.parametrize("reflect,pipeline,fuse", [(False, "tma", "always"), (False, "tma", "auto"), (False, "tma", "never"),
+                                                   (False, "gather", "never"), (True, "gather", "never")])
+def test_hifigan_generator_matches_oracle(pkg, H, reflect, pipeline, fuse):
     """Whole generator (61 conv launches), seeded weights.  std 0.03 gives per-layer gains near 1 (the original
     N(0, 0.01^2) init lets biases dominate); larger scales saturate tanh and make the comparison chaotic."""
     cfg = type("Cfg", (H.HifiganConfig,), {"pad_reflect": reflect})
     W = H.init_weights(cfg, seed=1, std=0.03)
-    gen = H.HifiganGenerator(W, cfg, pipeline=pipeline)
+    gen = H.HifiganGenerator(W, cfg, pipeline=pipeline, fuse=fuse)
     g = torch.Generator().manual_seed(2)
     mel = -4 + 2 * torch.randn(2, 80, 9, generator=g)
     wav = gen.decode_batch(mel)
@@ -232,7 +233,9 @@ def test_hifigan_generator_matches_oracle(pkg, H, reflect, pipeline):
     # vs the oracle with bf16 storage of activations modelled: tighter
     refq = V.generator(mel, Wq, reflect=reflect, quantize=bf16r)
     assert rel_l2(wav, refq) < 1e-2, rel_l2(wav, refq)
-    if pipeline == "tma":   # 64- and 32-channel stages: fused residual units (k 11 at 64 channels stays unfused)
+    if fuse == "always":   # 64- and 32-channel stages: fused residual units (k 11 at 64 channels stays unfused)
         assert gen.launches == 1 + 2 * (1 + 18) + (1 + 3 + 3 + 6) + (1 + 9)
+    elif fuse == "auto":   # fused only where four CTAs share an SM: the 3-tap branch of the 32-channel stage
+        assert gen.launches == 1 + 3 * (1 + 18) + (1 + 3 + 6 + 6)
     else:
         assert gen.launches == 1 + 4 * (1 + 18)   # conv_pre + 4 x (upsample + 3 resblocks x 3 x 2 convs)

@@ -79,7 +79,9 @@ normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const 
         }
     }
     __syncthreads();
-    const float mean = s_mean, den = s_den;
+    // one reciprocal per row instead of a division per sample (<= 1.5 ulp from the reference's quotient; the
+    // IEEE division was a third of this kernel's instructions)
+    const float mean = s_mean, inv = 1.0f / s_den;
     const float* row = in + (size_t)b * n;
     float* orow = out + (size_t)b * n;
     const int lo = blockIdx.x * kRowChunk, hi = min(n, lo + kRowChunk);
@@ -97,15 +99,15 @@ normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const 
             for (int u = 0; u < U; ++u)
                 if (i + u * kPwThreads < hi / 4) {
                     float4 y;
-                    y.x = (v[u].x - mean) / den;
-                    y.y = (v[u].y - mean) / den;
-                    y.z = (v[u].z - mean) / den;
-                    y.w = (v[u].w - mean) / den;
+                    y.x = (v[u].x - mean) * inv;
+                    y.y = (v[u].y - mean) * inv;
+                    y.z = (v[u].z - mean) * inv;
+                    y.w = (v[u].w - mean) * inv;
                     o4[i + u * kPwThreads] = y;
                 }
         }
     } else {
-        for (int i = lo + threadIdx.x; i < hi; i += kPwThreads) orow[i] = (__ldg(row + i) - mean) / den;
+        for (int i = lo + threadIdx.x; i < hi; i += kPwThreads) orow[i] = (__ldg(row + i) - mean) * inv;
     }
 }
 

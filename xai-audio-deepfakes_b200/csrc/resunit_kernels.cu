@@ -335,8 +335,11 @@ int launch_resunit(const CUtensorMap& mx, const CUtensorMap& m1, const CUtensorM
         occ2 = adv_resident_ctas(resunit_kernel<C>, kRuThreads, smem2, 2 * C, 4);
         occ1 = adv_resident_ctas(resunit_kernel<C>, kRuThreads, smem1, 2 * C, 4);
     }
-    // a second (third ...) co-resident CTA is worth more than the second raw-slab buffer
-    a.nbuf = occ1 > occ2 ? 1 : 2;
+    // measured (64 channels, 3 taps): two CTAs with ONE raw-slab buffer each (the slab load then sits inside the
+    // per-tile chain) are slower than one CTA with two buffers (455 vs 374 us), so the single-buffer layout is
+    // only a fallback when two buffers do not fit at all
+    (void)occ1;
+    a.nbuf = 2;
     int per_sm = a.nbuf == 1 ? occ1 : occ2;
     const size_t smem = a.nbuf == 1 ? smem1 : smem2;
     const long tiles = (long)a.B * a.tiles_l;

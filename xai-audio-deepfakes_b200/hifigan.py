@@ -114,9 +114,11 @@ class HifiganGenerator:
     applied by the producing layer's epilogue.  ``pipeline="gather"``: first-generation kernel (operands gathered
     with ordinary loads, activation on load) - required for reflect padding."""
 
-    def __init__(self, weights=None, cfg=HifiganConfig, device=None, seed=0, pipeline=None, fuse=True):
+    def __init__(self, weights=None, cfg=HifiganConfig, device=None, seed=0, pipeline=None, fuse="auto"):
         self.cfg = cfg
-        self.fuse = fuse  # fused residual units on the narrow stages (False: every conv is its own launch)
+        # fused residual units on the narrow stages: "auto" = where measured faster, "always" = wherever the
+        # kernel supports the shape, "never" = every conv is its own launch
+        self.fuse = {True: "auto", False: "never"}.get(fuse, fuse)
         self.dev = device or ops._dev()
         self.pipeline = pipeline or ("gather" if cfg.pad_reflect else "tma")
         if self.pipeline == "tma" and cfg.pad_reflect:
@@ -199,6 +201,18 @@ class HifiganGenerator:
         smem = 2 * c1.taps * c1.cin * row + 3 * r1k(rows * row) + r1k((128 + c1.taps - 1) * row) + 1280
         return rows <= 256 and smem <= 227 * 1024
 
+    @staticmethod
+    def _fused_wins(c1):
+        """Measured on B200 (64 x 4 s clips): the fused unit's per-tile chain of hand-offs (TMA -> LeakyReLU pass ->
+        conv1 -> epilogue -> conv2 -> epilogue) takes ~4.5 us per tile per CTA whatever the tap count, so it beats
+        two separate conv launches only where 4 CTAs share an SM (32 channels, 3 taps: 237 vs 334 us per unit); with
+        3 or fewer resident CTAs the two-launch path is faster (7 taps: 385 vs 338 us; 64 channels: 374-487 vs
+        330-460 us)."""
+        row, rows = c1.cin * 2, 128 + (c1.taps - 1) * c1.dil
+        r1k = lambda v: (v + 1023) // 1024 * 1024
+        smem = 2 * c1.taps * c1.cin * row + 3 * r1k(rows * row) + r1k((128 + c1.taps - 1) * row) + 1280
+        return 4 * (smem + 1024) <= 228 * 1024
+
     def _resunit(self, x_raw, c1, c2, B, L):
         out = self._buf(B, L, c1.cout)
         check(lib().adv_resunit_bf16(ptr(x_raw), ptr(c1.w_tma), ptr(c1.bias), ptr(c2.w_tma), ptr(c2.bias), ptr(out), B, L,
@@ -213,7 +227,8 @@ class HifiganGenerator:
         n_stage = len(self.ups)
         o_act = o
         for si, ((up, s), stage) in enumerate(zip(self.ups, self.blocks)):
-            fused = [self.fuse and all(self._fusable(c1, c2) for c1, c2 in branch) for branch in stage]
+            fused = [self.fuse != "never" and all(self._fusable(c1, c2) and (self.fuse == "always" or self._fused_wins(c1))
+                                                  for c1, c2 in branch) for branch in stage]
             x_raw, x_act = self._conv_tma(o_act, up, B, L, act_slope=None if all(fused) else LRELU_SLOPE)
             L, ch = L * s, up.cout // s
             x_raw = x_raw.view(B, L, ch)
