@@ -174,6 +174,14 @@ int adv_avg3_bf16(const void* a, const void* b, const void* c, int64_t n, float 
 int adv_post_conv_tanh(const void* in, const float* w, const float* bias, int batch, int L, int C, int taps, float slope,
                        int pad_reflect, float* out, void* stream);
 
+/* Cross-correlation alignment shift of align_waveforms (hifigan.py:113-136):
+ *   cc[j] = sum_i ref[j + i - n_deg] * deg[i], j = 0 .. n_ref + n_deg;  *shift = argmax_j cc[j] - n_deg (first maximum).
+ * Direct fp32 accumulation like the reference's conv1d.  ws_val / ws_idx: dev scratch of adv_xcorr_blocks(n_ref, n_deg)
+ * floats / ints; shift: dev int.  Asynchronous on `stream`. */
+int adv_xcorr_blocks(int n_ref, int n_deg);
+int adv_xcorr_shift(const float* ref, int n_ref, const float* deg, int n_deg, float* ws_val, int* ws_idx, int* shift,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -335,3 +335,34 @@ def test_long_form_clip(ops):
     attr = torch.randn(2, n, generator=g, device="cuda")
     m, rel, irr = ops.td_mask(wav, attr)
     assert relerr(rel + irr, wav) < 1e-6 and float(m.max()) <= 1.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# align_waveforms (hifigan.py:113-136): cross-correlation arg-max on the GPU vs the reference's conv1d
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_ref,n_deg,delay", [(4000, 4000, 37), (5000, 4321, -113), (3000, 3500, 0), (1500, 700, 400),
+                                               (9000, 9100, -1030)])
+def test_align_shift_matches_reference_conv(pkg, n_ref, n_deg, delay):
+    g = torch.Generator().manual_seed(n_ref + n_deg)
+    base = torch.randn(n_ref + n_deg + 4096, generator=g)
+    ref = base[2048:2048 + n_ref].clone()
+    deg = (0.8 * base[2048 + delay:2048 + delay + n_deg] + 0.05 * torch.randn(n_deg, generator=g)).clone()
+    want = R.align_shift(ref, deg)
+    got = int(pkg.hifigan.align_shift(ref, deg).item())
+    assert got == want == delay
+    ra, da = pkg.hifigan.align_waveforms(ref.cuda(), deg.cuda())
+    assert ra.shape == da.shape and ra.shape[:2] == (1, 1)
+    if delay > 0:
+        assert torch.equal(ra[0, 0].cpu(), ref[delay:delay + ra.shape[-1]])
+    else:
+        assert torch.equal(da[0, 0].cpu(), deg[-delay:-delay + da.shape[-1]])
+
+
+def test_align_shift_full_clip(pkg):
+    """4 s clip vs its 66 816-sample vocoded counterpart (BASELINE configs[2] geometry): property check, the
+    direct CPU correlation would take minutes."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    base = torch.randn(140000, generator=g, device="cuda")
+    ref = base[2000:66000]
+    deg = 0.7 * base[2000 - 1330:2000 - 1330 + 66816] + 0.1 * torch.randn(66816, generator=g, device="cuda")
+    assert int(pkg.hifigan.align_shift(ref, deg).item()) == -1330

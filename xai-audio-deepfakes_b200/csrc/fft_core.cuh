@@ -74,6 +74,18 @@ ADV_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y
 ADV_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 ADV_HD float2 cfma(float2 a, float2 s, float2 c) { return make_float2(fmaf(a.x, s.x, c.x), fmaf(a.y, s.y, c.y)); }
 #endif
+// PK = false: plain scalar forms.  The register-starved narrow-unit inverse (istft_p_kernel holds the next tile's
+// rows in flight) measured SLOWER with the packed forms (41.8 vs 39.3 us: pair alignment costs moves), every other
+// kernel faster (explain 98.5 -> 94.5 us).
+template <bool PK> ADV_HD float2 cadd_t(float2 a, float2 b) {
+    if constexpr (PK) return cadd(a, b); else return make_float2(a.x + b.x, a.y + b.y);
+}
+template <bool PK> ADV_HD float2 csub_t(float2 a, float2 b) {
+    if constexpr (PK) return csub(a, b); else return make_float2(a.x - b.x, a.y - b.y);
+}
+template <bool PK> ADV_HD float2 cfma_t(float2 a, float2 s, float2 c) {
+    if constexpr (PK) return cfma(a, s, c); else return make_float2(fmaf(a.x, s.x, c.x), fmaf(a.y, s.y, c.y));
+}
 ADV_HD float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -109,12 +121,12 @@ ADV_HD float2 twmul(float2 a) {
 
 // radix-2 butterfly with the twiddle folded into FMAs:  lo = e + W*o,  hi = e - W*o = 2e - lo
 // (6 FMA-pipe instructions for a general twiddle instead of 8; trivial twiddles stay pure adds)
-template <int N, int K, int DIR>
+template <int N, int K, int DIR, bool PK = true>
 ADV_HD void butterfly(float2 e, float2 o, float2& lo, float2& hi) {
     if constexpr (K == 0 || 4 * K == N) {
         const float2 t = twmul<N, K, DIR>(o);
-        lo = cadd(e, t);
-        hi = csub(e, t);
+        lo = cadd_t<PK>(e, t);
+        hi = csub_t<PK>(e, t);
     } else if constexpr (8 * K == N || 8 * K == 3 * N) {
         constexpr float h = 0.70710678118654752f;
         // W*o = h * (p, q) with p, q sums / differences of o's parts
@@ -127,57 +139,57 @@ ADV_HD void butterfly(float2 e, float2 o, float2& lo, float2& hi) {
             q = DIR < 0 ? -(o.x + o.y) : o.x - o.y;
         }
         const float2 pq = make_float2(p, q);
-        lo = cfma(pq, make_float2(h, h), e);
-        hi = cfma(pq, make_float2(-h, -h), e);
+        lo = cfma_t<PK>(pq, make_float2(h, h), e);
+        hi = cfma_t<PK>(pq, make_float2(-h, -h), e);
     } else {
         constexpr int idx = K * (32 / N);
         constexpr float c = kCos32[idx];
         constexpr float s = (DIR < 0 ? -1.0f : 1.0f) * kSin32[idx];
         lo = make_float2(fmaf(o.x, c, fmaf(-o.y, s, e.x)), fmaf(o.x, s, fmaf(o.y, c, e.y)));
-        hi = cfma(e, make_float2(2.0f, 2.0f), make_float2(-lo.x, -lo.y));
+        hi = cfma_t<PK>(e, make_float2(2.0f, 2.0f), make_float2(-lo.x, -lo.y));
     }
 }
 
 // N-point DFT of in[0], in[S], in[2S], ... -> out[0..N-1] (natural order), all in registers.
-template <int N, int DIR>
+template <int N, int DIR, bool PK = true>
 struct FFTReg {
     template <int S>
     static ADV_HD void run(const float2* in, float2* out) {
         float2 e[N / 2], o[N / 2];
-        FFTReg<N / 2, DIR>::template run<2 * S>(in, e);
-        FFTReg<N / 2, DIR>::template run<2 * S>(in + S, o);
+        FFTReg<N / 2, DIR, PK>::template run<2 * S>(in, e);
+        FFTReg<N / 2, DIR, PK>::template run<2 * S>(in + S, o);
         static_for<0, N / 2>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            butterfly<N, k, DIR>(e[k], o[k], out[k], out[k + N / 2]);
+            butterfly<N, k, DIR, PK>(e[k], o[k], out[k], out[k + N / 2]);
         });
     }
 };
-template <int DIR>
-struct FFTReg<4, DIR> {
+template <int DIR, bool PK>
+struct FFTReg<4, DIR, PK> {
     template <int S>
     static ADV_HD void run(const float2* in, float2* out) {
-        const float2 a = cadd(in[0], in[2 * S]), b = csub(in[0], in[2 * S]);
-        const float2 c = cadd(in[S], in[3 * S]);
-        const float2 d = twmul<4, 1, DIR>(csub(in[S], in[3 * S]));
-        out[0] = cadd(a, c);
-        out[2] = csub(a, c);
-        out[1] = cadd(b, d);
-        out[3] = csub(b, d);
+        const float2 a = cadd_t<PK>(in[0], in[2 * S]), b = csub_t<PK>(in[0], in[2 * S]);
+        const float2 c = cadd_t<PK>(in[S], in[3 * S]);
+        const float2 d = twmul<4, 1, DIR>(csub_t<PK>(in[S], in[3 * S]));
+        out[0] = cadd_t<PK>(a, c);
+        out[2] = csub_t<PK>(a, c);
+        out[1] = cadd_t<PK>(b, d);
+        out[3] = csub_t<PK>(b, d);
     }
 };
-template <int DIR>
-struct FFTReg<2, DIR> {
+template <int DIR, bool PK>
+struct FFTReg<2, DIR, PK> {
     template <int S>
     static ADV_HD void run(const float2* in, float2* out) {
-        out[0] = cadd(in[0], in[S]);
-        out[1] = csub(in[0], in[S]);
+        out[0] = cadd_t<PK>(in[0], in[S]);
+        out[1] = csub_t<PK>(in[0], in[S]);
     }
 };
 
-template <int N, int DIR>
+template <int N, int DIR, bool PK = true>
 ADV_HD void fft_inplace(float2* v) {
     float2 t[N];
-    FFTReg<N, DIR>::template run<1>(v, t);
+    FFTReg<N, DIR, PK>::template run<1>(v, t);
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = t[i];
 }
@@ -336,13 +348,13 @@ template <int NF>
 ADV_HD void inv_rows(float2* v) {
     using G = Geo<NF>;
 #pragma unroll
-    for (int r = 0; r < G::ROWS; ++r) fft_inplace<G::R2, +1>(v + r * G::R2);
+    for (int r = 0; r < G::ROWS; ++r) fft_inplace<G::R2, +1, false>(v + r * G::R2);
 }
 template <int NF, class TwFn>
 ADV_HD void inv_cols(float2* v, TwFn tw) {
 #pragma unroll
     for (int k1 = 1; k1 < 32; ++k1) v[k1] = cmulc(v[k1], tw(k1));
-    fft_inplace<32, +1>(v);
+    fft_inplace<32, +1, false>(v);
 }
 
 #ifdef __CUDACC__

@@ -304,6 +304,100 @@ band_swap_kernel(const float2* __restrict__ real, const float2* __restrict__ voc
     }
 }
 
+// ---- cross-correlation arg-max (align_waveforms, hifigan.py:113-136) ------------------------------------
+// cc[j] = sum_i ref[j + i - P] * deg[i],  P = n_deg, j = 0 .. n_ref + P  (the reference pads ref with P zeros on both
+// sides and runs conv1d); the alignment shift is argmax_j cc[j] - P.  Direct form, fp32 accumulation like the
+// reference's conv1d: a CTA owns kXcLags consecutive lags, streams deg in chunks through shared memory and slides
+// an 8-lag register window over the matching ref samples (1 shared load + 8 FMA per tap); chunks that only meet
+// the zero padding are skipped.  Stage 2 folds the per-CTA maxima (lowest index wins ties).
+constexpr int kXcThreads = 128, kXcPerThread = 8, kXcLags = kXcThreads * kXcPerThread, kXcChunk = 512;
+__device__ __forceinline__ int xc_pad(int i) { return i + (i >> 5); }  // stride-8 accesses hit 32 different banks
+
+__global__ void __launch_bounds__(kXcThreads)
+xcorr_partial_kernel(const float* __restrict__ ref, int n_ref, const float* __restrict__ deg, int n_deg,
+                     float* __restrict__ best_val, int* __restrict__ best_idx) {
+    __shared__ float refs[kXcLags + kXcChunk + 8 + (kXcLags + kXcChunk + 8) / 32 + 1];
+    __shared__ float degs[kXcChunk];
+    __shared__ float rv[kXcThreads / 32];
+    __shared__ int ri[kXcThreads / 32];
+    const int P = n_deg, n_lags = n_ref + P + 1;
+    const int j0 = blockIdx.x * kXcLags, t = threadIdx.x;
+    float acc[kXcPerThread];
+#pragma unroll
+    for (int r = 0; r < kXcPerThread; ++r) acc[r] = 0.0f;
+    // taps i that can meet a non-zero ref sample for some lag of this CTA: 0 <= j + i - P < n_ref
+    const int i_lo = max(0, P - (j0 + kXcLags - 1)), i_hi = min(n_deg, n_ref + P - j0);
+    for (int i0 = (i_lo / kXcChunk) * kXcChunk; i0 < i_hi; i0 += kXcChunk) {
+        __syncthreads();
+        for (int k = t; k < kXcChunk; k += kXcThreads) degs[k] = (i0 + k < n_deg) ? __ldg(deg + i0 + k) : 0.0f;
+        const int base = j0 + i0 - P;  // ref index of window element 0
+        for (int k = t; k < kXcLags + kXcChunk; k += kXcThreads) {
+            const int idx = base + k;
+            refs[xc_pad(k)] = (idx >= 0 && idx < n_ref) ? __ldg(ref + idx) : 0.0f;
+        }
+        __syncthreads();
+        float w[kXcPerThread];
+#pragma unroll
+        for (int r = 0; r < kXcPerThread; ++r) w[r] = refs[xc_pad(t * kXcPerThread + r)];
+#pragma unroll 8
+        for (int i = 0; i < kXcChunk; ++i) {
+            const float d = degs[i];
+#pragma unroll
+            for (int r = 0; r < kXcPerThread; ++r) acc[r] = fmaf(w[r], d, acc[r]);
+#pragma unroll
+            for (int r = 0; r + 1 < kXcPerThread; ++r) w[r] = w[r + 1];
+            w[kXcPerThread - 1] = refs[xc_pad(t * kXcPerThread + kXcPerThread + i)];
+        }
+    }
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < kXcPerThread; ++r) {
+        const int j = j0 + t * kXcPerThread + r;
+        if (j < n_lags && (acc[r] > bv)) { bv = acc[r]; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((t & 31) == 0) { rv[t >> 5] = bv; ri[t >> 5] = bi; }
+    __syncthreads();
+    if (t == 0) {
+        for (int k = 1; k < kXcThreads / 32; ++k)
+            if (rv[k] > bv || (rv[k] == bv && ri[k] < bi)) { bv = rv[k]; bi = ri[k]; }
+        best_val[blockIdx.x] = bv;
+        best_idx[blockIdx.x] = bi;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+xcorr_final_kernel(const float* __restrict__ best_val, const int* __restrict__ best_idx, int n, int pad, int* __restrict__ shift) {
+    __shared__ float rv[8];
+    __shared__ int ri[8];
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int k = threadIdx.x; k < n; k += 256) {
+        const float v = best_val[k];
+        const int i = best_idx[k];
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { rv[threadIdx.x >> 5] = bv; ri[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k)
+            if (rv[k] > bv || (rv[k] == bv && ri[k] < bi)) { bv = rv[k]; bi = ri[k]; }
+        *shift = bi - pad;
+    }
+}
+
 }  // namespace adv
 
 using namespace adv;
@@ -411,3 +505,18 @@ int adv_band_swap(const adv_c64* real, const adv_c64* voc, int batch, int T, int
 }
 
 }  // extern "C"
+
+extern "C" int adv_xcorr_blocks(int n_ref, int n_deg) {
+    if (n_ref <= 0 || n_deg <= 0) return 0;
+    return (n_ref + n_deg + 1 + kXcLags - 1) / kXcLags;
+}
+
+extern "C" int adv_xcorr_shift(const float* ref, int n_ref, const float* deg, int n_deg, float* ws_val, int* ws_idx, int* shift,
+                    void* stream) {
+    if (!ref || !deg || !ws_val || !ws_idx || !shift || n_ref <= 0 || n_deg <= 0) return ADV_ERR_INVALID;
+    const int blocks = adv_xcorr_blocks(n_ref, n_deg);
+    xcorr_partial_kernel<<<blocks, kXcThreads, 0, (cudaStream_t)stream>>>(ref, n_ref, deg, n_deg, ws_val, ws_idx);
+    xcorr_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ws_val, ws_idx, blocks, n_deg, shift);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}

@@ -290,3 +290,36 @@ class HifiganGenerator:
             for ks, dils in zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes):
                 fl += 2 * len(dils) * 2 * L * ch * ch * ks
         return fl + 2 * L * ch * cfg.conv_post_kernel
+
+
+def align_shift(ref_wav, deg_wav):
+    """Arg-max lag of the cross-correlation the reference computes with a direct conv1d (hifigan.py:113-126):
+    device int32 tensor holding ``argmax(conv1d(pad(ref, (P, P)), deg)) - P`` with ``P = len(deg)``."""
+    dev = ops._dev()
+    ref = ref_wav.reshape(-1).to(dev, torch.float32).contiguous()
+    deg = deg_wav.reshape(-1).to(dev, torch.float32).contiguous()
+    nb = lib().adv_xcorr_blocks(ref.numel(), deg.numel())
+    ws_val = torch.empty(nb, dtype=torch.float32, device=dev)
+    ws_idx = torch.empty(nb, dtype=torch.int32, device=dev)
+    shift = torch.empty(1, dtype=torch.int32, device=dev)
+    check(lib().adv_xcorr_shift(ptr(ref), ref.numel(), ptr(deg), deg.numel(), ptr(ws_val), ptr(ws_idx), ptr(shift),
+                                stream_ptr()), "adv_xcorr_shift")
+    return shift
+
+
+def align_waveforms(ref_wav, deg_wav):
+    """Same contract as the reference's ``align_waveforms`` (hifigan.py:113-136): returns ``(ref_aligned,
+    deg_aligned)``, views of shape [1, 1, n] trimmed to the common length after shifting by the cross-correlation
+    arg-max.  The O(N^2) correlation runs on the GPU; only the shift (one int) is read back, as the reference does
+    with ``.item()``."""
+    ref_wav = ref_wav.view(1, 1, -1)
+    deg_wav = deg_wav.view(1, 1, -1)
+    shift = int(align_shift(ref_wav, deg_wav).item())
+    if shift > 0:
+        ref_aligned = ref_wav[..., shift:]
+        deg_aligned = deg_wav[..., : ref_aligned.shape[-1]]
+    else:
+        deg_aligned = deg_wav[..., -shift:]
+        ref_aligned = ref_wav[..., : deg_aligned.shape[-1]]
+    n = min(ref_aligned.shape[-1], deg_aligned.shape[-1])
+    return ref_aligned[..., :n], deg_aligned[..., :n]
