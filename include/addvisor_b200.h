@@ -68,6 +68,22 @@ int adv_plan_tiles(const adv_plan* plan, int batch);
 int adv_stft(const adv_plan* plan, const float* wav, int64_t wav_stride, int batch,
              adv_c64* X, float* mag, float* phase, void* stream);
 
+/* Same transform with options.  ADV_STFT_ZERO_PAD: frames that reach past the clip edges read zeros instead of
+ * torch.stft's reflect padding - with the synthesis window and the input pre-multiplied by the reciprocal
+ * overlap-add envelope this is the adjoint of adv_istft, i.e. the backward pass of compute_invert_stft in the
+ * training loss (loss_function.py:46-47 under autograd, train_addvisor.py:364-366). */
+enum { ADV_STFT_ZERO_PAD = 1 };
+int adv_stft_ex(const adv_plan* plan, const float* wav, int64_t wav_stride, int batch,
+                adv_c64* X, float* mag, float* phase, int flags, void* stream);
+/* copies the plan's reciprocal overlap-add envelope 1 / (n_fft * sum_t w^2) over [0, n_out) to dev float out[n_out] */
+int adv_plan_inv_env(const adv_plan* plan, float* out, void* stream);
+/* Gradient of the linear mask path (loss_function.py:36-47) with respect to the mask:
+ *   gm[b][f][t] = c_f * Re(conj(X[b][t][f]) * A[b][t][f]),  f < Fm, t < Tm,   c_f = 1 for DC / Nyquist, 2 otherwise,
+ * A = adv_stft_ex(ZERO_PAD) of (grad_rel - grad_irr) * inv_env.  X: element strides (sb, st, sf); A frame-major
+ * [B][T][F]; gm dev float [B][Fm][Tm] (the mask network's layout). */
+int adv_mask_grad_linear(const adv_c64* X, int64_t sb, int64_t st, int64_t sf, const adv_c64* A, int batch, int F, int T,
+                         int Fm, int Tm, float* gm, void* stream);
+
 /* ---- AudioProcessor.compute_invert_stft (audioprocessor.py:117-131): torch.istft ----------------------
  * X: dev complex64, element (b,t,f) at X[b*sb + t*st + f*sf] (element strides); out: dev float [B][n_out].
  * stats (nullable): dev double [B][tiles][2] per-tile (sum, sum of squares) of the output, for the

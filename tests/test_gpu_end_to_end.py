@@ -127,3 +127,102 @@ def test_saliency_path(pkg, built_lib):
     assert abs(float(ig.sum()) - float(f(w))) < 1e-4 * abs(float(f(w))) + 1e-5
     ig_model = pkg.captum_saliency.integrated_gradients(model, w, n_steps=8)
     assert abs(float(ig_model.sum())) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------
+# training loss (loss_function.py:32-77): forward and backward of the linear mask path
+# ---------------------------------------------------------------------------------------------------
+def _torch_linear_path(mask, spec, n_fft, hop, win, window, n):
+    """loss_function.py:36-47 in plain torch on the CPU (mask zero-extended to the full grid)."""
+    B, Fb, T = spec.shape
+    m = torch.nn.functional.pad(mask, (0, T - mask.shape[2], 0, Fb - mask.shape[1]))
+    w = torch.ones(win) if window is None else window
+    ist = lambda s: torch.istft(s, n_fft, hop_length=hop, win_length=win, window=w, length=n)
+    return ist(m * spec), ist((1 - m) * spec)
+
+
+@pytest.mark.parametrize("n_fft,hop,win,hann,n,Fm,Tm", [
+    (512, 160, 512, False, 4800, 257, 31),     # benchmark geometry (rectangular window), full-size mask
+    (512, 128, 400, True, 4096, 250, 30),      # hann window shorter than n_fft, mask smaller than the grid
+    (1024, 322, 644, True, 9660, 512, 30),     # reference default geometry, U-Net-sized mask (512 x T-1)
+])
+def test_explain_linear_backward_matches_torch_autograd(pkg, built_lib, n_fft, hop, win, hann, n, Fm, Tm):
+    ops = pkg.ops
+    g = torch.Generator().manual_seed(n_fft + hop + Fm)
+    B = 3
+    wav = 0.1 * torch.randn(B, n, generator=g)
+    window = torch.hann_window(win) if hann else None
+    spec = torch.stft(wav, n_fft, hop_length=hop, win_length=win, window=torch.ones(win) if window is None else window,
+                      return_complex=True)
+    T = spec.shape[2]
+    assert Tm <= T
+    mask0 = torch.rand(B, Fm, Tm, generator=g)
+    a, b = torch.randn(B, n, generator=g), torch.randn(B, n, generator=g)
+
+    m_ref = mask0.clone().requires_grad_(True)
+    rel_r, irr_r = _torch_linear_path(m_ref, spec, n_fft, hop, win, window, n)
+    (rel_r * a).sum().add((irr_r * b).sum()).backward()
+
+    m_gpu = mask0.clone().cuda().requires_grad_(True)
+    rel, irr = ops.explain_linear(spec.cuda(), m_gpu, n_fft, hop, win, length=n, window=window)
+    assert float((rel.cpu() - rel_r.detach()).abs().max() / rel_r.abs().max()) < 1e-4
+    assert float((irr.cpu() - irr_r.detach()).abs().max() / irr_r.abs().max()) < 1e-4
+    ((rel * a.cuda()).sum() + (irr * b.cuda()).sum()).backward()
+    err = float((m_gpu.grad.cpu() - m_ref.grad).abs().max() / m_ref.grad.abs().max())
+    assert err < 1e-4, err
+
+
+def test_lmac_loss_forward_backward(pkg, built_lib):
+    """LMACLoss.loss_function on the GPU path vs the reference's expressions in plain torch on the CPU, same seeded
+    SSL model and logistic head: total loss, the three components and the gradient reaching the mask."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    import torch.nn.functional as F
+    sr, n_fft, hop, win = 16000, 512, 160, 512
+    cfg = dict(sampling_rate=sr, n_fft=n_fft, hop_length=hop, win_length=win, audio_length=1)
+    g = torch.Generator().manual_seed(11)
+    B = 2
+    wav = 0.1 * torch.randn(B, sr, generator=g)
+    ssl_cpu = tiny_wav2vec2(1)
+    clf = pkg.classifier_embedder.SimpleLogReg(0.8 * torch.randn(1, 192, generator=g).numpy(), [0.05])
+    class_pred = torch.tensor([[1.0], [0.0]])
+    _, mag, phase = R.compute_stft(wav, **cfg)
+    spec = torch.polar(mag, phase)
+    mask0 = torch.rand(B, 1, 256, mag.shape[2] - 1, generator=g)
+
+    # ---- reference expressions on the CPU (loss_function.py:32-62) ----
+    coef = torch.tensor(clf.coef_, dtype=torch.float32)
+    icpt = torch.tensor(clf.intercept_, dtype=torch.float32)
+    m_ref = mask0.clone().requires_grad_(True)
+    rel_r, irr_r = _torch_linear_path(m_ref.squeeze(1), spec, n_fft, hop, win, None, sr)
+
+    def logits_cpu(w):
+        x = (w - w.mean(dim=-1, keepdim=True)) / (w.std(dim=-1, keepdim=True) + 1e-7)
+        feats = ssl_cpu(x, output_hidden_states=True).hidden_states[9].mean(dim=1)
+        return feats @ coef.t() + icpt
+
+    l_in = F.binary_cross_entropy_with_logits(logits_cpu(rel_r), class_pred)
+    l_out = F.binary_cross_entropy_with_logits(logits_cpu(irr_r), 1 - class_pred)
+    l1 = m_ref.abs().mean()
+    w_ref = F.softplus(torch.tensor([3.0, 0.5, 3.0]))
+    total_ref = (w_ref * torch.stack([l_in, l_out, l1])).sum()
+    total_ref.backward()
+
+    # ---- product path ----
+    ce = pkg.classifier_embedder
+    ce.configure(wav2vec2=copy.deepcopy(ssl_cpu).cuda(), classifier=clf)
+    ap = pkg.audioprocessor.AudioProcessor(**cfg)
+    loss_mod = importlib_loss(pkg).LMACLoss(audio_processor=ap, torch_logreg=ce.TorchLogReg(clf)).cuda()
+    m_gpu = mask0.clone().cuda().requires_grad_(True)
+    total, losses, w = loss_mod.loss_function(m_gpu, mag.cuda(), phase.cuda(), class_pred.cuda())
+    total.backward()
+    assert abs(float(total) - float(total_ref)) < 2e-3 * max(1.0, abs(float(total_ref)))
+    assert float((losses.cpu() - torch.stack([l_in, l_out, l1]).detach()).abs().max()) < 2e-3
+    gref = m_ref.grad
+    err = float((m_gpu.grad.cpu() - gref).abs().max() / gref.abs().max())
+    assert err < 5e-3, err
+
+
+def importlib_loss(pkg):
+    import importlib
+    return importlib.import_module(pkg.__name__ + ".loss_function")

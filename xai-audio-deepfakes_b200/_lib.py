@@ -22,6 +22,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
 ADV_OK, ADV_ERR_INVALID, ADV_ERR_UNSUPPORTED, ADV_ERR_NOLA = 0, -1, -2, -3
 ADV_ERR_SHORT_INPUT, ADV_ERR_CUDA, ADV_ERR_SHAPE = -4, -5, -6
 MASK_LOG1P, MASK_LINEAR = 0, 1
+STFT_ZERO_PAD = 1
 
 
 def sources():
@@ -97,6 +98,11 @@ _SIGS.update({
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "adv_resunit_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "adv_stft_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                              C.c_void_p]),
+    "adv_plan_inv_env": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adv_mask_grad_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "adv_xcorr_blocks": (C.c_int, [C.c_int, C.c_int]),
     "adv_xcorr_shift": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "adv_mel_to_channels_last": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -180,7 +180,21 @@ int adv_plan_tiles(const adv_plan* plan, int batch) {
 int adv_stft(const adv_plan* plan, const float* wav, int64_t wav_stride, int batch, adv_c64* X, float* mag,
              float* phase, void* stream) {
     if (!plan || !wav || !X || batch <= 0 || plan->d.n_in <= 0 || wav_stride < plan->d.n_in) return ADV_ERR_INVALID;
-    return launch_stft(plan, wav, wav_stride, batch, (float2*)X, mag, phase, (cudaStream_t)stream);
+    return launch_stft(plan, wav, wav_stride, batch, (float2*)X, mag, phase, 0, (cudaStream_t)stream);
+}
+
+int adv_stft_ex(const adv_plan* plan, const float* wav, int64_t wav_stride, int batch, adv_c64* X, float* mag,
+                float* phase, int flags, void* stream) {
+    if (!plan || !wav || !X || batch <= 0 || plan->d.n_in <= 0 || wav_stride < plan->d.n_in) return ADV_ERR_INVALID;
+    if (flags & ~ADV_STFT_ZERO_PAD) return ADV_ERR_INVALID;
+    return launch_stft(plan, wav, wav_stride, batch, (float2*)X, mag, phase, flags, (cudaStream_t)stream);
+}
+
+int adv_plan_inv_env(const adv_plan* plan, float* out, void* stream) {
+    if (!plan || !out || plan->d.n_out <= 0) return ADV_ERR_INVALID;
+    ADV_CUDA_CHECK(cudaMemcpyAsync(out, plan->d.inv_env, sizeof(float) * (size_t)plan->d.n_out, cudaMemcpyDeviceToDevice,
+                                   (cudaStream_t)stream));
+    return ADV_OK;
 }
 
 int adv_istft(const adv_plan* plan, const adv_c64* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,

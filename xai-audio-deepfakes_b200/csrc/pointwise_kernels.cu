@@ -304,6 +304,35 @@ band_swap_kernel(const float2* __restrict__ real, const float2* __restrict__ voc
     }
 }
 
+// ---- gradient of the linear mask path w.r.t. the mask (backward of loss_function.py:36-47) -----------------
+// 32 x 32 tiles: frame-major reads (f fastest) of X and A, transposed through shared memory so that the
+// [B][Fm][Tm] gradient (t fastest) is written coalesced.
+__global__ void __launch_bounds__(256)
+mask_grad_linear_kernel(const float2* __restrict__ X, int64_t sb, int64_t st, int64_t sf, const float2* __restrict__ A,
+                        int F, int T, int Fm, int Tm, float* __restrict__ gm) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, f0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int t = t0 + ty + 8 * j, f = f0 + tx;
+        float g = 0.0f;
+        if (t < Tm && f < Fm) {
+            const float2 x = __ldg(X + (size_t)b * sb + (size_t)t * st + (size_t)f * sf);
+            const float2 a = __ldg(A + ((size_t)b * T + t) * F + f);
+            const float c = (f == 0 || f == F - 1) ? 1.0f : 2.0f;
+            g = c * fmaf(x.x, a.x, x.y * a.y);
+        }
+        tile[ty + 8 * j][tx] = g;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int f = f0 + ty + 8 * j, t = t0 + tx;
+        if (f < Fm && t < Tm) gm[((size_t)b * Fm + f) * Tm + t] = tile[tx][ty + 8 * j];
+    }
+}
+
 // ---- cross-correlation arg-max (align_waveforms, hifigan.py:113-136) ------------------------------------
 // cc[j] = sum_i ref[j + i - P] * deg[i],  P = n_deg, j = 0 .. n_ref + P  (the reference pads ref with P zeros on both
 // sides and runs conv1d); the alignment shift is argmax_j cc[j] - P.  Direct form, fp32 accumulation like the
@@ -517,6 +546,16 @@ extern "C" int adv_xcorr_shift(const float* ref, int n_ref, const float* deg, in
     const int blocks = adv_xcorr_blocks(n_ref, n_deg);
     xcorr_partial_kernel<<<blocks, kXcThreads, 0, (cudaStream_t)stream>>>(ref, n_ref, deg, n_deg, ws_val, ws_idx);
     xcorr_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ws_val, ws_idx, blocks, n_deg, shift);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+extern "C" int adv_mask_grad_linear(const adv_c64* X, int64_t sb, int64_t st, int64_t sf, const adv_c64* A, int batch, int F,
+                                    int T, int Fm, int Tm, float* gm, void* stream) {
+    if (!X || !A || !gm || batch <= 0 || F <= 0 || T <= 0 || Fm <= 0 || Tm <= 0 || Fm > F || Tm > T) return ADV_ERR_INVALID;
+    dim3 grid((Fm + 31) / 32, (Tm + 31) / 32, batch);
+    mask_grad_linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)X, sb, st, sf, (const float2*)A, F, T, Fm,
+                                                                  Tm, gm);
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }

@@ -330,7 +330,7 @@ stft_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, float2
 // bulk byte count (possibly 0) - one phase per call.  All threads must call it.
 template <int NT>
 __device__ __forceinline__ int stage_segment_async(float* seg, int seglen, const float* __restrict__ row, int base,
-                                                   int n_in, uint64_t* bar, int gtid = -1) {
+                                                   int n_in, uint64_t* bar, int gtid = -1, bool pad_zero = false) {
     if (gtid < 0) gtid = threadIdx.x;  // index inside the cooperating group of NT threads (CTA or warp)
     const int shift = base & 3;
     const int lo = max(base, 0), hi = min(base + seglen, n_in);
@@ -345,8 +345,10 @@ __device__ __forceinline__ int stage_segment_async(float* seg, int seglen, const
     for (int i = gtid; i < nP; i += NT) {
         const int pos = i < nL ? base + i : a1 + (i - nL);
         int idx = pos;
-        if (idx < 0) idx = -idx;
-        else if (idx >= n_in) idx = 2 * (n_in - 1) - idx;
+        if (!pad_zero) {
+            if (idx < 0) idx = -idx;
+            else if (idx >= n_in) idx = 2 * (n_in - 1) - idx;
+        }
         seg[pos - base + shift] = (idx >= 0 && idx < n_in) ? __ldg(row + idx) : 0.0f;
     }
     return shift;
@@ -530,7 +532,8 @@ stft_w_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int 
     const bool elected = (l == 0);
     const TwSmem<G::LANES> tw{tw_s + rot * 32 * G::LANES, l};
     int b = item / items_per_clip, t0 = (item - b * items_per_clip) * FW;
-    int shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar, lane);
+    int shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar, lane,
+                                        P.pad_zero != 0);
 
     for (uint32_t it = 0;; ++it) {
         __syncwarp();  // plain-load part of the slice visible to the warp
@@ -559,7 +562,7 @@ stft_w_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int 
             b = next / items_per_clip;
             t0 = (next - b * items_per_clip) * FW;
             shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar,
-                                            lane);
+                                            lane, P.pad_zero != 0);
         }
         if (BULK) {  // the previous item's rows have left the staging memory (it doubles as transpose scratch)
             if (elected) bulk_wait_read();
@@ -1818,8 +1821,10 @@ static int launch_stft_p(const adv_plan* p, const float* wav, int64_t wav_stride
 
 template <int NF, bool RECT>
 static int launch_stft_w(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
-                         float* phase, cudaStream_t s) {
+                         float* phase, int flags, cudaStream_t s) {
     using C = WCfg<NF>;
+    PlanDev pd = p->d;
+    pd.pad_zero = (flags & ADV_STFT_ZERO_PAD) ? 1 : 0;
     // bulk-async output staging where two CTAs per SM still fit (n_fft 512)
     constexpr bool BULK = (NF == 512);
     static const bool want_bulk = getenv("ADV_STFT_BULK") != nullptr;  // measured slower (22.3 vs 17.2 us): off
@@ -1835,11 +1840,11 @@ static int launch_stft_w(const adv_plan* p, const float* wav, int64_t wav_stride
     do {                                                                                                    \
         if (bulk) {                                                                                         \
             if ((rc = set_smem(stft_w_kernel<NF, M, PH, RECT, BULK>, smem)) != ADV_OK) return rc;           \
-            stft_w_kernel<NF, M, PH, RECT, BULK><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total, \
+            stft_w_kernel<NF, M, PH, RECT, BULK><<<grid, kThreads, smem, s>>>(pd, wav, wav_stride, (int)total, \
                                                                            items_per_clip, X, mag, phase);  \
         } else {                                                                                            \
             if ((rc = set_smem(stft_w_kernel<NF, M, PH, RECT, false>, smem)) != ADV_OK) return rc;          \
-            stft_w_kernel<NF, M, PH, RECT, false><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total, \
+            stft_w_kernel<NF, M, PH, RECT, false><<<grid, kThreads, smem, s>>>(pd, wav, wav_stride, (int)total, \
                                                                             items_per_clip, X, mag, phase); \
         }                                                                                                   \
     } while (0)
@@ -1853,9 +1858,10 @@ static int launch_stft_w(const adv_plan* p, const float* wav, int64_t wav_stride
 }
 
 int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
-                float* phase, cudaStream_t s) {
+                float* phase, int flags, cudaStream_t s) {
     static const char* var = getenv("ADV_STFT");  // A/B switch: "v2" one tile per CTA, "p" persistent CTA tiles
     const int which = var == nullptr ? 0 : (var[0] == 'v' ? 2 : (var[0] == 'p' ? 1 : 0));
+    if (which != 0 && (flags & ADV_STFT_ZERO_PAD)) return ADV_ERR_UNSUPPORTED;  // older kernels: reflect padding only
     if (which == 2)
         return p->d.n_fft == 512 ? launch_stft_nf<512>(p, wav, wav_stride, batch, X, mag, phase, s)
                                  : launch_stft_nf<1024>(p, wav, wav_stride, batch, X, mag, phase, s);
@@ -1867,10 +1873,10 @@ int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int bat
                               : launch_stft_p<1024, false>(p, wav, wav_stride, batch, X, mag, phase, s);
     }
     if (p->d.n_fft == 512)
-        return p->d.rect_full ? launch_stft_w<512, true>(p, wav, wav_stride, batch, X, mag, phase, s)
-                              : launch_stft_w<512, false>(p, wav, wav_stride, batch, X, mag, phase, s);
-    return p->d.rect_full ? launch_stft_w<1024, true>(p, wav, wav_stride, batch, X, mag, phase, s)
-                          : launch_stft_w<1024, false>(p, wav, wav_stride, batch, X, mag, phase, s);
+        return p->d.rect_full ? launch_stft_w<512, true>(p, wav, wav_stride, batch, X, mag, phase, flags, s)
+                              : launch_stft_w<512, false>(p, wav, wav_stride, batch, X, mag, phase, flags, s);
+    return p->d.rect_full ? launch_stft_w<1024, true>(p, wav, wav_stride, batch, X, mag, phase, flags, s)
+                          : launch_stft_w<1024, false>(p, wav, wav_stride, batch, X, mag, phase, flags, s);
 }
 
 template <int NF>

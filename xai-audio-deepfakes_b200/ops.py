@@ -152,6 +152,54 @@ def explain_spec(spec, mask, n_fft, hop, win_length, length=None, mode="log1p", 
     return rel, irr
 
 
+class _ExplainLinearFn(torch.autograd.Function):
+    """Differentiable linear mask path of the training loss (loss_function.py:36-47):
+        rel = istft(m * X),  irr = istft((1 - m) * X).
+    Forward = the fused explain kernel.  Backward: both maps are linear in m with the same adjoint, so
+        dL/dm = c_f * Re(conj(X) * STFT0(w; (g_rel - g_irr) * inv_env))
+    - one element-wise product, ONE forward STFT with zero (not reflect) edge padding and the synthesis window,
+    one fused conj-multiply + transpose.  ``spec`` gets no gradient (it is data on this path)."""
+
+    @staticmethod
+    def forward(ctx, mask, spec, n_fft, hop, win_length, length, window):
+        spec_d, sb, st, sf = _spec_strides(spec.detach())
+        rel, irr = explain_spec(spec_d, mask.detach(), n_fft, hop, win_length, length=length, mode="linear", window=window)
+        ctx.save_for_backward(spec_d)
+        ctx.geom = (n_fft, hop, win_length, length, window, tuple(mask.shape))
+        return rel, irr
+
+    @staticmethod
+    def backward(ctx, g_rel, g_irr):
+        (spec,) = ctx.saved_tensors
+        n_fft, hop, win_length, length, window, mshape = ctx.geom
+        B, Fb, T = spec.shape
+        n_out = int(length) if length is not None else hop * (T - 1)
+        if 1 + n_out // hop != T:
+            raise NotImplementedError("explain backward needs length // hop + 1 == frames (the reference's geometry)")
+        dev = spec.device
+        plan_i = get_plan(n_fft, hop, win_length, window, T, 0, n_out)
+        inv_env = torch.empty(n_out, dtype=torch.float32, device=dev)
+        check(lib().adv_plan_inv_env(plan_i.handle, ptr(inv_env), stream_ptr()), "adv_plan_inv_env")
+        zero = lambda g: torch.zeros((B, n_out), dtype=torch.float32, device=dev) if g is None else g.to(dev, torch.float32)
+        d = ((zero(g_rel) - zero(g_irr)) * inv_env).contiguous()
+        plan_f = get_plan(n_fft, hop, win_length, window, T, n_out, 0)
+        A = torch.empty((B, T, Fb), dtype=torch.complex64, device=dev)
+        check(lib().adv_stft_ex(plan_f.handle, ptr(d), d.stride(0), B, ptr(A), None, None, _lib.STFT_ZERO_PAD, stream_ptr()),
+              "adv_stft_ex")
+        m3 = mshape if len(mshape) == 3 else (mshape[0], mshape[2], mshape[3])
+        gm = torch.empty(m3, dtype=torch.float32, device=dev)
+        check(lib().adv_mask_grad_linear(ptr(spec), spec.stride(0), spec.stride(2), spec.stride(1), ptr(A), B, Fb, T,
+                                         m3[1], m3[2], ptr(gm), stream_ptr()), "adv_mask_grad_linear")
+        return gm.reshape(mshape), None, None, None, None, None, None
+
+
+def explain_linear(spec, mask, n_fft, hop, win_length, length=None, window=None):
+    """Linear-mode explain from an STFT, differentiable w.r.t. ``mask`` (training callers: loss_function.py)."""
+    if torch.is_grad_enabled() and mask.requires_grad:
+        return _ExplainLinearFn.apply(mask, spec, n_fft, hop, win_length, length, window)
+    return explain_spec(spec, mask, n_fft, hop, win_length, length=length, mode="linear", window=window)
+
+
 def mask_apply(mag, phase, mask, mode="log1p"):
     """(|X|, angle X, mask) [B,F,T] -> (rel, irr) complex [B,F,T] exactly as the reference spells it
     (expm1(m*log1p(mag)) * exp(1j*phase)); outputs are frame-major like torch.stft's."""
