@@ -60,7 +60,8 @@ int adv_plan_bins(const adv_plan* plan);
 int adv_plan_frames(const adv_plan* plan);
 /* number of output tiles per clip the istft / explain kernels use for batch size B
  * (= second dimension of the `stats` array below) */
-int adv_plan_tiles(const adv_plan* plan, int batch);
+int adv_plan_tiles(const adv_plan* plan, int batch);        /* adv_explain / adv_explain_spec */
+int adv_plan_tiles_istft(const adv_plan* plan, int batch);  /* adv_istft */
 
 /* ---- AudioProcessor.compute_stft (audioprocessor.py:82-112): torch.stft + .abs() + .angle() -----------
  * wav: dev float [B][wav_stride], first n_in samples of each row are used (caller pads/crops, :83-98).

@@ -63,6 +63,7 @@ _SIGS = {
     "adv_plan_bins": (C.c_int, [C.c_void_p]),
     "adv_plan_frames": (C.c_int, [C.c_void_p]),
     "adv_plan_tiles": (C.c_int, [C.c_void_p, C.c_int]),
+    "adv_plan_tiles_istft": (C.c_int, [C.c_void_p, C.c_int]),
     "adv_stft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_void_p]),
     "adv_istft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p,
@@ -189,6 +190,9 @@ class Plan:
 
     def tiles(self, batch):
         return lib().adv_plan_tiles(self.handle, batch)
+
+    def tiles_istft(self, batch):
+        return lib().adv_plan_tiles_istft(self.handle, batch)
 
     def __del__(self):
         try:

@@ -898,6 +898,13 @@ istft_p_kernel(PlanDev P, Tiling TL, int total_tiles, const float2* __restrict__
     const float* wl = win_s + l;
     const int c0 = l - wlo, ovl = support - P.hop, two_hop = 2 * P.hop;
     for (;;) {
+        const int next = tile + gridDim.x;
+        const int cur_b = b, cur_tile = tile - b * TL.tiles;
+        const TileGeom cg = g;
+        // warps whose units are all past the tile's last frame have nothing to transform (short tiles are chosen
+        // on purpose when they balance the rounds better, see choose_tiling)
+        const bool warp_live = __ballot_sync(0xffffffffu, va_cur) != 0;
+        if (warp_live) {
         float2 v[32];
         {
             float2 ya[17];
@@ -907,9 +914,6 @@ istft_p_kernel(PlanDev P, Tiling TL, int total_tiles, const float2* __restrict__
             merge_regs<NF>(v, l, ya, yb);
         }
         unit_fft_inverse_v<NF>(v, l, tw, my);  // (starts with a __syncwarp: the unit's slot reads are done)
-        const int next = tile + gridDim.x;
-        const int cur_b = b, cur_tile = tile - b * TL.tiles;
-        const TileGeom cg = g;
         // private strip of the unit: frame a at [0, support), frame b at [hop, hop + support)
         // (the previous tile's epilogue finished reading the strips: barrier at the loop end)
 #pragma unroll
@@ -927,6 +931,10 @@ istft_p_kernel(PlanDev P, Tiling TL, int total_tiles, const float2* __restrict__
                 const float old = k < ovl ? pbu[P.hop + k] : 0.0f;
                 pbu[P.hop + k] = fmaf(v[n1].y, wl[n1 * G::R2], old);
             }
+        }
+        } else {
+            // the gather may still touch this strip (frames clipped at the end of the clip): it must read zeros
+            for (int k = l; k < lb; k += G::LANES) pbu[k] = 0.0f;
         }
         if (next < total_tiles) {  // next tile's rows: in flight across the barrier and the epilogue
             b = next / TL.tiles;
@@ -1619,6 +1627,8 @@ explain_p512_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restri
             shift = (g.t_lo * P.hop - NF / 2) & 3;
         }
 
+        const int fa = cg.t_lo + 2 * u;
+        if (fa <= cg.t_hi) {  // (warp-uniform) units past the tile's last frame have nothing to transform
         float2 xa[9], xb[9];
         lean_fft_forward(v, l, tw, my);
         {
@@ -1627,10 +1637,11 @@ explain_p512_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restri
             wide_exchange8(send, recv, prt);
             w512::split_post(v, l, recv, xa, xb);
         }
-        const int fa = cg.t_lo + 2 * u;
         if (ovl < 0)
             for (int k = support + l; k < P.hop; k += 32) pbu[k] = make_float2(0.f, 0.f);
-#pragma unroll 1
+        // fully unrolled: a rolled loop has to rotate frame b's spectrum into frame a's registers (5 % of the
+        // kernel's instructions were moves); the body is ~1.8 k SASS instructions, the kernel stays under 100 KB
+#pragma unroll
         for (int half = 0; half < 2; ++half) {
             const bool valid = fa + half <= cg.t_hi;
             const int col = 2 * u + half;
@@ -1682,6 +1693,10 @@ explain_p512_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restri
                 }
             }
             __syncwarp();  // frame a's strip stores are visible to the unit before frame b's read-modify-write
+        }
+        } else {
+            // the gather may still touch this strip (frames clipped at the end of the clip): it must read zeros
+            for (int k = l; k < lb; k += 32) pbu[k] = make_float2(0.f, 0.f);
         }
 
         // reciprocal envelope of this thread's first groups: requested before the barrier
@@ -1882,7 +1897,7 @@ int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int bat
 template <int NF>
 static int launch_istft_nf(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch,
                            float* out, double* stats, cudaStream_t s) {
-    const Tiling tl = choose_tiling(p, batch);
+    const Tiling tl = choose_tiling(p, batch, 2);
     const size_t smem = Cfg<NF>::istft_bytes(p->d.hop, p->d.whi - p->d.wlo, tl.hops_per_tile * p->d.hop);
     int rc = set_smem(istft_kernel<NF>, smem);
     if (rc != ADV_OK) return rc;
@@ -1914,7 +1929,7 @@ static int launch_istft_p(const adv_plan* p, const Tiling& tl, const float2* X, 
 template <int NF>
 static int launch_istft_pv(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch,
                            float* out, double* stats, cudaStream_t s) {
-    const Tiling tl = choose_tiling(p, batch);
+    const Tiling tl = choose_tiling(p, batch, 2);
     // widest gather the geometry allows: hop, row pitch and base address must keep VEC-sample groups aligned
     const uintptr_t base = reinterpret_cast<uintptr_t>(out);
     int vec = 1;
@@ -1976,7 +1991,7 @@ static int launch_explain_wide(const adv_plan* p, const Tiling& tl, const float*
 int launch_explain(const adv_plan* p, const float* wav, int64_t wav_stride, const float2* X, int64_t sb,
                    int64_t st, int64_t sf, const float* mask, int Fm, int Tm, int mode, int batch, float* rel,
                    float* irr, double* stats, cudaStream_t s) {
-    const Tiling tl = choose_tiling(p, batch);
+    const Tiling tl = choose_tiling(p, batch, 1);
     const bool spec = (X != nullptr);
     static const bool narrow = getenv("ADV_EXPLAIN_NARROW") != nullptr;  // keep the 16-lane-unit kernel reachable
     static const bool oldwide = getenv("ADV_EXPLAIN_W512") != nullptr;   // A/B: the one-tile-per-CTA wide kernel

@@ -76,7 +76,7 @@ def istft(spec, n_fft, hop, win_length, length=None, window=None, return_stats=F
     out = torch.empty((B, n_out), dtype=torch.float32, device=spec.device)
     stats = None
     if return_stats:
-        stats = torch.empty((B, plan.tiles(B), 2), dtype=torch.float64, device=spec.device)
+        stats = torch.empty((B, plan.tiles_istft(B), 2), dtype=torch.float64, device=spec.device)
     check(lib().adv_istft(plan.handle, ptr(spec), sb, st, sf, B, ptr(out), ptr(stats), stream_ptr()), "adv_istft")
     return (out, stats) if return_stats else out
 
