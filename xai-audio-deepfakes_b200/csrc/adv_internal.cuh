@@ -14,8 +14,6 @@ struct PlanDev {
     int wlo, whi;          // window support [wlo, whi) inside n_fft (non-zero taps)
     int phases;            // ceil(support / hop): frames t and t+phases never overlap
     int rect_full;         // window == 1 on all n_fft taps (torch's default when win_length == n_fft)
-    int pad_zero;          // forward transform: frames past the clip edges read zeros instead of torch.stft's
-                           // reflect padding (the adjoint of istft's centre trimming; set per launch)
     const float* window;   // dev [n_fft], window centred in n_fft
     const float* inv_env;  // dev [n_out], 1 / (n_fft * sum_t w^2), 0 where no frame lands
     const float2* tw;      // dev [2][32][lanes]: exp(-2*pi*i*l*k1/n_fft), then the row-rotated variant

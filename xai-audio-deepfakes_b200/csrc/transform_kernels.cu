@@ -495,7 +495,7 @@ struct WCfg {
     }
 };
 
-template <int NF, bool MAG, bool PHASE, bool RECT, bool BULK>
+template <int NF, bool MAG, bool PHASE, bool RECT, bool BULK, bool ZP = false>  // ZP: zero instead of reflect padding
 __global__ void __launch_bounds__(kThreads, 2)
 stft_w_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int total_items, int items_per_clip,
               float2* __restrict__ X, float* __restrict__ mag, float* __restrict__ phase) {
@@ -532,8 +532,7 @@ stft_w_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int 
     const bool elected = (l == 0);
     const TwSmem<G::LANES> tw{tw_s + rot * 32 * G::LANES, l};
     int b = item / items_per_clip, t0 = (item - b * items_per_clip) * FW;
-    int shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar, lane,
-                                        P.pad_zero != 0);
+    int shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar, lane, ZP);
 
     for (uint32_t it = 0;; ++it) {
         __syncwarp();  // plain-load part of the slice visible to the warp
@@ -562,7 +561,7 @@ stft_w_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int 
             b = next / items_per_clip;
             t0 = (next - b * items_per_clip) * FW;
             shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar,
-                                            lane, P.pad_zero != 0);
+                                            lane, ZP);
         }
         if (BULK) {  // the previous item's rows have left the staging memory (it doubles as transpose scratch)
             if (elected) bulk_wait_read();
@@ -1838,12 +1837,11 @@ template <int NF, bool RECT>
 static int launch_stft_w(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
                          float* phase, int flags, cudaStream_t s) {
     using C = WCfg<NF>;
-    PlanDev pd = p->d;
-    pd.pad_zero = (flags & ADV_STFT_ZERO_PAD) ? 1 : 0;
+    const bool zero_pad = (flags & ADV_STFT_ZERO_PAD) != 0;
     // bulk-async output staging where two CTAs per SM still fit (n_fft 512)
     constexpr bool BULK = (NF == 512);
     static const bool want_bulk = getenv("ADV_STFT_BULK") != nullptr;  // measured slower (22.3 vs 17.2 us): off
-    const bool bulk = BULK && want_bulk;
+    const bool bulk = BULK && want_bulk && !zero_pad;
     const size_t smem = C::stft_bytes(p->d.hop, bulk);
     const int items_per_clip = (p->d.T + C::FW - 1) / C::FW;
     const long total = (long)items_per_clip * batch;
@@ -1851,15 +1849,23 @@ static int launch_stft_w(const adv_plan* p, const float* wav, int64_t wav_stride
     const long ctas = (total + C::WARPS - 1) / C::WARPS;
     const int grid = (int)(ctas < 2L * sm_count() ? ctas : 2L * sm_count());
     int rc;
+    if (zero_pad) {  // the adjoint-of-istft use (training backward): spectrum only
+        if (mag || phase) return ADV_ERR_UNSUPPORTED;
+        if ((rc = set_smem(stft_w_kernel<NF, false, false, RECT, false, true>, smem)) != ADV_OK) return rc;
+        stft_w_kernel<NF, false, false, RECT, false, true><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total,
+                                                                                       items_per_clip, X, mag, phase);
+        ADV_CUDA_CHECK(cudaGetLastError());
+        return ADV_OK;
+    }
 #define ADV_LAUNCH_STFT(M, PH)                                                                              \
     do {                                                                                                    \
         if (bulk) {                                                                                         \
             if ((rc = set_smem(stft_w_kernel<NF, M, PH, RECT, BULK>, smem)) != ADV_OK) return rc;           \
-            stft_w_kernel<NF, M, PH, RECT, BULK><<<grid, kThreads, smem, s>>>(pd, wav, wav_stride, (int)total, \
+            stft_w_kernel<NF, M, PH, RECT, BULK><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total, \
                                                                            items_per_clip, X, mag, phase);  \
         } else {                                                                                            \
             if ((rc = set_smem(stft_w_kernel<NF, M, PH, RECT, false>, smem)) != ADV_OK) return rc;          \
-            stft_w_kernel<NF, M, PH, RECT, false><<<grid, kThreads, smem, s>>>(pd, wav, wav_stride, (int)total, \
+            stft_w_kernel<NF, M, PH, RECT, false><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total, \
                                                                             items_per_clip, X, mag, phase); \
         }                                                                                                   \
     } while (0)
