@@ -1026,12 +1026,9 @@ __device__ __forceinline__ void mask_gains(float2 x, float m, float& g_rel, floa
         g_irr = 1.0f - m;
         return;
     }
-    const float r2 = fmaf(x.x, x.x, x.y * x.y);
-    if (r2 < 1e-30f) {  // limit a -> 0: gain -> m (the product with X vanishes either way)
-        g_rel = m;
-        g_irr = 1.0f - m;
-        return;
-    }
+    // |X|^2 clamped away from 0: for a -> 0 the gains tend to (m, 1 - m) and the product with X vanishes either
+    // way, so the clamp replaces a branch per bin (1e-30 keeps rsqrt and a = r2 * ia normal numbers)
+    const float r2 = fmaxf(fmaf(x.x, x.x, x.y * x.y), 1e-30f);
     const float ia = rsqrtf(r2);
     const float a = r2 * ia;
     float er;
@@ -1564,20 +1561,25 @@ explain_p512_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restri
     // every load of a tile that can be requested ahead of time: segment (bulk + plain edges), mask tile
     auto request_tile = [&](int bb, const TileGeom& gg, float* mask_dst) {
         stage_segment_async<NT>(seg, seglen, wav + (size_t)bb * wav_stride, gg.t_lo * P.hop - NF / 2, P.n_in, bar);
+        // thread -> fixed column c = tid & 31 and rows f = (tid >> 5) + 16 j: source and destination advance by a
+        // constant per step, the column test is loop-invariant
+        const int c = tid & 31, f0 = tid >> 5;
+        const int t = gg.t_lo + c;
+        const bool col_ok = t < Tm && t <= gg.t_hi;
         const float* mrow = mask + (size_t)bb * Fm * Tm;
-        constexpr int kTrips = (F * FT + NT - 1) / NT;
+        const float* src = mrow + (size_t)f0 * Tm + (col_ok ? t : 0);
+        uint32_t dst = smem_u32(mask_dst + f0 * MP + c);
+        constexpr int kRowsPerStep = NT / 32, kTrips = (F + kRowsPerStep - 1) / kRowsPerStep;
 #pragma unroll
         for (int j = 0; j < kTrips; ++j) {
-            const int e = tid + j * NT;
-            if (e < F * FT) {
-                const int f = e >> 5, c = e & 31;
-                const int t = gg.t_lo + c;
-                const bool ok = f < Fm && t < Tm && t <= gg.t_hi;
-                const float* src = ok ? mrow + (size_t)f * Tm + t : mrow;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(mask_dst + f * MP + c)), "l"(src),
-                             "r"(ok ? 4 : 0)
+            const int f = f0 + j * kRowsPerStep;
+            if (f < F) {
+                const bool ok = col_ok && f < Fm;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(ok ? src : mrow), "r"(ok ? 4 : 0)
                              : "memory");
             }
+            src += (size_t)kRowsPerStep * Tm;
+            dst += kRowsPerStep * MP * 4;
         }
         cp_async_commit();
     };
