@@ -366,3 +366,47 @@ def test_align_shift_full_clip(pkg):
     ref = base[2000:66000]
     deg = 0.7 * base[2000 - 1330:2000 - 1330 + 66816] + 0.1 * torch.randn(66816, generator=g, device="cuda")
     assert int(pkg.hifigan.align_shift(ref, deg).item()) == -1330
+
+
+# ---------------------------------------------------------------------------------------------------
+# persistent kernels: grid / alignment / fallback corner cases
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,n,hop", [(1, 16000, 160),      # fewer tiles than SMs: most CTAs get one tile or none
+                                     (300, 8000, 160),     # many more tiles than resident CTAs: long per-CTA tile lists
+                                     (3, 16001, 160),      # n_out not a multiple of 4: scalar gather / old explain kernel
+                                     (5, 12000, 100),      # hop % 4 == 0 but 2*hop % 32 != 0: no bank rotation
+                                     (4, 9000, 90)])       # hop % 4 != 0: VEC = 2 gather, explain falls back
+def test_persistent_kernels_corner_cases(ops, B, n, hop):
+    n_fft, win = 512, 512
+    g = torch.Generator().manual_seed(B * n + hop)
+    wav = 0.1 * torch.randn(B, n, generator=g)
+    T, Fb = 1 + n // hop, n_fft // 2 + 1
+    mask = torch.rand(B, Fb, T, generator=g)
+    cfg = dict(sampling_rate=n, n_fft=n_fft, hop_length=hop, win_length=win, audio_length=1)
+    Xr, _, _ = R.compute_stft(wav, **cfg)
+    X, _, _ = ops.stft(wav, n_fft, hop, win, want_mag=False, want_phase=False)
+    assert relerr(torch.view_as_real(X), torch.view_as_real(Xr)) < TOL
+    y = ops.istft(X, n_fft, hop, win, length=n)
+    assert relerr(y, R.compute_invert_stft(Xr, **cfg)) < TOL
+    rel, irr = ops.explain(wav, mask, n_fft, hop, win, length=n)
+    rel_r, irr_r = R.explain(wav, mask, **cfg)
+    assert relerr(rel, rel_r) < TOL and relerr(irr, irr_r) < TOL
+
+
+def test_persistent_kernels_unaligned_outputs(ops):
+    """output rows that start 4 bytes off a 16-byte boundary: the launchers must pick the narrower gather /
+    the non-persistent explain kernel instead of issuing misaligned 128-bit stores"""
+    n_fft, hop, win, n, B = 512, 160, 512, 16000, 3
+    g = torch.Generator().manual_seed(77)
+    wav = 0.1 * torch.randn(B, n, generator=g)
+    mask = torch.rand(B, n_fft // 2 + 1, 1 + n // hop, generator=g)
+    cfg = dict(sampling_rate=n, n_fft=n_fft, hop_length=hop, win_length=win, audio_length=1)
+    rel_r, irr_r = R.explain(wav, mask, **cfg)
+    big = torch.zeros(2 * B * n + 8, device="cuda")
+    rel = big[1:1 + B * n].view(B, n)
+    irr = big[B * n + 5:B * n + 5 + B * n].view(B, n)
+    tiles = ops.explain_tiles(n_fft, hop, win, n, B, length=n)
+    stats = torch.empty((B, tiles, 4), dtype=torch.float64, device="cuda")
+    ops.explain(wav, mask, n_fft, hop, win, length=n, out=(rel, irr, stats))
+    assert relerr(rel, rel_r) < TOL and relerr(irr, irr_r) < TOL
+    assert float(big[0]) == 0.0 and float(big[B * n + 1:B * n + 5].abs().max()) == 0.0   # nothing written outside
