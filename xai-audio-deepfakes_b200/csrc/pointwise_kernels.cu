@@ -54,7 +54,9 @@ row_stats_kernel(const float* __restrict__ in, int n, int parts, double* __restr
 // ---- (x - mean) / (std_unbiased + 1e-7) -----------------------------------------------------------
 // blockIdx.z selects one of up to two arrays that share a stats buffer (the explain kernel's rel / irr
 // outputs: (sum, sumsq) pairs at columns col and col + 2), so both normalisers are one launch.
-__global__ void __launch_bounds__(kPwThreads)
+// (<= 32 registers: two CTAs fit next to a resident explain CTA, so the normaliser of batch i streams through L2 /
+//  HBM while the issue-bound explain kernel of batch i+1 owns the SMs)
+__global__ void __launch_bounds__(kPwThreads, 8)
 normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const float* __restrict__ in1,
                  float* __restrict__ out1, int n, const double* __restrict__ stats, int parts, int width, int col) {
     __shared__ float s_mean, s_den;
@@ -116,7 +118,7 @@ constexpr int kLmacPerBlock = 1024;
 
 __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-__global__ void __launch_bounds__(kPwThreads)
+__global__ void __launch_bounds__(kPwThreads, 8)
 lmac_kernel(const float* __restrict__ p_in, const float* __restrict__ th_in, const float* __restrict__ q_in, int n,
             int flags, float* __restrict__ scores, double* __restrict__ sums, double* __restrict__ partials,
             unsigned int* __restrict__ counter) {

@@ -1531,8 +1531,15 @@ __device__ __forceinline__ void lean_fft_inverse(float2* v, int l, TwWide tw, fl
     w512::inv_cols(v, tw);
 }
 
+// Register cap of the persistent explain kernel.  128 would be free (512 threads, one CTA per SM) and is 2.5 %
+// faster for the kernel alone (84.2 vs 86.3 us), but at 96 the SM keeps 16 K registers for two CTAs of the
+// memory-bound normaliser, which then runs NEXT TO the issue-bound explain kernel of the following batch instead of
+// after it: the pipelined step drops from 90 to ~81 us (measured, bench.py).
+#ifndef ADV_EXPLAIN_MAXREG
+#define ADV_EXPLAIN_MAXREG 96
+#endif
 template <int MODE, bool RECT>
-__global__ void __launch_bounds__(kWideThreads, 1)
+__global__ void __maxnreg__(ADV_EXPLAIN_MAXREG)
 explain_p512_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restrict__ wav, int64_t wav_stride,
                     const float* __restrict__ mask, int Fm, int Tm, float* __restrict__ rel, float* __restrict__ irr,
                     double* __restrict__ stats) {

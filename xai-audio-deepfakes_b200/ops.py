@@ -125,6 +125,15 @@ def explain(wave, mask, n_fft, hop, win_length, length=None, mode="log1p", windo
     return rel, irr
 
 
+def normalize_pair_(rel, irr, stats):
+    """In-place zero_mean_unit_var_norm of both explain outputs from the per-tile sums the explain kernel wrote
+    (stats float64 [B, tiles, 4]); one launch."""
+    B, n_out = rel.shape
+    check(lib().adv_normalize_pair(ptr(rel), ptr(irr), B, n_out, ptr(stats), stats.shape[1], stream_ptr()),
+          "adv_normalize_pair")
+    return rel, irr
+
+
 def explain_tiles(n_fft, hop, win_length, n, batch, length=None, window=None):
     """Tiles per clip the explain kernel will use (second dim of its ``stats`` buffer)."""
     T = 1 + n // hop

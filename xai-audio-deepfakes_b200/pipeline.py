@@ -50,6 +50,17 @@ class ExplainPipeline:
         ops.lmac(self.logits[0], self.logits[1], self.logits[2], is_logit=True, want_scores=False,
                  workspace=self.ws, accumulate=self.accumulate)
 
+    # the same step in two parts, for callers that overlap part 2 of batch i with part 1 of batch i+1
+    def enqueue_explain(self):
+        ap = self.ap
+        ops.explain(self.wav, self.mask, ap.n_fft, ap.hop_length, ap.win_length, length=self.n, mode=self.mode,
+                    normalize=False, out=(self.rel, self.irr, self.stats))
+
+    def enqueue_post(self):
+        ops.normalize_pair_(self.rel, self.irr, self.stats)
+        ops.lmac(self.logits[0], self.logits[1], self.logits[2], is_logit=True, want_scores=False,
+                 workspace=self.ws, accumulate=self.accumulate)
+
     def _capture(self):
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream())
@@ -72,6 +83,65 @@ class ExplainPipeline:
             self._enqueue()
         self.launches += KERNELS_PER_STEP
         return self.sums
+
+
+class PipelinedPool:
+    """Software-pipelined evaluation over a pool of batches, captured as ONE CUDA graph:
+
+        explain(j)                      on one of ``explain_streams`` normal-priority streams (round robin, so the
+                                        almost empty last round of batch j overlaps the first round of batch j+1)
+        normalize(j) -> lmac_reduce(j)  on a HIGH-priority stream, after explain(j)
+
+    The fused explain kernel is instruction-issue bound and its register footprint is capped (96 per thread) so
+    that two 256-thread CTAs of the memory-bound normaliser fit next to a resident explain CTA: the normaliser of
+    batch j streams through L2 / HBM while explain(j+1) owns the issue slots.  One replay = ``len(pool)`` steps."""
+
+    def __init__(self, audio_processor, batch, sets, mode="log1p", explain_streams=2, accumulate=True):
+        self.pipes = [ExplainPipeline(audio_processor, batch, mode, use_graph=False, accumulate=accumulate)
+                      for _ in range(sets)]
+        dev = self.pipes[0].dev
+        self.es = [torch.cuda.Stream(device=dev) for _ in range(max(1, explain_streams))]
+        self.ns = torch.cuda.Stream(device=dev, priority=-1)
+        self.cap = torch.cuda.Stream(device=dev)
+        self.graph = None
+        self.launches = 0
+
+    def _enqueue_all(self, root):
+        start = torch.cuda.Event()
+        start.record(root)
+        for s in self.es + [self.ns]:
+            s.wait_event(start)
+        for j, p in enumerate(self.pipes):
+            e = self.es[j % len(self.es)]
+            with torch.cuda.stream(e):
+                p.enqueue_explain()
+                done = torch.cuda.Event()
+                done.record(e)
+            with torch.cuda.stream(self.ns):
+                self.ns.wait_event(done)
+                p.enqueue_post()
+        for s in self.es + [self.ns]:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            root.wait_event(ev)
+
+    def capture(self):
+        torch.cuda.synchronize()
+        with torch.cuda.stream(self.cap):   # warm up outside capture (plans, function attributes)
+            self._enqueue_all(self.cap)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.cap):
+            self._enqueue_all(self.cap)
+        for p in self.pipes:
+            p.sums.zero_()
+
+    def replay(self):
+        """``len(self.pipes)`` steps on the current stream (asynchronous)."""
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        self.launches += KERNELS_PER_STEP * len(self.pipes)
 
 
 class HostFedPipeline:
