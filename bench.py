@@ -312,6 +312,22 @@ def main():
     t_stft3 = graph_time(lambda i: ops.stft(pool[i].wav, **kw), reps)
     t_istft = graph_time(lambda i: ops.istft(specs[i], length=N, **kw), reps)
     del specs
+    # mel front-end of the vocoder path (hifigan.py:163-178 geometry: n_fft 1024, hop 256, hann 1024, 80 mels):
+    # STFT + 3xTF32 tcgen05 filterbank projection with the log epilogue, 64 clips per call
+    mel_k = None
+    try:
+        mel_mod = import_module("xai-audio-deepfakes_b200.mel")
+        mt = mel_mod.MelSpectrogram(16000, 1024, 256, 1024, 80, 0.0, 8000.0, 1.0, "slaney", "slaney", log_compress=True)
+        t_mel = graph_time(lambda i: mt(pool[i].wav), reps)
+        Tm_, Fm_ = 1 + N // 256, 513
+        mel_bytes = 4 * N + 4 * 80 * Tm_          # fused view: wave in, mel out (the spectrum is an intermediate)
+        mel_flops = 2.0 * Tm_ * 544 * 80 * 3      # 3xTF32 passes over K padded to 544
+        mel_k = {"us": t_mel * 1e6, "GBps": mel_bytes * BATCH / t_mel / 1e9,
+                 "frac": mel_bytes * BATCH / t_mel / 1e9 / peak, "tf32_tflops": mel_flops * BATCH / t_mel / 1e12,
+                 "note": "STFT (n_fft 1024, hop 256, hann) + 3xTF32 tcgen05 filterbank GEMM + log, two launches; "
+                         "bytes = wave in + mel out"}
+    except Exception as e:
+        mel_k = {"error": repr(e)[:200]}
 
     # ---- end to end through the public API with pinned host inputs
     hp = pipeline.HostFedPipeline(ap, BATCH, use_graph=True)
@@ -400,6 +416,7 @@ def main():
                                  "frac": (BYTES_STFT + 8 * F * T) * BATCH / t_stft3 / 1e9 / peak, "us": t_stft3 * 1e6},
             "istft": {"GBps": BYTES_ISTFT * BATCH / t_istft / 1e9, "frac": BYTES_ISTFT * BATCH / t_istft / 1e9 / peak,
                       "us": t_istft * 1e6},
+            "mel_frontend": mel_k,
         },
         "vocoder": voc,
         "cpu_baseline": cpu,

@@ -211,8 +211,14 @@ struct MelArgs {
     float clip;
 };
 
+__device__ __noinline__ float mel_pow_slow(float r2, float e) { return powf(r2, e); }
+
+// 512 threads: every K-block's gather + tf32 split is spread over 16 warps (8 bins per thread instead of 32), which
+// is what hides the global-load latency with one CTA per SM; warps 0-3 own the TMEM lanes for the epilogue.
+constexpr int kMelThreads = 512;
+
 template <int NM>  // padded mel count (multiple of 16)
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kMelThreads)
 mel_tc_kernel(MelArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -238,29 +244,56 @@ mel_tc_kernel(MelArgs a) {
     const int kc = tid & 7;  // 16-byte chunk = 4 fp32 = 4 bins
     constexpr uint32_t idesc = make_idesc(FMT_TF32, kTileM, NM);
     const int nkb = a.Kpad / 32;
+    constexpr int kBIters = (NM * 8 + kMelThreads - 1) / kMelThreads;
+    constexpr int kRowPass = kMelThreads / 8, kAIters = kTileM / kRowPass;  // rows gathered per pass, passes
 
-    for (int kb = 0; kb < nkb; ++kb) {
+    // Two register sets: ALL global loads of K-block kb+1 (32 spectrum bins and this thread's filterbank chunks) are
+    // requested before K-block kb is converted and multiplied, so their latency is covered by the conversion
+    // arithmetic and the barrier instead of being paid eight times per block (the first version loaded four bins at a
+    // time with 48 registers: 342 us for 64 clips, all of it exposed latency with one 128-thread CTA per SM).
+    struct Regs {
+        float2 xv[kAIters][4];
+        float4 bh[kBIters], bl[kBIters];
+    };
+    auto load_block = [&](int kb, Regs& r) {
+        const int f0 = kb * 32 + kc * 4;
+#pragma unroll
+        for (int i = 0; i < kAIters; ++i) {
+            const long m = m0 + (tid >> 3) + kRowPass * i;
+            const float2* src = a.X + (size_t)m * a.F + f0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                r.xv[i][j] = (m < a.rows && f0 + j < a.F) ? __ldg(src + j) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < kBIters; ++it) {
+            const int q = tid + it * kMelThreads;
+            if (q < NM * 8) {
+                const size_t g = (size_t)(q >> 3) * a.Kpad + kb * 32 + (q & 7) * 4;
+                r.bh[it] = __ldg(reinterpret_cast<const float4*>(a.fb_hi + g));
+                r.bl[it] = __ldg(reinterpret_cast<const float4*>(a.fb_lo + g));
+            }
+        }
+    };
+    auto do_block = [&](int kb, const Regs& r) {
         const int s = kb & 1;
         unsigned char* Ahi = smem + s * kStageBytes;
         unsigned char* Alo = Ahi + kATileBytes;
         unsigned char* Bhi = Alo + kATileBytes;
         unsigned char* Blo = Bhi + kBTile;
         if (kb >= 2) bar_wait(&bars[s], ((kb >> 1) - 1) & 1);
-        const int f0 = kb * 32 + kc * 4;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = (tid >> 3) + 16 * i;
-            const long m = m0 + row;
+        for (int i = 0; i < kAIters; ++i) {
+            const int row = (tid >> 3) + kRowPass * i;
             float hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float p = 0.0f;
-                const int f = f0 + j;
-                if (m < a.rows && f < a.F) {
-                    const float2 x = __ldg(a.X + (size_t)m * a.F + f);
-                    const float r2 = fmaf(x.x, x.x, x.y * x.y);
-                    p = a.power == 2.0f ? r2 : (a.power == 1.0f ? sqrtf(r2) : powf(r2, 0.5f * a.power));
-                }
+                const float2 x = r.xv[i][j];
+                const float r2 = fmaf(x.x, x.x, x.y * x.y);
+                // power 1: r2 * rsqrt(r2) (<= 2 ulp; IEEE sqrtf's inlined slow path made the unrolled kernel 140 KB of
+                // code and a third of its stall samples were instruction-cache misses); other exponents: out of line
+                const float p = a.power == 2.0f ? r2
+                                : (a.power == 1.0f ? r2 * rsqrtf(fmaxf(r2, 1e-37f)) : mel_pow_slow(r2, 0.5f * a.power));
                 hi[j] = __uint_as_float(__float_as_uint(p) & 0xFFFFE000u);  // what the tf32 datapath keeps
                 lo[j] = p - hi[j];
             }
@@ -268,12 +301,14 @@ mel_tc_kernel(MelArgs a) {
             *reinterpret_cast<float4*>(Ahi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
-        for (int q = tid; q < NM * 8; q += kGemmThreads) {
-            const int row = q >> 3, c = q & 7;
-            const size_t g = (size_t)row * a.Kpad + kb * 32 + c * 4;
-            const uint32_t off = sw128_offset(row, c);
-            *reinterpret_cast<float4*>(Bhi + off) = __ldg(reinterpret_cast<const float4*>(a.fb_hi + g));
-            *reinterpret_cast<float4*>(Blo + off) = __ldg(reinterpret_cast<const float4*>(a.fb_lo + g));
+#pragma unroll
+        for (int it = 0; it < kBIters; ++it) {
+            const int q = tid + it * kMelThreads;
+            if (q < NM * 8) {
+                const uint32_t off = sw128_offset(q >> 3, q & 7);
+                *reinterpret_cast<float4*>(Bhi + off) = r.bh[it];
+                *reinterpret_cast<float4*>(Blo + off) = r.bl[it];
+            }
         }
         fence_async_smem();
         __syncthreads();
@@ -289,6 +324,16 @@ mel_tc_kernel(MelArgs a) {
             }
             mma_commit(&bars[s]);
         }
+    };
+    Regs r0, r1;
+    load_block(0, r0);
+    for (int kb = 0; kb < nkb; kb += 2) {
+        if (kb + 1 < nkb) load_block(kb + 1, r1);
+        do_block(kb, r0);
+        if (kb + 1 < nkb) {
+            if (kb + 2 < nkb) load_block(kb + 2, r0);
+            do_block(kb + 1, r1);
+        }
     }
     {
         const int last = nkb - 1;
@@ -300,7 +345,7 @@ mel_tc_kernel(MelArgs a) {
     const long b = m < a.rows ? m / a.T : 0;
     const int t = (int)(m - b * a.T);
 #pragma unroll 1
-    for (int c0 = 0; c0 < NM; c0 += 8) {
+    for (int c0 = 0; c0 < (warp < 4 ? NM : 0); c0 += 8) {
         float v[8];
         tmem_ld8(trow + c0, v);
         if (m < a.rows) {
@@ -456,7 +501,7 @@ int adv_mel_project(const adv_c64* X, int64_t rows, int T, int F, const float* f
     do {                                                                                                \
         const size_t smem = 2 * (2 * (size_t)kATileBytes + 2 * (((size_t)NM * kRowBytes + 1023) / 1024 * 1024)) + 64 + 1024; \
         if ((rc = set_smem_attr(mel_tc_kernel<NM>, smem)) != ADV_OK) return rc;                         \
-        mel_tc_kernel<NM><<<grid, kGemmThreads, smem, s>>>(a);                                          \
+        mel_tc_kernel<NM><<<grid, kMelThreads, smem, s>>>(a);                                          \
     } while (0)
     if (n_mels <= 64) ADV_MEL(64);
     else if (n_mels <= 80) ADV_MEL(80);
