@@ -1847,11 +1847,9 @@ static int launch_stft_w(const adv_plan* p, const float* wav, int64_t wav_stride
                          float* phase, int flags, cudaStream_t s) {
     using C = WCfg<NF>;
     const bool zero_pad = (flags & ADV_STFT_ZERO_PAD) != 0;
-    // bulk-async output staging where two CTAs per SM still fit (n_fft 512)
-    constexpr bool BULK = (NF == 512);
-    static const bool want_bulk = getenv("ADV_STFT_BULK") != nullptr;  // measured slower (22.3 vs 17.2 us): off
-    const bool bulk = BULK && want_bulk && !zero_pad;
-    const size_t smem = C::stft_bytes(p->d.hop, bulk);
+    // (the BULK = true form of the kernel - finished rows staged in shared memory and written by bulk-async stores -
+    //  measured slower, 22.3 vs 17.2 us, and is not instantiated)
+    const size_t smem = C::stft_bytes(p->d.hop, false);
     const int items_per_clip = (p->d.T + C::FW - 1) / C::FW;
     const long total = (long)items_per_clip * batch;
     if (total > 0x7fffffffL) return ADV_ERR_UNSUPPORTED;
@@ -1868,15 +1866,9 @@ static int launch_stft_w(const adv_plan* p, const float* wav, int64_t wav_stride
     }
 #define ADV_LAUNCH_STFT(M, PH)                                                                              \
     do {                                                                                                    \
-        if (bulk) {                                                                                         \
-            if ((rc = set_smem(stft_w_kernel<NF, M, PH, RECT, BULK>, smem)) != ADV_OK) return rc;           \
-            stft_w_kernel<NF, M, PH, RECT, BULK><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total, \
-                                                                           items_per_clip, X, mag, phase);  \
-        } else {                                                                                            \
-            if ((rc = set_smem(stft_w_kernel<NF, M, PH, RECT, false>, smem)) != ADV_OK) return rc;          \
-            stft_w_kernel<NF, M, PH, RECT, false><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total, \
-                                                                            items_per_clip, X, mag, phase); \
-        }                                                                                                   \
+        if ((rc = set_smem(stft_w_kernel<NF, M, PH, RECT, false>, smem)) != ADV_OK) return rc;              \
+        stft_w_kernel<NF, M, PH, RECT, false><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total, \
+                                                                        items_per_clip, X, mag, phase);     \
     } while (0)
     if (mag && phase) ADV_LAUNCH_STFT(true, true);
     else if (mag) ADV_LAUNCH_STFT(true, false);
