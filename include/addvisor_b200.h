@@ -147,6 +147,11 @@ int adv_mask_head(const float* y1, const float* w, const float* bias, int batch,
 int adv_band_swap(const adv_c64* real, const adv_c64* voc, int batch, int T, int F, int f_lo, int f_hi,
                   adv_c64* out, void* stream);
 
+/* all bands of the fabrication loop in one launch: out[k][b][t][f] = (edges[k] <= f < edges[k+1]) ? voc : real,
+ * k < n_bands; edges: dev int [n_bands + 1]; out: dev complex64 [n_bands][B][T][F] (one batched adv_istft follows) */
+int adv_band_swap_multi(const adv_c64* real, const adv_c64* voc, int batch, int T, int F, const int* edges, int n_bands,
+                        adv_c64* out, void* stream);
+
 /* ==== tensor-core (tcgen05 / TMEM) entry points ========================================================== */
 
 /* ---- mel filterbank projection: MelSpectrogram / mel_spectogram (audioprocessor.py:38-44, hifigan.py:163-178)

@@ -410,3 +410,25 @@ def test_persistent_kernels_unaligned_outputs(ops):
     ops.explain(wav, mask, n_fft, hop, win, length=n, out=(rel, irr, stats))
     assert relerr(rel, rel_r) < TOL and relerr(irr, irr_r) < TOL
     assert float(big[0]) == 0.0 and float(big[B * n + 1:B * n + 5].abs().max()) == 0.0   # nothing written outside
+
+
+def test_band_swap_fabrication_matches_reference_loop(pkg, ops):
+    """hifigan.py:188-225 on a short pair: 8 band-swapped hann iSTFTs vs the reference's loop in torch on the CPU"""
+    g = torch.Generator().manual_seed(21)
+    n = 6000
+    s_ref, s_voc = 0.1 * torch.randn(n, generator=g), 0.1 * torch.randn(n, generator=g)
+    w = torch.hann_window(1024)
+    st = lambda x: torch.stft(x, n_fft=1024, hop_length=256, win_length=1024, window=w, return_complex=True)
+    real, voc = st(s_ref), st(s_voc)
+    want = []
+    for start in range(0, 8000, 1000):
+        comb = R.band_swap(real, voc, start, start + 1000)
+        want.append(torch.istft(comb, n_fft=1024, hop_length=256, win_length=1024, window=w))
+    want = torch.stack(want)
+    got = pkg.hifigan.band_swapped_waveforms(s_ref, s_voc)
+    assert got.shape == want.shape
+    assert relerr(got, want) < TOL
+    # the one-band op and the all-band op agree bit for bit
+    one = ops.band_swap(real.unsqueeze(0), voc.unsqueeze(0), *ops.band_rows(513, 3000, 4000))
+    allb = ops.band_swap_all(real.unsqueeze(0), voc.unsqueeze(0))
+    assert torch.equal(one[0].cpu(), allb[3].cpu())

@@ -104,6 +104,8 @@ _SIGS.update({
     "adv_plan_inv_env": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "adv_mask_grad_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "adv_band_swap_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p]),
     "adv_xcorr_blocks": (C.c_int, [C.c_int, C.c_int]),
     "adv_xcorr_shift": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "adv_mel_to_channels_last": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

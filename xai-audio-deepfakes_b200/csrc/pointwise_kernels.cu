@@ -306,6 +306,19 @@ band_swap_kernel(const float2* __restrict__ real, const float2* __restrict__ voc
     }
 }
 
+// all bands of the fabrication loop at once (hifigan.py:206-214, train_logReg_swapping.py:64-75 run it once per
+// 1 kHz band): out[k] = real with rows [edges[k], edges[k+1]) taken from voc; real / voc are read once per band
+// from L2, the n_bands x larger output is what the one batched iSTFT that follows consumes
+__global__ void __launch_bounds__(kPwThreads)
+band_swap_multi_kernel(const float2* __restrict__ real, const float2* __restrict__ voc, int64_t total, int F,
+                       const int* __restrict__ edges, int n_bands, float2* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * kPwThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kPwThreads) {
+        const int f = (int)(i % F);
+        const float2 r = __ldg(real + i), v = __ldg(voc + i);
+        for (int k = 0; k < n_bands; ++k) out[(int64_t)k * total + i] = (f >= edges[k] && f < edges[k + 1]) ? v : r;
+    }
+}
+
 // ---- gradient of the linear mask path w.r.t. the mask (backward of loss_function.py:36-47) -----------------
 // 32 x 32 tiles: frame-major reads (f fastest) of X and A, transposed through shared memory so that the
 // [B][Fm][Tm] gradient (t fastest) is written coalesced.
@@ -565,6 +578,18 @@ extern "C" int adv_mask_grad_linear(const adv_c64* X, int64_t sb, int64_t st, in
     dim3 grid((Fm + 31) / 32, (Tm + 31) / 32, batch);
     mask_grad_linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)X, sb, st, sf, (const float2*)A, F, T, Fm,
                                                                   Tm, gm);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+extern "C" int adv_band_swap_multi(const adv_c64* real, const adv_c64* voc, int batch, int T, int F, const int* edges,
+                                   int n_bands, adv_c64* out, void* stream) {
+    if (!real || !voc || !out || !edges || batch <= 0 || T <= 0 || F <= 0 || n_bands <= 0) return ADV_ERR_INVALID;
+    const int64_t total = (int64_t)batch * T * F;
+    int gx = (int)((total + kPwThreads - 1) / kPwThreads);
+    if (gx > 148 * 16) gx = 148 * 16;
+    band_swap_multi_kernel<<<gx, kPwThreads, 0, (cudaStream_t)stream>>>((const float2*)real, (const float2*)voc, total, F,
+                                                                       edges, n_bands, (float2*)out);
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }

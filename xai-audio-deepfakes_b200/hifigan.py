@@ -323,3 +323,15 @@ def align_waveforms(ref_wav, deg_wav):
         ref_aligned = ref_wav[..., : deg_aligned.shape[-1]]
     n = min(ref_aligned.shape[-1], deg_aligned.shape[-1])
     return ref_aligned[..., :n], deg_aligned[..., :n]
+
+
+def band_swapped_waveforms(s_ref, s_voc, n_fft=1024, hop_length=256, win_length=1024, band_width=1000, f_max=8000):
+    """hifigan.py:188-225 for one aligned pair: hann STFT of both signals, every 1 kHz band of the vocoded spectrum
+    swapped into the real one, hann iSTFT without ``length`` (``hop * (T - 1)`` samples).  Returns [n_bands, samples].
+    Two STFT launches, ONE band-swap launch, ONE batched iSTFT launch instead of the reference's 8 x (clone + masked
+    copy + istft)."""
+    window = torch.hann_window(win_length)
+    wav = torch.stack([s_ref.reshape(-1), s_voc.reshape(-1)]).to(ops._dev(), torch.float32)
+    X, _, _ = ops.stft(wav, n_fft, hop_length, win_length, window=window, want_mag=False, want_phase=False)
+    combined = ops.band_swap_all(X[0:1], X[1:2], band_width, f_max)
+    return ops.istft(combined, n_fft, hop_length, win_length, length=None, window=window)

@@ -289,3 +289,35 @@ def band_swap(spec_real, spec_voc, f_lo, f_hi):
     out = torch.empty_like(a)
     check(lib().adv_band_swap(ptr(a), ptr(b), B, T, Fb, int(f_lo), int(f_hi), ptr(out), stream_ptr()), "adv_band_swap")
     return out.transpose(1, 2)
+
+
+def band_rows(n_bins, start_hz, end_hz, f_top=8000.0):
+    """Row range [lo, hi) selected by the reference's ``(freqs >= start) & (freqs < end)`` with
+    ``freqs = linspace(0, f_top, n_bins)`` (hifigan.py:206-210, train_logReg_swapping.py:66-72)."""
+    freqs = torch.linspace(0, f_top, n_bins)
+    idx = torch.nonzero((freqs >= start_hz) & (freqs < end_hz)).flatten()
+    return (int(idx[0]), int(idx[-1]) + 1) if idx.numel() else (0, 0)
+
+
+def band_swap_all(spec_real, spec_voc, band_width=1000, f_max=8000, f_top=8000.0):
+    """The whole fabrication loop of hifigan.py:206-214 / train_logReg_swapping.py:64-75 in one launch: for every
+    ``band_width`` band below ``f_max`` the rows of ``spec_voc`` replace those of ``spec_real``.
+    spec_* complex [B,F,T] -> complex [n_bands*B, F, T] (band-major), ready for one batched istft."""
+    dev = _dev()
+    fm = lambda t: t.to(dev, torch.complex64).transpose(1, 2).contiguous()
+    a, b = fm(spec_real), fm(spec_voc)
+    B, T, Fb = a.shape
+    starts = list(range(0, f_max, band_width))
+    edges = []
+    for s0 in starts:
+        lo, hi = band_rows(Fb, s0, s0 + band_width, f_top)
+        if edges and edges[-1] != lo:
+            raise NotImplementedError("bands must tile the frequency axis contiguously")
+        if not edges:
+            edges.append(lo)
+        edges.append(hi)
+    e = torch.tensor(edges, dtype=torch.int32, device=dev)
+    out = torch.empty((len(starts) * B, T, Fb), dtype=torch.complex64, device=dev)
+    check(lib().adv_band_swap_multi(ptr(a), ptr(b), B, T, Fb, ptr(e), len(starts), ptr(out), stream_ptr()),
+          "adv_band_swap_multi")
+    return out.transpose(1, 2)
