@@ -121,7 +121,7 @@ def synth_host(seed, batch=BATCH):
     return wav, mask, logits
 
 
-def run_reference(args):
+def run_reference(args, out=sys.stdout):
     """--impl reference: the oracle port of the reference CPU path, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -149,7 +149,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
 
 
 def time_loop(fn, iters):
@@ -164,7 +164,18 @@ def time_loop(fn, iters):
     return a.elapsed_time(b) * 1e-3
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version line at
+    init whatever NCCL_DEBUG says), so file descriptor 1 is pointed at stderr for the rest of the process and the
+    JSON line goes to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = _claim_stdout()
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--gpus", type=int, default=1)
     ap_.add_argument("--steps", type=int, default=5000)
@@ -180,7 +191,7 @@ def main():
                           "wave of one step's kernels overlaps the head of the next step's")
     args = ap_.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -423,7 +434,7 @@ def main():
         "clocks": clocks,
         "lmac_means": metrics,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
