@@ -245,9 +245,33 @@ def main():
     np.savez_compressed(os.path.join(OUT, "mel_default_small.npz"), wav=c2n(wav),
                         mel=c2n(ap.mel_transform(wav)), fb=c2n(ap.mel_transform.mel_scale.fb),
                         params=np.array([4000, 1024, 322, 644, 80]))
+    golden_align()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("golden bytes:", total)
 
 
+def golden_align():
+    """---- 9. align_waveforms (hifigan.py:113-136), the FunctionDef lifted unchanged with ``ast`` (the module body
+    cannot be imported: it downloads the vocoder).  Three pairs: delayed / advanced / equal-length noisy copies."""
+    import torch.nn.functional as F
+    env = {"torch": torch, "F": F}
+    lift(os.path.join(REF, "hifigan.py"), ["align_waveforms"], env)
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for i, (n_ref, n_deg, delay) in enumerate([(1800, 1800, 23), (2000, 1700, -57), (1500, 1900, 0)]):
+        base = torch.randn(n_ref + n_deg + 1024, generator=g)
+        ref = base[512:512 + n_ref].clone()
+        deg = (0.8 * base[512 + delay:512 + delay + n_deg] + 0.05 * torch.randn(n_deg, generator=g)).clone()
+        ra, da = env["align_waveforms"](ref, deg)
+        out[f"ref{i}"], out[f"deg{i}"] = c2n(ref), c2n(deg)
+        out[f"ref_aligned{i}"], out[f"deg_aligned{i}"] = c2n(ra), c2n(da)
+        out[f"delay{i}"] = np.array(delay)
+    np.savez_compressed(os.path.join(OUT, "align.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-align":   # adds one fixture without touching the others
+        os.makedirs(OUT, exist_ok=True)
+        golden_align()
+    else:
+        main()

@@ -432,3 +432,12 @@ def test_band_swap_fabrication_matches_reference_loop(pkg, ops):
     one = ops.band_swap(real.unsqueeze(0), voc.unsqueeze(0), *ops.band_rows(513, 3000, 4000))
     allb = ops.band_swap_all(real.unsqueeze(0), voc.unsqueeze(0))
     assert torch.equal(one[0].cpu(), allb[3].cpu())
+
+
+def test_align_waveforms_against_reference_golden(pkg):
+    g = golden("align.npz")
+    for i in range(3):
+        ref, deg = torch.from_numpy(g[f"ref{i}"]), torch.from_numpy(g[f"deg{i}"])
+        ra, da = pkg.hifigan.align_waveforms(ref.cuda(), deg.cuda())
+        assert np.array_equal(ra.cpu().numpy(), g[f"ref_aligned{i}"])
+        assert np.array_equal(da.cpu().numpy(), g[f"deg_aligned{i}"])

@@ -125,3 +125,16 @@ def test_dft64_metric_scores_match_oracle():
     s = R.lmac_scores(*(torch.from_numpy(a) for a in (p, th, q))).numpy()
     d = dft64.lmac_scores(p, th, q)
     np.testing.assert_allclose(s, d, atol=2e-4)
+
+
+def test_align_shift_against_reference_golden():
+    """oracle align_shift vs the unmodified reference align_waveforms (hifigan.py:113-136, lifted by make_golden)."""
+    g = golden("align.npz")
+    for i in range(3):
+        ref, deg = torch.from_numpy(g[f"ref{i}"]), torch.from_numpy(g[f"deg{i}"])
+        shift = R.align_shift(ref, deg)
+        assert shift == int(g[f"delay{i}"])
+        ra = g[f"ref_aligned{i}"]
+        assert ra.shape[:2] == (1, 1)
+        want = ref[shift:shift + ra.shape[-1]] if shift > 0 else ref[:ra.shape[-1]]
+        assert np.array_equal(ra[0, 0], want.numpy())
