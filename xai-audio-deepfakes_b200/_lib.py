@@ -40,12 +40,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = os.environ.get("ADV_NVCC_EXTRA", "").split()  # e.g. -DADV_NO_F32X2 for A/B builds
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+    objdir = os.path.join(_HERE, "..", "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):  # translation units compile in parallel (the transform kernels alone take minutes)
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        res = subprocess.run([nvcc] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
+        return obj, res
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
+        results = list(pool.map(compile_one, srcs))
+    for obj, res in results:
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+    tmp = LIB_PATH + ".tmp"
+    res = subprocess.run([nvcc, "-shared", "-o", tmp] + [o for o, _ in results], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 
