@@ -391,7 +391,7 @@ def main():
         w, m, l = synth_host(1234)
         cpu_path_step(R, w, m, l)
         reps_c, t0 = 0, time.perf_counter()
-        while reps_c < 3 or (time.perf_counter() - t0 < 10.0 and reps_c < 40):
+        while reps_c < 3 or (time.perf_counter() - t0 < 12.0 and reps_c < 400):  # ~12 s of CPU work
             cpu_path_step(R, w, m, l)
             reps_c += 1
         dtc = (time.perf_counter() - t0) / reps_c
