@@ -83,7 +83,8 @@ def test_istft_matches_oracle(ops, n_fft, hop, win, n, B):
     assert relerr(got, want) < TOL
     fm = spec.transpose(1, 2).contiguous().transpose(1, 2)                         # torch.stft's layout
     got2, stats = ops.istft(fm.cuda(), n_fft, hop, win, length=n, return_stats=True)
-    assert torch.equal(got, got2)
+    # (strided rows take the narrow-unit kernel, frame-major rows the wide-unit one: same result up to round-off)
+    assert relerr(got2, want) < TOL and relerr(got2, got.cpu()) < 1e-5
     s = stats.sum(dim=1).cpu()
     np.testing.assert_allclose(s[:, 0], want.double().sum(dim=1), rtol=1e-4, atol=1e-3)
     np.testing.assert_allclose(s[:, 1], (want.double() ** 2).sum(dim=1), rtol=1e-4)

@@ -38,7 +38,8 @@ struct adv_plan {
 
 namespace adv {
 void set_cuda_error(cudaError_t e);
-Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm);  // resident CTAs per SM of the consumer
+Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm, bool balanced = false);  // resident CTAs per SM of the consumer
+bool istft_balanced();  // tiling policy of the stand-alone iSTFT kernels (ADV_ISTFT_BALANCED=1 selects the round-balanced tile length; default: longest tile)
 int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
                 float* phase, int flags, cudaStream_t s);
 int launch_istft(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,

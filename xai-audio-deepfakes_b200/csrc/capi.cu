@@ -38,7 +38,13 @@ static int tile_frame_span(const PlanDev& d, int k) {
     return worst;
 }
 
-Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm) {
+bool istft_balanced() {
+    static const char* e = getenv("ADV_ISTFT_BALANCED");
+    static const bool on = e && e[0] == '1';  // measured: no gain for the wide-unit kernel (30.7 vs 29.7 us), off
+    return on;
+}
+
+Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm, bool balanced) {
     // A tile costs one CTA pass whose length grows with the frames it transforms (each unit with a live frame
     // runs its FFTs; idle units skip them), and the persistent kernels run ceil(tiles * batch / resident CTAs)
     // rounds.  Pick the tile length that minimises rounds x (frames + fixed cost) instead of simply the longest
@@ -58,7 +64,9 @@ Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm) {
     // pipelined step 9 % slower (101.7 vs 94.8 us): with the longest tiles the 7th round is almost empty and the next
     // kernels / the next batch's launch fill it, while 6.92 full rounds leave nothing to overlap.  The longest tile is
     // therefore the default; ADV_TILING_BALANCED=1 selects the balanced policy (stand-alone kernel latency).
-    static const bool longest = getenv("ADV_TILING_BALANCED") == nullptr;
+    static const bool env_longest = getenv("ADV_TILING_BALANCED") == nullptr;
+    // (the stand-alone iSTFT can ask for the balanced policy, see istft_balanced)
+    const bool longest = env_longest && !balanced;
     int best_k = 0;
     long best_cost = 0;
     const int k_min = longest ? p->max_hops : (p->max_hops / 2 > 1 ? p->max_hops / 2 : 1);
@@ -205,7 +213,7 @@ int adv_plan_tiles(const adv_plan* plan, int batch) {
 }
 int adv_plan_tiles_istft(const adv_plan* plan, int batch) {
     if (!plan || batch <= 0 || plan->d.n_out <= 0) return ADV_ERR_INVALID;
-    return choose_tiling(plan, batch, 2).tiles;
+    return choose_tiling(plan, batch, 2, istft_balanced()).tiles;
 }
 
 int adv_stft(const adv_plan* plan, const float* wav, int64_t wav_stride, int batch, adv_c64* X, float* mag,

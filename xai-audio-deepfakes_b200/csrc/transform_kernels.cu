@@ -28,6 +28,8 @@
 
 namespace adv {
 
+// (a float-reciprocal quotient with a one-step correction was measured here: slower - 31.2 vs 29.7 us for the wide
+// iSTFT, 89 vs 87 us for the fused kernel - the MUFU / conversion pipe is the scarcer resource)
 __device__ __forceinline__ int floordiv(int a, int b) {  // b > 0
     int q = a / b;
     return (a % b != 0 && a < 0) ? q - 1 : q;
@@ -1768,6 +1770,195 @@ explain_p512_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// iSTFT, n_fft = 512, wide units (one warp per complex FFT = two frames), persistent
+//
+// The narrow-unit inverse (istft_p_kernel) keeps 32 complex values per lane: 128 registers, 16 warps per SM,
+// and it is instruction-issue / latency bound far below the HBM roofline.  Here a whole warp transforms the
+// frame pair (16 values per lane), so a 512-thread CTA needs <= 64 registers per thread and TWO of them share
+// an SM (32 warps): while one CTA waits for its spectrum rows or sits in the gather, the other runs FFTs.
+//   * rows: lane (r, h) reads the 8 (+ Nyquist) one-sided bins of w512::bin_of - per load instruction a warp
+//     covers two full 128-byte runs of the row;
+//   * both frames of the unit go through ONE complex inverse FFT (merge = the explain kernel's);
+//   * HS > 0 (rectangular full window, hop = 32 * HS): sample k = 32 j + l of frame b lands on sample
+//     32 (j + HS) + l of the unit's strip, i.e. in the SAME lane as frame a's sample - the unit's two frames are
+//     overlap-added in registers and the strip is written once (16 + HS stores, no read-modify-write);
+//   * gather: four consecutive samples per step as in istft_p_kernel; the reciprocal envelope comes from L2.
+// Requires contiguous rows (bin stride 1), hop % 4 == 0, n_out % 4 == 0, 16-byte aligned output rows.
+// ------------------------------------------------------------------------------------------------
+struct IWCfg {
+    static constexpr int UNITS = 16, NF = 512;
+    static __host__ __device__ int strip(int hop, int support) { return (hop + support + 4 + 3) & ~3; }
+    static size_t bytes(int hop, int support) {
+        return al16(sizeof(float2) * 512) + al16(sizeof(float) * UNITS * w512::SCRATCH) + al16(sizeof(float) * NF) +
+               al16(sizeof(float) * UNITS * strip(hop, support)) + al16(sizeof(double) * 2 * (kWideThreads / 32));
+    }
+};
+
+template <bool RECT, int HS>
+__global__ void __launch_bounds__(kWideThreads, 2)
+istft_w512_kernel(PlanDev P, Tiling TL, int total_tiles, const float2* __restrict__ X, int64_t sb, int64_t st,
+                  float* __restrict__ out, double* __restrict__ stats) {
+    using C = IWCfg;
+    constexpr int UNITS = C::UNITS, NF = C::NF, NT = kWideThreads;
+    // HS > 0: hop, support and the strip pitch are compile-time constants (index arithmetic of the gather folds)
+    constexpr bool FIX = RECT && HS > 0;
+    const int hop = FIX ? 32 * HS : P.hop;
+    const int wlo = FIX ? 0 : P.wlo & ~3;  // strip origin rounded down to a multiple of 4 (extra taps are exact zeros)
+    const int support = FIX ? NF : P.whi - wlo, lb = hop + support;
+    const int strip = FIX ? C::strip(32 * HS, NF) : C::strip(P.hop, P.whi - P.wlo);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(512);
+    float* scratch = cv.take<float>(UNITS * w512::SCRATCH);
+    float* win_s = cv.take<float>(NF);
+    float* pb = cv.take<float>(UNITS * strip);
+    double* red = cv.take<double>(2 * (NT / 32));
+
+    const int tid = threadIdx.x, u = tid >> 5, l = tid & 31;
+    tw_s[(tid & 15) * 32 + (tid >> 4)] = P.tw[tid];  // plan table [32][16] -> [16 k1][32 lanes]
+    win_s[tid] = P.window[tid];
+
+    // lane (r, h): slots 0..7 are bins bin0 + 16 i (w512::bin_of), slot 8 is the Nyquist bin on lane 1 only
+    const int bin0 = (l & 1) ? 128 + ((16 - (l >> 1)) & 15) : (l >> 1);
+    float2 xa[9], xb[9];
+    auto load_rows = [&](int t_id) {
+        const int bb = t_id / TL.tiles;
+        const TileGeom gg = tile_geom<NF>(P, TL, t_id - bb * TL.tiles);
+        const int fa = gg.t_lo + 2 * u;
+        const float2* xa_p = X + (size_t)bb * sb + (size_t)fa * st + bin0;
+        const float2* xb_p = xa_p + st;
+        const float2 z = make_float2(0.f, 0.f);
+        if (fa + 1 <= gg.t_hi) {  // (warp-uniform) both frames live: the common case
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                xa[i] = __ldg(xa_p + 16 * i);
+                xb[i] = __ldg(xb_p + 16 * i);
+            }
+            xa[8] = l == 1 ? __ldg(xa_p + 128) : z;
+            xb[8] = l == 1 ? __ldg(xb_p + 128) : z;
+        } else {
+            const bool va = fa <= gg.t_hi;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                xa[i] = va ? __ldg(xa_p + 16 * i) : z;
+                xb[i] = z;
+            }
+            xa[8] = (va && l == 1) ? __ldg(xa_p + 128) : z;
+            xb[8] = z;
+        }
+    };
+    // next tile's rows -> L2 (no registers held across the gather): lane l touches line l of each row
+    auto prefetch_rows = [&](int t_id) {
+        const int bb = t_id / TL.tiles;
+        const TileGeom gg = tile_geom<NF>(P, TL, t_id - bb * TL.tiles);
+        const int fa = gg.t_lo + 2 * u;
+        if (fa + 1 <= gg.t_hi && l * 16 < 257) {
+            const float2* xa_p = X + (size_t)bb * sb + (size_t)fa * st + l * 16;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xa_p));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xa_p + st));
+        }
+    };
+    int tile = blockIdx.x;
+    __syncthreads();
+
+    float* my = scratch + u * w512::SCRATCH;
+    const TwWide tw{tw_s, l};
+    const float* wl = win_s + l;
+    const int prt = w512::partner_row(l);
+    float* pbu = pb + u * strip;
+    const int c0 = l - wlo, ovl = support - hop, two_hop = 2 * hop;
+    const float inv_two_hop = 1.0f / (float)two_hop;
+
+    for (;;) {
+        const int b = tile / TL.tiles, cur_tile = tile - b * TL.tiles;
+        const TileGeom g = tile_geom<NF>(P, TL, cur_tile);
+        const int next = tile + gridDim.x;
+        if (g.t_lo + 2 * u <= g.t_hi) {  // (warp-uniform) units past the tile's last frame have nothing to transform
+            load_rows(tile);
+            float2 v[16];
+            {
+                float2 send[8], recv[8];
+                w512::merge_pre(v, l, xa, xb, send);
+                wide_exchange8(send, recv, prt);
+                w512::merge_post(v, l, recv);
+            }
+            lean_fft_inverse(v, l, tw, my);
+            // private strip of the unit: frame a at [0, support), frame b at [hop, hop + support)
+            // (the previous tile's gather finished reading the strips: barrier at the loop end)
+            if (RECT && HS > 0) {
+#pragma unroll
+                for (int j = 0; j < 16 + HS; ++j) {
+                    float o = j < 16 ? v[j < 16 ? j : 0].x : 0.0f;
+                    if (j >= HS) o += v[j >= HS ? j - HS : 0].y;
+                    pbu[j * 32 + l] = o;
+                }
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    const int k = n1 * 32 + c0;
+                    if ((unsigned)k < (unsigned)support) pbu[k] = RECT ? v[n1].x : v[n1].x * wl[n1 * 32];
+                }
+                if (ovl < 0)  // degenerate (hop > support, only legal for single-frame plans): clear the gap
+                    for (int k = support + l; k < hop; k += 32) pbu[k] = 0.0f;
+                __syncwarp();
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    const int k = n1 * 32 + c0;
+                    if ((unsigned)k < (unsigned)support) {
+                        const float old = k < ovl ? pbu[hop + k] : 0.0f;
+                        pbu[hop + k] = RECT ? v[n1].y + old : fmaf(v[n1].y, wl[n1 * 32], old);
+                    }
+                }
+            }
+        } else {
+            // the gather may still touch this strip (frames clipped at the end of the clip): it must read zeros
+            for (int k = l; k < lb; k += 32) pbu[k] = 0.0f;
+        }
+        // Holding the next rows in registers across the gather (or from the end of the gather across the barrier)
+        // was measured: 36 more live registers spill ~600 bytes per thread at the 64-register cap and the kernel
+        // takes 47 us instead of 30.  The L2 prefetch costs two instructions and no registers.
+        if (next < total_tiles) prefetch_rows(next);
+        __syncthreads();
+
+        // gather: 4 samples per step; strips covering offset x are u = x / two_hop, u-1, ... while k < lb
+        const int S = g.s1 - g.s0;
+        const int x0 = g.p0 - (g.t_lo * hop + wlo);
+        float* orow = out + (size_t)b * P.n_out + g.s0;
+        const float* erow = P.inv_env + g.s0;
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int q = tid * 4; q < S; q += NT * 4) {  // (n_out % 4 == 0 and hop % 4 == 0: S % 4 == 0)
+            const float4 e = __ldg(reinterpret_cast<const float4*>(erow + q));
+            const int x = x0 + q;
+            int uu = min(UNITS - 1, (int)(((float)x + 0.5f) * inv_two_hop));  // exact: x < 2^20
+            int k = x - uu * two_hop;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            while (uu >= 0 && k < lb) {
+                vadd(a, *reinterpret_cast<const float4*>(pb + uu * strip + k));
+                --uu;
+                k += two_hop;
+            }
+            float sq;
+            const float sm = vmul_stats(a, e, sq);
+            *reinterpret_cast<float4*>(orow + q) = a;
+            acc0 += (double)sm;
+            acc1 += (double)sq;
+        }
+        if (stats != nullptr) {
+            double acc[2] = {acc0, acc1};
+            block_sum<2, NT>(acc, red);
+            if (tid == 0) {
+                double* srow = stats + ((size_t)b * TL.tiles + cur_tile) * 2;
+                srow[0] = acc[0];
+                srow[1] = acc[1];
+            }
+        }
+        if (next >= total_tiles) break;
+        tile = next;
+        __syncthreads();  // strips and reduction scratch are free again
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
 // cudaFuncSetAttribute once per (kernel, size high-water mark): keeps the launch path free of
@@ -1904,7 +2095,7 @@ int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int bat
 template <int NF>
 static int launch_istft_nf(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch,
                            float* out, double* stats, cudaStream_t s) {
-    const Tiling tl = choose_tiling(p, batch, 2);
+    const Tiling tl = choose_tiling(p, batch, 2, istft_balanced());
     const size_t smem = Cfg<NF>::istft_bytes(p->d.hop, p->d.whi - p->d.wlo, tl.hops_per_tile * p->d.hop);
     int rc = set_smem(istft_kernel<NF>, smem);
     if (rc != ADV_OK) return rc;
@@ -1936,7 +2127,7 @@ static int launch_istft_p(const adv_plan* p, const Tiling& tl, const float2* X, 
 template <int NF>
 static int launch_istft_pv(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch,
                            float* out, double* stats, cudaStream_t s) {
-    const Tiling tl = choose_tiling(p, batch, 2);
+    const Tiling tl = choose_tiling(p, batch, 2, istft_balanced());
     // widest gather the geometry allows: hop, row pitch and base address must keep VEC-sample groups aligned
     const uintptr_t base = reinterpret_cast<uintptr_t>(out);
     int vec = 1;
@@ -1947,12 +2138,41 @@ static int launch_istft_pv(const adv_plan* p, const float2* X, int64_t sb, int64
     return launch_istft_p<NF, 1>(p, tl, X, sb, st, sf, batch, out, stats, s);
 }
 
+template <bool RECT, int HS>
+static int launch_istft_w512(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int batch, float* out,
+                             double* stats, cudaStream_t s) {
+    const Tiling tl = choose_tiling(p, batch, 2, istft_balanced());  // (same tiling as istft_p_kernel: the stats layout is unchanged)
+    const size_t smem = IWCfg::bytes(p->d.hop, p->d.whi - p->d.wlo);
+    const long total = (long)tl.tiles * batch;
+    if (total > 0x7fffffffL) return ADV_ERR_UNSUPPORTED;
+    auto kernel = istft_w512_kernel<RECT, HS>;
+    int rc = set_smem(kernel, smem);
+    if (rc != ADV_OK) return rc;
+    static const int resident = adv_resident_ctas(kernel, kWideThreads, smem, 0, 2);
+    const long slots = (long)resident * sm_count();
+    const int grid = (int)(total < slots ? total : slots);
+    kernel<<<grid, kWideThreads, smem, s>>>(p->d, tl, (int)total, X, sb, st, out, stats);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
 int launch_istft(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
                  double* stats, cudaStream_t s) {
     static const bool v2 = getenv("ADV_ISTFT_V2") != nullptr;  // A/B switch: the one-tile-per-CTA kernel
     if (v2)
         return p->d.n_fft == 512 ? launch_istft_nf<512>(p, X, sb, st, sf, batch, out, stats, s)
                                  : launch_istft_nf<1024>(p, X, sb, st, sf, batch, out, stats, s);
+    // n_fft 512, contiguous rows, 4-sample groups aligned: the wide-unit kernel (ADV_ISTFT_W512=0 selects the
+    // narrow-unit istft_p_kernel)
+    static const char* w512_env = getenv("ADV_ISTFT_W512");
+    static const bool w512_on = !(w512_env && w512_env[0] == '0');
+    if (w512_on && p->d.n_fft == 512 && sf == 1 && p->d.hop % 4 == 0 && p->d.n_out % 4 == 0 &&
+        reinterpret_cast<uintptr_t>(out) % 16 == 0 && IWCfg::bytes(p->d.hop, p->d.whi - p->d.wlo) <= 110 * 1024) {
+        if (p->d.rect_full && p->d.hop == 160)
+            return launch_istft_w512<true, 5>(p, X, sb, st, batch, out, stats, s);
+        return p->d.rect_full ? launch_istft_w512<true, 0>(p, X, sb, st, batch, out, stats, s)
+                              : launch_istft_w512<false, 0>(p, X, sb, st, batch, out, stats, s);
+    }
     // n_fft 1024 (one unit per warp, 8 units per CTA): the persistent kernel measured slower than the
     // one-tile-per-CTA kernel (51 vs 47 us on 64 x 5 s clips) - it spills around the row prefetch
     static const bool p1024 = getenv("ADV_ISTFT_P1024") != nullptr;
