@@ -73,6 +73,36 @@ static inline int adv_resident_ctas(K kernel, int threads, size_t dyn_smem, int 
     return n < 1 ? 1 : n;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched through launch_pdl() may start its CTAs - table
+// staging, barrier initialisation, index arithmetic - while the previous kernel of the stream is still draining
+// its last round; pdl_wait() (griddepcontrol.wait) then blocks until that kernel has completed and its memory is
+// visible, and MUST precede the first access to anything another kernel may have produced or may still read
+// (inputs and outputs alike; plan tables are constants).  pdl_launch_dependents() lets the next kernel of the
+// stream do the same with us.  Works in stream capture (programmatic graph edges).  Opt-in (ADV_PDL=1): see
+// pdl_enabled() in capi.cu for the measurement behind the default.
+namespace adv {
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+}  // namespace adv
+
 #define ADV_CUDA_CHECK(expr)                         \
     do {                                             \
         cudaError_t _e = (expr);                     \

@@ -38,6 +38,16 @@ static int tile_frame_span(const PlanDev& d, int k) {
     return worst;
 }
 
+bool pdl_enabled() {
+    // Measured (B200, 64 x 4 s clips): back-to-back launches of one kernel gain 0.4 - 1.2 us (stft 17.1 -> 16.7,
+    // istft 29.1 -> 28.7, explain 87.0 -> 85.8 us), but the pooled multi-stream step LOSES 20 % (774 k -> 613 k clips/s):
+    // early-scheduled CTAs of the next explain kernel sit in griddepcontrol.wait on the shared memory the normaliser
+    // CTAs of the high-priority stream were meant to use.  Opt-in therefore: ADV_PDL=1.
+    static const char* e = getenv("ADV_PDL");
+    static const bool on = e && e[0] == '1';
+    return on;
+}
+
 bool istft_balanced() {
     static const char* e = getenv("ADV_ISTFT_BALANCED");
     static const bool on = e && e[0] == '1';  // measured: no gain for the wide-unit kernel (30.7 vs 29.7 us), off

@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(kPwThreads, 8)
 normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const float* __restrict__ in1,
                  float* __restrict__ out1, int n, const double* __restrict__ stats, int parts, int width, int col) {
     __shared__ float s_mean, s_den;
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y, z = blockIdx.z;
     const float* in = z ? in1 : in0;
     float* out = z ? out1 : out0;
@@ -123,6 +125,8 @@ lmac_kernel(const float* __restrict__ p_in, const float* __restrict__ th_in, con
             int flags, float* __restrict__ scores, double* __restrict__ sums, double* __restrict__ partials,
             unsigned int* __restrict__ counter) {
     const bool is_logit = flags & ADV_LMAC_LOGITS, accumulate = flags & ADV_LMAC_ACCUMULATE;
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ double red[5][kPwThreads / 32];
     __shared__ bool last;
     double acc[5] = {0, 0, 0, 0, 0};
@@ -470,18 +474,16 @@ int adv_normalize(const float* in, float* out, int batch, int n, const double* s
     if (!in || !out || !stats || batch <= 0 || n <= 1 || parts <= 0 || width < 2 || col < 0 || col + 2 > width)
         return ADV_ERR_INVALID;
     const int chunks = (n + kRowChunk - 1) / kRowChunk;
-    normalize_kernel<<<dim3(chunks, batch, 1), kPwThreads, 0, (cudaStream_t)stream>>>(in, out, in, out, n, stats, parts,
-                                                                                     width, col);
-    ADV_CUDA_CHECK(cudaGetLastError());
+    ADV_CUDA_CHECK(launch_pdl(normalize_kernel, dim3(chunks, batch, 1), dim3(kPwThreads), 0, (cudaStream_t)stream, in, out,
+                              in, out, n, stats, parts, width, col));
     return ADV_OK;
 }
 
 int adv_normalize_pair(float* rel, float* irr, int batch, int n, const double* stats, int parts, void* stream) {
     if (!rel || !irr || !stats || batch <= 0 || n <= 1 || parts <= 0) return ADV_ERR_INVALID;
     const int chunks = (n + kRowChunk - 1) / kRowChunk;
-    normalize_kernel<<<dim3(chunks, batch, 2), kPwThreads, 0, (cudaStream_t)stream>>>(rel, rel, irr, irr, n, stats, parts, 4,
-                                                                                     0);
-    ADV_CUDA_CHECK(cudaGetLastError());
+    ADV_CUDA_CHECK(launch_pdl(normalize_kernel, dim3(chunks, batch, 2), dim3(kPwThreads), 0, (cudaStream_t)stream, rel, rel,
+                              irr, irr, n, stats, parts, 4, 0));
     return ADV_OK;
 }
 
@@ -490,9 +492,8 @@ int adv_lmac_blocks(int n) { return n <= 0 ? 0 : (n + kLmacPerBlock - 1) / kLmac
 int adv_lmac_reduce(const float* p, const float* theta, const float* q, int n, int flags, float* scores,
                     double* sums, double* block_partials, unsigned int* counter, void* stream) {
     if (!p || !theta || !q || !sums || !block_partials || !counter || n <= 0) return ADV_ERR_INVALID;
-    lmac_kernel<<<adv_lmac_blocks(n), kPwThreads, 0, (cudaStream_t)stream>>>(p, theta, q, n, flags, scores, sums,
-                                                                            block_partials, counter);
-    ADV_CUDA_CHECK(cudaGetLastError());
+    ADV_CUDA_CHECK(launch_pdl(lmac_kernel, dim3(adv_lmac_blocks(n)), dim3(kPwThreads), 0, (cudaStream_t)stream, p, theta, q,
+                              n, flags, scores, sums, block_partials, counter));
     return ADV_OK;
 }
 

@@ -524,8 +524,10 @@ stft_w_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int 
     if (lane == 0) mbar_init(bar, 1);
     for (int i = tid; i < 32 * G::LANES; i += kThreads) cp_async16(tw_s + 2 * i, P.tw + 2 * i);  // both tables
     for (int i = tid; i < NF / 4; i += kThreads) cp_async16(win_s + 4 * i, P.window + 4 * i);
+    pdl_launch_dependents();
     cp_async_wait_all();
     __syncthreads();  // tables staged, barriers initialised
+    pdl_wait();       // everything above touches plan constants only
     if (item >= total_items) return;
 
     // bank rotation of the odd unit (see above): only when the units' slices start on the same bank
@@ -1598,7 +1600,9 @@ explain_p512_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restri
         tw_s[(tid & 15) * 32 + (tid >> 4)] = P.tw[tid];
         win_s[tid] = P.window[tid];
     }
+    pdl_launch_dependents();
     __syncthreads();
+    pdl_wait();  // (everything above touches plan constants only)
     request_tile(b, g, mask_all);
     const int shift0 = (g.t_lo * P.hop - NF / 2) & 3;
     int shift = shift0;
@@ -1817,6 +1821,7 @@ istft_w512_kernel(PlanDev P, Tiling TL, int total_tiles, const float2* __restric
     const int tid = threadIdx.x, u = tid >> 5, l = tid & 31;
     tw_s[(tid & 15) * 32 + (tid >> 4)] = P.tw[tid];  // plan table [32][16] -> [16 k1][32 lanes]
     win_s[tid] = P.window[tid];
+    pdl_launch_dependents();
 
     // lane (r, h): slots 0..7 are bins bin0 + 16 i (w512::bin_of), slot 8 is the Nyquist bin on lane 1 only
     const int bin0 = (l & 1) ? 128 + ((16 - (l >> 1)) & 15) : (l >> 1);
@@ -1860,6 +1865,7 @@ istft_w512_kernel(PlanDev P, Tiling TL, int total_tiles, const float2* __restric
     };
     int tile = blockIdx.x;
     __syncthreads();
+    pdl_wait();  // (everything above touches plan constants only)
 
     float* my = scratch + u * w512::SCRATCH;
     const TwWide tw{tw_s, l};
@@ -2050,16 +2056,16 @@ static int launch_stft_w(const adv_plan* p, const float* wav, int64_t wav_stride
     if (zero_pad) {  // the adjoint-of-istft use (training backward): spectrum only
         if (mag || phase) return ADV_ERR_UNSUPPORTED;
         if ((rc = set_smem(stft_w_kernel<NF, false, false, RECT, false, true>, smem)) != ADV_OK) return rc;
-        stft_w_kernel<NF, false, false, RECT, false, true><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total,
-                                                                                       items_per_clip, X, mag, phase);
+        ADV_CUDA_CHECK(launch_pdl(stft_w_kernel<NF, false, false, RECT, false, true>, grid, kThreads, smem, s, p->d, wav,
+                                  wav_stride, (int)total, items_per_clip, X, mag, phase));
         ADV_CUDA_CHECK(cudaGetLastError());
         return ADV_OK;
     }
 #define ADV_LAUNCH_STFT(M, PH)                                                                              \
     do {                                                                                                    \
         if ((rc = set_smem(stft_w_kernel<NF, M, PH, RECT, false>, smem)) != ADV_OK) return rc;              \
-        stft_w_kernel<NF, M, PH, RECT, false><<<grid, kThreads, smem, s>>>(p->d, wav, wav_stride, (int)total, \
-                                                                        items_per_clip, X, mag, phase);     \
+        ADV_CUDA_CHECK(launch_pdl(stft_w_kernel<NF, M, PH, RECT, false>, grid, kThreads, smem, s, p->d, wav, \
+                                  wav_stride, (int)total, items_per_clip, X, mag, phase));                  \
     } while (0)
     if (mag && phase) ADV_LAUNCH_STFT(true, true);
     else if (mag) ADV_LAUNCH_STFT(true, false);
@@ -2151,7 +2157,7 @@ static int launch_istft_w512(const adv_plan* p, const float2* X, int64_t sb, int
     static const int resident = adv_resident_ctas(kernel, kWideThreads, smem, 0, 2);
     const long slots = (long)resident * sm_count();
     const int grid = (int)(total < slots ? total : slots);
-    kernel<<<grid, kWideThreads, smem, s>>>(p->d, tl, (int)total, X, sb, st, out, stats);
+    ADV_CUDA_CHECK(launch_pdl(kernel, grid, kWideThreads, smem, s, p->d, tl, (int)total, X, sb, st, out, stats));
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }
@@ -2233,8 +2239,8 @@ int launch_explain(const adv_plan* p, const float* wav, int64_t wav_stride, cons
 #define ADV_PWIDE(MODE, RECT)                                                                                   \
     do {                                                                                                        \
         if ((rc = set_smem(explain_p512_kernel<MODE, RECT>, smem)) != ADV_OK) return rc;                        \
-        explain_p512_kernel<MODE, RECT><<<grid, kWideThreads, smem, s>>>(p->d, tl, (int)total, wav, wav_stride,  \
-                                                                         mask, Fm, Tm, rel, irr, stats);        \
+        ADV_CUDA_CHECK(launch_pdl(explain_p512_kernel<MODE, RECT>, grid, kWideThreads, smem, s, p->d, tl,       \
+                                  (int)total, wav, wav_stride, mask, Fm, Tm, rel, irr, stats));                 \
     } while (0)
             if (mode == ADV_MASK_LOG1P) { if (p->d.rect_full) ADV_PWIDE(ADV_MASK_LOG1P, true); else ADV_PWIDE(ADV_MASK_LOG1P, false); }
             else { if (p->d.rect_full) ADV_PWIDE(ADV_MASK_LINEAR, true); else ADV_PWIDE(ADV_MASK_LINEAR, false); }
