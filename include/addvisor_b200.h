@@ -204,6 +204,17 @@ int adv_xcorr_blocks(int n_ref, int n_deg);
 int adv_xcorr_shift(const float* ref, int n_ref, const float* deg, int n_deg, float* ws_val, int* ws_idx, int* shift,
                     void* stream);
 
+/* The same correlation through the frequency domain (overlap-save with 1024-point frames, hop 512): O(N log N)
+ * instead of the O(N^2) of the reference's conv1d.  The caller runs adv_stft_ex(ADV_STFT_ZERO_PAD) on the padded deg
+ * (512-tap rectangular window) and ref (1024-tap rectangular window), then
+ *   adv_xcorr_fd_mac: Z[0] = 0, Z[q + 1][k] = (-1)^k sum_b conj(D[b + 1][k]) R[q + b + 1][k], q < nq, b < nb
+ *                     (D, R, Z frame-major [frames][bins]; R has t_r frames, missing frames count as zero),
+ * then adv_istft (n_fft 1024, hop 512, win 512): cc[j] sits at output sample j + 256, and
+ *   adv_argmax_first: *out = (first arg-max of x[0 .. n)) - sub.
+ * Host composition: hifigan.align_shift. */
+int adv_xcorr_fd_mac(const adv_c64* D, int nb, const adv_c64* R, int t_r, adv_c64* Z, int nq, int bins, void* stream);
+int adv_argmax_first(const float* x, int n, int sub, int* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

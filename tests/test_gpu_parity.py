@@ -343,13 +343,14 @@ def test_long_form_clip(ops):
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n_ref,n_deg,delay", [(4000, 4000, 37), (5000, 4321, -113), (3000, 3500, 0), (1500, 700, 400),
                                                (9000, 9100, -1030)])
-def test_align_shift_matches_reference_conv(pkg, n_ref, n_deg, delay):
+@pytest.mark.parametrize("method", ["fft", "direct"])
+def test_align_shift_matches_reference_conv(pkg, n_ref, n_deg, delay, method):
     g = torch.Generator().manual_seed(n_ref + n_deg)
     base = torch.randn(n_ref + n_deg + 4096, generator=g)
     ref = base[2048:2048 + n_ref].clone()
     deg = (0.8 * base[2048 + delay:2048 + delay + n_deg] + 0.05 * torch.randn(n_deg, generator=g)).clone()
     want = R.align_shift(ref, deg)
-    got = int(pkg.hifigan.align_shift(ref, deg).item())
+    got = int(pkg.hifigan.align_shift(ref, deg, method=method).item())
     assert got == want == delay
     ra, da = pkg.hifigan.align_waveforms(ref.cuda(), deg.cuda())
     assert ra.shape == da.shape and ra.shape[:2] == (1, 1)
@@ -367,6 +368,22 @@ def test_align_shift_full_clip(pkg):
     ref = base[2000:66000]
     deg = 0.7 * base[2000 - 1330:2000 - 1330 + 66816] + 0.1 * torch.randn(66816, generator=g, device="cuda")
     assert int(pkg.hifigan.align_shift(ref, deg).item()) == -1330
+    assert int(pkg.hifigan.align_shift(ref, deg, method="direct").item()) == -1330
+
+
+@pytest.mark.parametrize("n_ref,n_deg", [(700, 300), (512, 512), (1024, 511), (513, 1500), (40, 9), (6000, 2047)])
+def test_xcorr_fft_curve_matches_direct(pkg, n_ref, n_deg):
+    """the whole correlation curve of the frequency-domain path (not only its arg-max) against the reference's conv1d
+    on the CPU, including block / frame boundary sizes"""
+    import torch.nn.functional as F
+    H = pkg.hifigan
+    g = torch.Generator().manual_seed(n_ref * 7 + n_deg)
+    ref, deg = torch.randn(n_ref, generator=g), torch.randn(n_deg, generator=g)
+    want = F.conv1d(F.pad(ref.view(1, 1, -1), (n_deg, n_deg)), deg.view(1, 1, -1)).reshape(-1)
+    got = H.xcorr_curve(ref, deg).cpu()
+    assert got.shape == want.shape
+    assert relerr(got, want) < 1e-5
+    assert int(H.align_shift(ref, deg).item()) == int(torch.argmax(want)) - n_deg
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -453,6 +453,72 @@ xcorr_final_kernel(const float* __restrict__ best_val, const int* __restrict__ b
     }
 }
 
+// ---- cross-correlation through the frequency domain (overlap-save, 1024-point frames, hop 512) ------------------
+// With D[t] = zero-padded STFT frames of the 512-tap blocks of deg (rectangular 512-window centred in the frame) and
+// R[t] = STFT frames of the zero-padded ref (full rectangular window), both frame-major [frames][513]:
+//     Z[q + 1][k] = (-1)^k * sum_b conj(D[b + 1][k]) * R[q + b + 1][k],      Z[0][k] = 0
+// is the spectrum whose iSTFT (512-window, hop 512) holds cc[512 q + j] at output sample 512 q + j + 256: the two
+// quarter-frame shifts (block at in-frame offset 256 on the way in, valid lags moved under the synthesis window on
+// the way out) are e^{-i pi k / 2} each.  One CTA per output frame, one thread per bin, 4 blocks of deg in flight.
+__global__ void __launch_bounds__(256)
+xcorr_fd_mac_kernel(const float2* __restrict__ D, int nb, const float2* __restrict__ R, int t_r, float2* __restrict__ Z,
+                    int bins) {
+    const int q = blockIdx.x;  // output frame q (frame 0 is the zero frame)
+    for (int k = threadIdx.x; k < bins; k += 256) {
+        float2 acc = make_float2(0.f, 0.f);
+        if (q > 0) {
+            const int hi = min(nb, t_r - q);  // R frames q + b must exist: b < t_r - q
+            int b = 0;
+            for (; b + 4 <= hi; b += 4) {
+                float2 d[4], r[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    d[j] = __ldg(D + (size_t)(b + j + 1) * bins + k);
+                    r[j] = __ldg(R + (size_t)(q + b + j) * bins + k);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {  // conj(d) * r
+                    acc.x = fmaf(d[j].x, r[j].x, fmaf(d[j].y, r[j].y, acc.x));
+                    acc.y = fmaf(d[j].x, r[j].y, fmaf(-d[j].y, r[j].x, acc.y));
+                }
+            }
+            for (; b < hi; ++b) {
+                const float2 d = __ldg(D + (size_t)(b + 1) * bins + k), r = __ldg(R + (size_t)(q + b) * bins + k);
+                acc.x = fmaf(d.x, r.x, fmaf(d.y, r.y, acc.x));
+                acc.y = fmaf(d.x, r.y, fmaf(-d.y, r.x, acc.y));
+            }
+            if (k & 1) { acc.x = -acc.x; acc.y = -acc.y; }
+        }
+        Z[(size_t)q * bins + k] = acc;
+    }
+}
+
+// first maximum of x[0 .. n): *out = argmax - sub (single CTA; n is a few hundred thousand at most)
+__global__ void __launch_bounds__(1024)
+argmax_first_kernel(const float* __restrict__ x, int n, int sub, int* __restrict__ out) {
+    __shared__ float rv[32];
+    __shared__ int ri[32];
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int k = threadIdx.x; k < n; k += 1024) {
+        const float v = __ldg(x + k);
+        if (v > bv) { bv = v; bi = k; }  // (k increases per thread: the first maximum is kept)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { rv[threadIdx.x >> 5] = bv; ri[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 32; ++k)
+            if (rv[k] > bv || (rv[k] == bv && ri[k] < bi)) { bv = rv[k]; bi = ri[k]; }
+        *out = bi - sub;
+    }
+}
+
 }  // namespace adv
 
 using namespace adv;
@@ -569,6 +635,22 @@ extern "C" int adv_xcorr_shift(const float* ref, int n_ref, const float* deg, in
     const int blocks = adv_xcorr_blocks(n_ref, n_deg);
     xcorr_partial_kernel<<<blocks, kXcThreads, 0, (cudaStream_t)stream>>>(ref, n_ref, deg, n_deg, ws_val, ws_idx);
     xcorr_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ws_val, ws_idx, blocks, n_deg, shift);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+extern "C" int adv_xcorr_fd_mac(const adv_c64* D, int nb, const adv_c64* R, int t_r, adv_c64* Z, int nq, int bins,
+                               void* stream) {
+    if (!D || !R || !Z || nb <= 0 || t_r <= 0 || nq <= 0 || bins <= 0) return ADV_ERR_INVALID;
+    xcorr_fd_mac_kernel<<<nq + 1, 256, 0, (cudaStream_t)stream>>>((const float2*)D, nb, (const float2*)R, t_r, (float2*)Z,
+                                                                  bins);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+extern "C" int adv_argmax_first(const float* x, int n, int sub, int* out, void* stream) {
+    if (!x || !out || n <= 0) return ADV_ERR_INVALID;
+    argmax_first_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, sub, out);
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }

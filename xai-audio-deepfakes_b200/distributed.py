@@ -37,3 +37,53 @@ def allreduce_sums(sums: torch.Tensor) -> torch.Tensor:
     if initialized() and world_size() > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     return sums
+
+
+def chunk_bounds(n_chunks: int, r: int | None = None, w: int | None = None):
+    """Shard of whole chunks owned by rank ``r`` (same rule as :func:`shard_bounds`, in units of chunks)."""
+    return shard_bounds(n_chunks, r, w)
+
+
+@torch.no_grad()
+def evaluate_synthetic_sharded(audio_processor, n_clips: int, chunk: int = 1024, seed: int = 1234, mode: str = "log1p",
+                               rank_: int | None = None, world_: int | None = None, reduce: bool = True):
+    """BASELINE configs[3] / SURVEY 8(d) cfg-4: ``n_clips`` synthetic clips, batch-sharded over the ranks in whole
+    chunks of ``chunk`` clips.  Chunk ``c`` is generated ON THE DEVICE from ``seed + c`` (global chunk index), so every
+    world size sees identical data; each rank runs explain -> normalise x2 -> LMAC sums on its chunks and the only
+    exchange is the all-reduce of the partial sums.
+
+    Returns a float64 device tensor [10]: the six LMAC sums {FF, fidelity, AD, AI, AG, count} followed by a checksum
+    of the transform outputs before normalisation {sum rel, sum rel^2, sum irr, sum irr^2} (from the per-tile
+    partials the fused kernel writes), so that world-size invariance covers the kernels and not only the metrics.
+    The classifier is not on this path (reference torch module): its three logit vectors are synthetic, N(0, 2^2).
+    ``rank_`` / ``world_`` override the process group (single-process tests of the sharding)."""
+    from . import ops
+    ap = audio_processor
+    dev = ops._dev()
+    n = int(ap.audio_length * ap.sampling_rate)
+    F, T = ap.n_fft // 2 + 1, 1 + n // ap.hop_length
+    n_chunks = (n_clips + chunk - 1) // chunk
+    lo, hi = chunk_bounds(n_chunks, rank_, world_)
+    total = torch.zeros(10, dtype=torch.float64, device=dev)
+    gen = torch.Generator(device=dev)
+    ws = {}
+    for c in range(lo, hi):
+        size = min(chunk, n_clips - c * chunk)
+        gen.manual_seed(seed + c)
+        wav = 0.1 * torch.randn(size, n, generator=gen, device=dev)
+        mask = torch.rand(size, F, T, generator=gen, device=dev)
+        logits = 2.0 * torch.randn(3, size, generator=gen, device=dev)
+        tiles = ops.explain_tiles(ap.n_fft, ap.hop_length, ap.win_length, n, size, length=n)
+        rel = torch.empty((size, n), dtype=torch.float32, device=dev)
+        irr = torch.empty_like(rel)
+        stats = torch.empty((size, tiles, 4), dtype=torch.float64, device=dev)
+        ops.explain(wav, mask, ap.n_fft, ap.hop_length, ap.win_length, length=n, mode=mode, normalize=True,
+                    out=(rel, irr, stats))
+        if size not in ws:
+            ws[size] = ops.LmacWorkspace(size, dev)
+        _, sums = ops.lmac(logits[0], logits[1], logits[2], is_logit=True, want_scores=False, workspace=ws[size])
+        total[:6] += sums
+        total[6:] += stats.sum(dim=(0, 1))
+    if reduce:
+        allreduce_sums(total)
+    return total

@@ -292,19 +292,68 @@ class HifiganGenerator:
         return fl + 2 * L * ch * cfg.conv_post_kernel
 
 
-def align_shift(ref_wav, deg_wav):
+def align_shift(ref_wav, deg_wav, method="fft"):
     """Arg-max lag of the cross-correlation the reference computes with a direct conv1d (hifigan.py:113-126):
-    device int32 tensor holding ``argmax(conv1d(pad(ref, (P, P)), deg)) - P`` with ``P = len(deg)``."""
+    device int32 tensor holding ``argmax(conv1d(pad(ref, (P, P)), deg)) - P`` with ``P = len(deg)``.
+
+    ``method="fft"`` (default): overlap-save through our own transform kernels - zero-padded STFT (n_fft 1024,
+    hop 512) of deg in 512-tap blocks and of the padded ref, one multiply-accumulate launch over (output frame, bin),
+    one iSTFT, one arg-max: O(N log N), 6 launches.  ``method="direct"``: the O(N^2) fp32 accumulation in the
+    reference's own order of operations (adv_xcorr_shift).  Both return the first maximum; they can only differ when
+    two lags tie to within fp32 round-off of the correlation peak."""
     dev = ops._dev()
     ref = ref_wav.reshape(-1).to(dev, torch.float32).contiguous()
     deg = deg_wav.reshape(-1).to(dev, torch.float32).contiguous()
-    nb = lib().adv_xcorr_blocks(ref.numel(), deg.numel())
-    ws_val = torch.empty(nb, dtype=torch.float32, device=dev)
-    ws_idx = torch.empty(nb, dtype=torch.int32, device=dev)
     shift = torch.empty(1, dtype=torch.int32, device=dev)
-    check(lib().adv_xcorr_shift(ptr(ref), ref.numel(), ptr(deg), deg.numel(), ptr(ws_val), ptr(ws_idx), ptr(shift),
-                                stream_ptr()), "adv_xcorr_shift")
+    if method == "direct":
+        nb = lib().adv_xcorr_blocks(ref.numel(), deg.numel())
+        ws_val = torch.empty(nb, dtype=torch.float32, device=dev)
+        ws_idx = torch.empty(nb, dtype=torch.int32, device=dev)
+        check(lib().adv_xcorr_shift(ptr(ref), ref.numel(), ptr(deg), deg.numel(), ptr(ws_val), ptr(ws_idx), ptr(shift),
+                                    stream_ptr()), "adv_xcorr_shift")
+        return shift
+    if method != "fft":
+        raise ValueError("method must be 'fft' or 'direct'")
+    cc = xcorr_curve(ref, deg)
+    check(lib().adv_argmax_first(ptr(cc), cc.numel(), deg.numel(), ptr(shift), stream_ptr()), "adv_argmax_first")
     return shift
+
+
+def xcorr_curve(ref_wav, deg_wav):
+    """``conv1d(pad(ref, (P, P)), deg)`` (hifigan.py:119-122), all ``len(ref) + len(deg) + 1`` lags, by overlap-save
+    through the transform kernels: zero-padded STFTs (n_fft 1024, hop 512) of deg in 512-tap blocks and of the padded
+    ref, adv_xcorr_fd_mac over (output frame, bin), one iSTFT whose 512-tap synthesis window keeps exactly the valid
+    half of every circular correlation.  Returns a device float32 view [n_lags]."""
+    from ._lib import STFT_ZERO_PAD, get_plan
+    dev = ops._dev()
+    ref = ref_wav.reshape(-1).to(dev, torch.float32).contiguous()
+    deg = deg_wav.reshape(-1).to(dev, torch.float32).contiguous()
+    NF, H, BINS = 1024, 512, 513
+    n_ref, P = ref.numel(), deg.numel()
+    n_lags = n_ref + P + 1
+    nb, nq = (P + H - 1) // H, (n_lags + H - 1) // H
+    # deg blocks: block b = deg[512 b : 512 b + 512] sits in frame b + 1 under the centred 512-tap window
+    x = torch.zeros((1, H * nb + H), dtype=torch.float32, device=dev)
+    x[0, 256:256 + P] = deg
+    # ref padded by P zeros in front (the reference's F.pad); frame t holds y[512 (t - 1) : 512 (t + 1)]
+    y = torch.zeros((1, H * (nq + nb + 1)), dtype=torch.float32, device=dev)
+    y[0, P:P + n_ref] = ref
+
+    def zstft(sig, win):
+        n = sig.shape[1]
+        T = 1 + n // H
+        plan = get_plan(NF, H, win, None, T, n, 0)
+        X = torch.empty((1, T, BINS), dtype=torch.complex64, device=dev)
+        check(lib().adv_stft_ex(plan.handle, ptr(sig), sig.stride(0), 1, ptr(X), None, None, STFT_ZERO_PAD, stream_ptr()),
+              "adv_stft_ex")
+        return X, T
+
+    D, _ = zstft(x, H)
+    R, t_r = zstft(y, NF)
+    Z = torch.empty((1, nq + 1, BINS), dtype=torch.complex64, device=dev)
+    check(lib().adv_xcorr_fd_mac(ptr(D), nb, ptr(R), t_r, ptr(Z), nq, BINS, stream_ptr()), "adv_xcorr_fd_mac")
+    out = ops.istft(Z.transpose(1, 2), NF, H, H, length=n_lags + 256)  # cc[j] = out[j + 256]
+    return out[0, 256:]
 
 
 def align_waveforms(ref_wav, deg_wav):
