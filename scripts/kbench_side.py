@@ -60,7 +60,10 @@ t = timed(lambda i: ops.lmac(lg[0], lg[1], lg[2], is_logit=True, want_scores=Fal
 out["lmac_100k"] = {"us": t * 1e6, "GBps": 100000 * 12 / t / 1e9}
 
 ref, deg = torch.randn(64000, generator=g, device="cuda"), torch.randn(66816, generator=g, device="cuda")
-t = timed(lambda i: H.align_shift(ref, deg), reps=5)
+t = timed(lambda i: H.align_shift(ref, deg, method="direct"), reps=5)
 fma = 0.5 * (64000 + 66816 + 1) * 66816  # about half of the lag x tap rectangle meets non-zero samples
-out["xcorr_4s_pair"] = {"us": t * 1e6, "TFMA/s": fma / t / 1e12}
+out["xcorr_4s_pair_direct"] = {"us": t * 1e6, "TFMA/s": fma / t / 1e12}
+t = timed(lambda i: H.align_shift(ref, deg), reps=20)
+out["xcorr_4s_pair_fft"] = {"us": t * 1e6, "launches": "2 fills + 2 copies (torch) + 2 stft + mac + istft + argmax",
+                            "same_shift": int(H.align_shift(ref, deg)) == int(H.align_shift(ref, deg, method="direct"))}
 print(json.dumps(out, indent=1))
