@@ -1,0 +1,91 @@
+"""BASELINE configs[4] / SURVEY 8(d) cfg-5: 30 s long-form clips through the saliency path (captum_saliency.py:
+136-146,170-186): attribution -> |a| / max|a| time-domain mask -> wave * m, wave * (1 - m) -> compute_stft of the
+three waveforms (reference defaults n_fft 1024 / hop 322 / win 644) -> FF / fidelity sums.  The attribution itself
+(IntegratedGradients through the reference's wav2vec2 + logReg torch modules, 50 steps) is not ours and not timed:
+a seeded N(0,1) tensor of the same shape stands in, as do the three logit vectors.
+
+    python scripts/cfg5_longform.py [--clips 16]            # per GPU; under torch.distributed.run: weak scaling
+
+Prints one JSON line on rank 0: clips/s (max over ranks, CUDA events), per-kernel time and achieved HBM GB/s."""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+ap_ = argparse.ArgumentParser()
+ap_.add_argument("--clips", type=int, default=16)
+ap_.add_argument("--reps", type=int, default=20)
+args = ap_.parse_args()
+world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+torch.cuda.set_device(local)
+if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+pkg = importlib.import_module("xai-audio-deepfakes_b200")
+pkg._lib.build()
+ops, D = pkg.ops, pkg.distributed
+ap = pkg.audioprocessor.AudioProcessor(audio_length=30)  # reference defaults: 16 kHz, 1024 / 322 / 644
+B, n = args.clips, 480000
+F, T = 513, 1 + n // 322
+POOL = 6  # rotating sets: 6 x (2 x 30.7 MB in) > L2 together with the outputs
+g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+wavs = [0.1 * torch.randn(B, n, generator=g, device="cuda") for _ in range(POOL)]
+attrs = [torch.randn(B, n, generator=g, device="cuda") for _ in range(POOL)]
+logits = 2.0 * torch.randn(3, B, generator=g, device="cuda")
+ws = ops.LmacWorkspace(B, torch.device("cuda"))
+
+
+def timed(fn, reps=args.reps):
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(reps):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / reps
+
+
+def step(i):
+    w, a = wavs[i % POOL], attrs[i % POOL]
+    _, rel, irr = ops.td_mask(w, a, want_mask=False)
+    for x in (w, rel, irr):
+        ap.compute_stft(x)
+    _, sums = ops.lmac(logits[0], logits[1], logits[2], is_logit=True, want_scores=False, workspace=ws,
+                       accumulate=True)
+    return sums
+
+
+peak = 6537.0
+try:
+    peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+t_td = timed(lambda i: ops.td_mask(wavs[i % POOL], attrs[i % POOL], want_mask=False))
+t_st = timed(lambda i: ap.compute_stft(wavs[i % POOL]))
+if world > 1:
+    dist.barrier()
+t_all = timed(step)
+sums = ws.sums.clone()
+tt = torch.tensor([t_all], dtype=torch.float64, device="cuda")
+if world > 1:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    D.allreduce_sums(sums)
+if rank == 0:
+    by_td, by_st = B * n * 4 * 5, B * (4 * n + 16 * F * T)  # 4N*2 + 4N*3 and 4N + 16FT
+    print(json.dumps({
+        "workload": f"configs[4]: {B} x 30 s clips per GPU, saliency masks + 3 x compute_stft (1024/322/644) + LMAC sums; "
+                    "attribution and logits synthetic (IG through the reference's torch classifier is not timed)",
+        "n_gpus": world, "clips_per_s": world * B / float(tt), "ms_per_step": float(tt) * 1e3,
+        "td_mask": {"us": t_td * 1e6, "GBps": by_td / t_td / 1e9, "frac": by_td / t_td / 1e9 / peak},
+        "compute_stft_X_mag_phase": {"us": t_st * 1e6, "GBps": by_st / t_st / 1e9, "frac": by_st / t_st / 1e9 / peak},
+        "count": float(sums[5])}))
+if world > 1:
+    dist.destroy_process_group()
