@@ -1777,6 +1777,113 @@ explain_p512_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// STFT, n_fft = 512, wide units + warp-autonomous (one warp = one complex FFT = two frames per item)
+//
+// Same scheme as stft_w_kernel (every warp owns its frames, its slice of the waveform, its mbarrier and its place
+// in the item list; the next slice is requested by one bulk-async copy as soon as the warp holds the current
+// samples), but with the 32-lane x 16-value FFT of the fused kernel: 64 registers per thread instead of 128, so
+// FOUR 256-thread CTAs share an SM (32 warps instead of 16) and the sqrt / atan2 / store tail of one warp hides
+// behind the butterflies of the others.  Lane (r, h) ends up with bins bin0 + 16 i of both frames: every store
+// instruction of the warp writes two full 128-byte runs of the row.
+// ------------------------------------------------------------------------------------------------
+struct WWCfg {
+    static constexpr int WARPS = kThreads / 32, NF = 512, F = 257;
+    static __host__ __device__ size_t seg_floats(int hop) { return ((size_t)hop + NF + 8 + 3) & ~size_t(3); }  // 16-byte pitch
+    static size_t bytes(int hop) {
+        return al16(sizeof(float2) * 512) + al16(sizeof(float) * WARPS * w512::SCRATCH) + al16(sizeof(float) * NF) +
+               al16(sizeof(float) * WARPS * seg_floats(hop)) + al16(sizeof(uint64_t) * WARPS);
+    }
+};
+
+template <bool MAG, bool PHASE, bool RECT>
+__global__ void __launch_bounds__(kThreads, 4)
+stft_ww_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int total_items, int items_per_clip,
+               float2* __restrict__ X, float* __restrict__ mag, float* __restrict__ phase) {
+    using C = WWCfg;
+    constexpr int F = C::F, NF = C::NF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(512);
+    float* scratch = cv.take<float>(C::WARPS * w512::SCRATCH);
+    float* win_s = cv.take<float>(NF);
+    float* seg_all = cv.take<float>(C::WARPS * C::seg_floats(P.hop));
+    uint64_t* bars = cv.take<uint64_t>(C::WARPS);
+
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    float* seg = seg_all + (size_t)w * C::seg_floats(P.hop);
+    uint64_t* bar = bars + w;
+    const int seglen = P.hop + NF;
+    const int stride = gridDim.x * C::WARPS;
+    int item = blockIdx.x * C::WARPS + w;
+
+    if (l == 0) mbar_init(bar, 1);
+    for (int i = tid; i < 512; i += kThreads) tw_s[(i & 15) * 32 + (i >> 4)] = P.tw[i];  // [32][16] -> [16 k1][32 lanes]
+    for (int i = tid; i < NF; i += kThreads) win_s[i] = P.window[i];
+    pdl_launch_dependents();
+    __syncthreads();  // tables staged, barriers initialised
+    pdl_wait();
+    if (item >= total_items) return;
+
+    float* my = scratch + w * w512::SCRATCH;
+    const TwWide tw{tw_s, l};
+    const int prt = w512::partner_row(l);
+    const int bin0 = (l & 1) ? 128 + ((16 - (l >> 1)) & 15) : (l >> 1);  // w512::bin_of(l, i) = bin0 + 16 i, i < 8
+    int b = item / items_per_clip, t0 = (item - b * items_per_clip) * 2;
+    int shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar, l);
+
+    for (uint32_t it = 0;; ++it) {
+        __syncwarp();  // plain-load part of the slice visible to the warp
+        mbar_wait(bar, it & 1);
+        float2 v[16];
+        {
+            const float* sa = seg + shift + l;
+            const float* sb = sa + P.hop;
+            const float* wl = win_s + l;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+                const float ww = RECT ? 1.0f : wl[n1 * 32];
+                v[n1] = make_float2(sa[n1 * 32] * ww, sb[n1 * 32] * ww);
+            }
+        }
+        const int cur_b = b, fa = t0;
+        const int next = item + stride;
+        __syncwarp();  // every lane holds its samples: the slice buffer is free for the next item
+        if (next < total_items) {
+            b = next / items_per_clip;
+            t0 = (next - b * items_per_clip) * 2;
+            shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar, l);
+        }
+        lean_fft_forward(v, l, tw, my);
+        float2 xa[9], xb[9];
+        {
+            float2 send[8], recv[8];
+            w512::split_pre(v, send);
+            wide_exchange8(send, recv, prt);
+            w512::split_post(v, l, recv, xa, xb);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int t = fa + half;
+            if (t >= P.T) continue;
+            const float2* x = half ? xb : xa;
+            const size_t row = ((size_t)cur_b * P.T + t) * F + bin0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                if (i == 8 && l != 1) continue;  // slot 8 is the Nyquist bin (256 = bin0 + 128 on lane 1)
+                X[row + 16 * i] = x[i];
+                if (MAG) {
+                    const float r2 = fmaf(x[i].x, x[i].x, x[i].y * x[i].y);
+                    mag[row + 16 * i] = r2 * rsqrtf(fmaxf(r2, 1e-37f));
+                }
+                if (PHASE) phase[row + 16 * i] = fast_atan2f(x[i].y, x[i].x);
+            }
+        }
+        if (next >= total_items) break;
+        item = next;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // iSTFT, n_fft = 512, wide units (one warp per complex FFT = two frames), persistent
 //
 // The narrow-unit inverse (istft_p_kernel) keeps 32 complex values per lane: 128 registers, 16 warps per SM,
@@ -2079,6 +2186,34 @@ static int launch_stft_w(const adv_plan* p, const float* wav, int64_t wav_stride
     return ADV_OK;
 }
 
+template <bool RECT>
+static int launch_stft_ww(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
+                          float* phase, cudaStream_t s) {
+    using C = WWCfg;
+    const size_t smem = C::bytes(p->d.hop);
+    const int items_per_clip = (p->d.T + 1) / 2;
+    const long total = (long)items_per_clip * batch;
+    if (total > 0x7fffffffL) return ADV_ERR_UNSUPPORTED;
+    const long ctas = (total + C::WARPS - 1) / C::WARPS;
+    int rc;
+#define ADV_LAUNCH_STFT(M, PH)                                                                                   \
+    do {                                                                                                         \
+        auto kernel = stft_ww_kernel<M, PH, RECT>;                                                               \
+        if ((rc = set_smem(kernel, smem)) != ADV_OK) return rc;                                                  \
+        static const int resident = adv_resident_ctas(kernel, kThreads, smem, 0, 4);                             \
+        const long slots = (long)resident * sm_count();                                                          \
+        const int grid = (int)(ctas < slots ? ctas : slots);                                                     \
+        ADV_CUDA_CHECK(launch_pdl(kernel, grid, kThreads, smem, s, p->d, wav, wav_stride, (int)total,            \
+                                  items_per_clip, X, mag, phase));                                               \
+    } while (0)
+    if (mag && phase) ADV_LAUNCH_STFT(true, true);
+    else if (mag) ADV_LAUNCH_STFT(true, false);
+    else if (phase) ADV_LAUNCH_STFT(false, true);
+    else ADV_LAUNCH_STFT(false, false);
+#undef ADV_LAUNCH_STFT
+    return ADV_OK;
+}
+
 int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
                 float* phase, int flags, cudaStream_t s) {
     static const char* var = getenv("ADV_STFT");  // A/B switch: "v2" one tile per CTA, "p" persistent CTA tiles
@@ -2094,6 +2229,15 @@ int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int bat
         return p->d.rect_full ? launch_stft_p<1024, true>(p, wav, wav_stride, batch, X, mag, phase, s)
                               : launch_stft_p<1024, false>(p, wav, wav_stride, batch, X, mag, phase, s);
     }
+    // n_fft 512, reflect padding, magnitude and / or phase requested (compute_stft's full return): the wide-unit kernel.
+    // Measured per 64 x 4 s clips: X + |X| + angle 31.5 us (wide) vs 36.3 us (narrow); X only 18.5 vs 17.1 us - the
+    // two-frame items of the wide kernel pay their per-item staging twice as often, which only the heavier sqrt / atan2
+    // tail amortises.  ADV_STFT_WW=0 / =all force the narrow / the wide kernel.
+    static const char* ww_env = getenv("ADV_STFT_WW");
+    static const bool ww_on = !(ww_env && ww_env[0] == '0'), ww_all = ww_env && ww_env[0] == 'a';
+    if (ww_on && (mag || phase || ww_all) && p->d.n_fft == 512 && !(flags & ADV_STFT_ZERO_PAD))
+        return p->d.rect_full ? launch_stft_ww<true>(p, wav, wav_stride, batch, X, mag, phase, s)
+                              : launch_stft_ww<false>(p, wav, wav_stride, batch, X, mag, phase, s);
     if (p->d.n_fft == 512)
         return p->d.rect_full ? launch_stft_w<512, true>(p, wav, wav_stride, batch, X, mag, phase, flags, s)
                               : launch_stft_w<512, false>(p, wav, wav_stride, batch, X, mag, phase, flags, s);
