@@ -323,6 +323,29 @@ def main():
     t_stft3 = graph_time(lambda i: ops.stft(pool[i].wav, **kw), reps)
     t_istft = graph_time(lambda i: ops.istft(specs[i], length=N, **kw), reps)
     del specs
+    # the same two kernels at 256 clips per launch (BASELINE configs[2]'s batch): fixed launch / ramp / tail costs
+    # amortised, 4 rotating sets (0.26 GB of waveforms, 0.84 GB of spectra) > L2
+    big = None
+    try:
+        BB = 256
+        wb = [0.1 * torch.randn(BB, N, generator=gen, device="cuda") for _ in range(4)]
+        sb_ = [ops.stft(w_, want_mag=False, want_phase=False, **kw)[0] for w_ in wb]
+
+        def big_time(fn):
+            fn(0)
+            torch.cuda.synchronize()
+            return time_loop(lambda i: fn(i % 4), 40) / 40
+
+        tb_s = big_time(lambda i: ops.stft(wb[i], want_mag=False, want_phase=False, **kw))
+        tb_3 = big_time(lambda i: ops.stft(wb[i], **kw))
+        tb_i = big_time(lambda i: ops.istft(sb_[i], length=N, **kw))
+        big = {"clips_per_launch": BB,
+               "stft_X": {"us": tb_s * 1e6, "frac": BYTES_STFT * BB / tb_s / 1e9 / peak},
+               "stft_X_mag_phase": {"us": tb_3 * 1e6, "frac": (BYTES_STFT + 8 * F * T) * BB / tb_3 / 1e9 / peak},
+               "istft": {"us": tb_i * 1e6, "frac": BYTES_ISTFT * BB / tb_i / 1e9 / peak}}
+        del wb, sb_
+    except Exception as e:
+        big = {"error": repr(e)[:200]}
     # mel front-end of the vocoder path (hifigan.py:163-178 geometry: n_fft 1024, hop 256, hann 1024, 80 mels):
     # STFT + 3xTF32 tcgen05 filterbank projection with the log epilogue, 64 clips per call
     mel_k = None
@@ -399,10 +422,21 @@ def main():
                "sample": f"{reps_c} x {BATCH} clips of the same workload, torch {torch.__version__} CPU fp32, "
                          f"os.cpu_count()={os.cpu_count()}"}
 
-    traffic = None
+    traffic, issue = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("explain_kernel_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic = tj.get("explain_kernel_bytes_per_launch")
+        # what actually bounds the fused kernel: instruction issue (one warp-instruction per scheduler per cycle).
+        # Instruction count per launch from the committed ncu capture, time measured live, clock = the sampled one.
+        wi = tj.get("explain_kernel_warp_inst_per_launch")
+        mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        if wi:
+            n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+            peak_i = n_sm * 4 * mhz * 1e6
+            issue = {"warp_inst_per_launch": wi, "achieved_ginst_s": wi / t_k / 1e9, "peak_ginst_s": peak_i / 1e9,
+                     "frac": wi / t_k / peak_i, "note": "smsp__inst_executed.sum (ncu, profiles/traffic.json) / live "
+                     "kernel time vs SMs x 4 schedulers x sampled SM clock"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps,
@@ -419,7 +453,8 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "explain_p512_kernel<log1p,rect> (fused STFT + mask / 1-mask + 2 x iSTFT, persistent)",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                     "peak_source": peak_src, "bytes_per_launch": BYTES_EXPLAIN * BATCH, "us_per_launch": t_k * 1e6},
+                     "peak_source": peak_src, "bytes_per_launch": BYTES_EXPLAIN * BATCH, "us_per_launch": t_k * 1e6,
+                     "issue": issue},
         "kernels": {
             "stft_X": {"GBps": BYTES_STFT * BATCH / t_stft / 1e9, "frac": BYTES_STFT * BATCH / t_stft / 1e9 / peak,
                        "us": t_stft * 1e6},
@@ -428,6 +463,7 @@ def main():
             "istft": {"GBps": BYTES_ISTFT * BATCH / t_istft / 1e9, "frac": BYTES_ISTFT * BATCH / t_istft / 1e9 / peak,
                       "us": t_istft * 1e6},
             "mel_frontend": mel_k,
+            "batch256": big,
         },
         "vocoder": voc,
         "cpu_baseline": cpu,

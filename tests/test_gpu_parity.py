@@ -67,9 +67,12 @@ def test_stft_matches_oracle(ops, n_fft, hop, win, n, B):
     assert relerr(torch.view_as_real(X), torch.view_as_real(Xr)) < TOL
     assert relerr(mag, magr) < TOL
     assert phase_err(ph, phr, magr) < 1e-3
-    # X-only variant writes the same spectrum
+    # X-only variant: same spectrum (n_fft 512 routes the two variants to different kernels - narrow units for X
+    # only, wide units with magnitude / phase - so equality holds up to fp32 round-off, not bit for bit)
     X2, m2, p2 = ops.stft(wav, n_fft, hop, win, want_mag=False, want_phase=False)
-    assert m2 is None and p2 is None and torch.equal(X2, X)
+    assert m2 is None and p2 is None
+    assert relerr(torch.view_as_real(X2), torch.view_as_real(Xr)) < TOL
+    assert relerr(torch.view_as_real(X2), torch.view_as_real(X)) < 1e-5
 
 
 @pytest.mark.parametrize("n_fft,hop,win,n,B", GEOMS)
