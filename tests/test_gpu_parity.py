@@ -47,6 +47,10 @@ GEOMS = [
     (512, 37, 512, 3000, 1),      # tiny odd hop: 14 overlap phases
     (1024, 512, 1024, 9000, 1),
     (512, 512, 512, 4096, 1),     # no overlap at all
+    (512, 256, 512, 4000, 3),     # wide-unit kernels, generic strip path (hop != 160), 50% overlap
+    (512, 64, 512, 2048, 2),      # wide-unit kernels, 8 frames per sample
+    (512, 160, 320, 4800, 2),     # wide-unit kernels, window support inside the frame (wlo = 96)
+    (512, 160, 512, 480, 1),      # a single tile with two live frame pairs; most units idle
 ]
 
 
