@@ -346,6 +346,32 @@ def main():
         del wb, sb_
     except Exception as e:
         big = {"error": repr(e)[:200]}
+    # the reference's DEFAULT geometry (AudioProcessor(): n_fft 1024, hop 322, win 644, 5 s clips) through the same
+    # entry points: these still run the first-generation n_fft 1024 kernels
+    refdef = None
+    try:
+        kw1 = dict(n_fft=1024, hop=322, win_length=644)
+        n1, F1, T1 = 80000, 513, 1 + 80000 // 322
+        w1 = [0.1 * torch.randn(BATCH, n1, generator=gen, device="cuda") for _ in range(8)]
+        m1 = [torch.rand(BATCH, F1, T1, generator=gen, device="cuda") for _ in range(8)]
+        s1 = [ops.stft(w_, want_mag=False, want_phase=False, **kw1)[0] for w_ in w1]
+
+        def t8(fn):
+            fn(0)
+            torch.cuda.synchronize()
+            return time_loop(lambda i: fn(i % 8), 40) / 40
+
+        t1e = t8(lambda i: ops.explain(w1[i], m1[i], length=n1, **kw1))
+        t1s = t8(lambda i: ops.stft(w1[i], **kw1))
+        t1i = t8(lambda i: ops.istft(s1[i], length=n1, **kw1))
+        by_e, by_s, by_i = 4 * n1 + 4 * F1 * T1 + 8 * n1, 4 * n1 + 16 * F1 * T1, 8 * F1 * T1 + 4 * n1
+        refdef = {"geometry": "64 x 5 s clips, n_fft 1024 / hop 322 / win 644",
+                  "explain": {"us": t1e * 1e6, "frac": by_e * BATCH / t1e / 1e9 / peak, "clips_per_s": BATCH / t1e},
+                  "stft_X_mag_phase": {"us": t1s * 1e6, "frac": by_s * BATCH / t1s / 1e9 / peak},
+                  "istft": {"us": t1i * 1e6, "frac": by_i * BATCH / t1i / 1e9 / peak}}
+        del w1, m1, s1
+    except Exception as e:
+        refdef = {"error": repr(e)[:200]}
     # mel front-end of the vocoder path (hifigan.py:163-178 geometry: n_fft 1024, hop 256, hann 1024, 80 mels):
     # STFT + 3xTF32 tcgen05 filterbank projection with the log epilogue, 64 clips per call
     mel_k = None
@@ -464,6 +490,7 @@ def main():
                       "us": t_istft * 1e6},
             "mel_frontend": mel_k,
             "batch256": big,
+            "reference_default_geometry": refdef,
         },
         "vocoder": voc,
         "cpu_baseline": cpu,

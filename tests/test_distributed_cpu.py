@@ -54,3 +54,15 @@ def test_shard_bounds_cover(pkg):
             spans = [pkg.distributed.shard_bounds(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_chunk_bounds_cover_whole_chunks(pkg):
+    """configs[3] shards whole chunks: every chunk is owned by exactly one rank, also with more ranks than chunks"""
+    D = pkg.distributed
+    for n_chunks in (0, 1, 5, 98):
+        for w in (1, 2, 4, 8):
+            owned = []
+            for r in range(w):
+                lo, hi = D.chunk_bounds(n_chunks, r, w)
+                owned += list(range(lo, hi))
+            assert owned == list(range(n_chunks))
