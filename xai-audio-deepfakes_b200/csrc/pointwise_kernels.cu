@@ -192,27 +192,65 @@ mask_apply_kernel(const float* __restrict__ mag, const float* __restrict__ phase
     const int b = blockIdx.z, f0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     const float* mrow = mask + (size_t)b * Fm * Tm;
-    for (int r = ty; r < 32; r += 8) {
-        const int f = f0 + r, t = t0 + tx;
-        tile[r][tx] = (f < Fm && t < Tm) ? __ldg(mrow + (size_t)f * Tm + t) : 0.0f;
+    // every load of the thread (4 mask-tile elements, 4 magnitudes, 4 phases) is issued before the first use: one
+    // memory latency per CTA instead of one per element
+    float mreg[4], areg[4], preg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = ty + 8 * j;
+        const int fm = f0 + r, tm = t0 + tx;
+        mreg[j] = (fm < Fm && tm < Tm) ? __ldg(mrow + (size_t)fm * Tm + tm) : 0.0f;
+        const int t = t0 + r, f = f0 + tx;
+        const bool ok = t < T && f < F;
+        const size_t idx = ((size_t)b * T + (ok ? t : 0)) * F + (ok ? f : 0);
+        areg[j] = ok ? __ldg(mag + idx) : 0.0f;
+        preg[j] = ok ? __ldg(phase + idx) : 0.0f;
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tile[ty + 8 * j][tx] = mreg[j];
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = ty + 8 * j;
         const int t = t0 + r, f = f0 + tx;
         if (t >= T || f >= F) continue;
         const size_t idx = ((size_t)b * T + t) * F + f;
         const float m = tile[tx][r];
-        const float a = __ldg(mag + idx);
+        const float a = areg[j];
         float s, c;
-        sincosf(__ldg(phase + idx), &s, &c);  // exp(1j*phase)
+        // exp(1j*phase): angles come from atan2, |phase| <= pi, where the MUFU forms are accurate to 2^-21 absolute;
+        // anything else (callers may pass unwrapped phases) takes libm's range reduction
+        const float ph = preg[j];
+        if (fabsf(ph) <= 3.2f) __sincosf(ph, &s, &c);
+        else sincosf(ph, &s, &c);
         float ar, ai;
         if (MODE == ADV_MASK_LINEAR) {
             ar = m * a;
             ai = (1.0f - m) * a;
         } else {
-            const float lm = log1pf(a);
-            ar = expm1f(m * lm);
-            ai = expm1f((1.0f - m) * lm);
+            // the fused kernel's gains (transform_kernels.cu mask_gains): (1+a)^m - 1 through MUFU lg2 / ex2 for a >= 1/16,
+            // Taylor series below; the complementary term needs no second exponential:
+            // expm1((1-m) log1p a) = (1+a)/(1+er) - 1 = (a - er)/(1 + er).  libm's log1pf + 2 x expm1f made this kernel
+            // instruction-bound (58.6 us for 64 clips = 48 % of the HBM roofline)
+            if (a >= 0.0625f) {
+                float lg, ex;
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(1.0f + a));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(m * lg));
+                ar = ex - 1.0f;
+            } else {
+                float L = fmaf(a, -1.0f / 6.0f, 0.2f);
+                L = fmaf(-a, L, 0.25f);
+                L = fmaf(-a, L, 1.0f / 3.0f);
+                L = fmaf(-a, L, 0.5f);
+                L = fmaf(-a, L, 1.0f);
+                const float y = m * L * a;
+                float e = fmaf(y, 1.0f / 120.0f, 1.0f / 24.0f);
+                e = fmaf(y, e, 1.0f / 6.0f);
+                e = fmaf(y, e, 0.5f);
+                e = fmaf(y, e, 1.0f);
+                ar = y * e;
+            }
+            ai = __fdividef(a - ar, 1.0f + ar);
         }
         rel[idx] = make_float2(ar * c, ar * s);
         irr[idx] = make_float2(ai * c, ai * s);
