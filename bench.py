@@ -206,6 +206,9 @@ def main():
 
     pkg = importlib.import_module("xai-audio-deepfakes_b200")
     pkg._lib.build()
+    # one process per GPU: keep each rank (and the pinned host buffers of the end-to-end leg) on the cores next to its
+    # GPU.  Single-process runs stay unbound: the CPU baseline wants every host core.
+    affinity = pkg.distributed.bind_host_to_gpu(local) if world > 1 and os.environ.get("ADV_NO_BIND") is None else None
     ops = pkg.ops
     from importlib import import_module
     pipeline = import_module("xai-audio-deepfakes_b200.pipeline")
@@ -473,7 +476,8 @@ def main():
                                "(classifier logits synthetic; SSL model is the reference's torch module, not timed)",
                    "batch_per_gpu": BATCH, "parallelism": f"dp{world}",
                    "l2": f"{POOL} rotating buffer sets (1.2 GB) > 126 MB L2", "cuda_graph": True,
-                   "schedule": args.schedule, "streams": ns},
+                   "schedule": args.schedule, "streams": ns,
+                   "host_affinity": (f"{len(affinity)} cpus local to the GPU (NVML)" if affinity else "unbound")},
         "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": hp.h2d_bytes,
                 "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps},
         "gpu_launches": launches,

@@ -32,6 +32,29 @@ def shard_bounds(n: int, r: int | None = None, w: int | None = None):
     return lo, min(n, lo + per)
 
 
+def bind_host_to_gpu(local_rank: int):
+    """Pin the calling process to the CPU cores NVML reports as local to GPU ``local_rank`` (same NUMA node / PCIe root),
+    so that the pinned host buffers it allocates afterwards are first-touched next to the GPU that reads them.  With
+    one process per GPU on an 8-GPU box this is what keeps the host-fed path (``pipeline.HostFedPipeline``) from
+    funnelling every H2D copy through one socket's memory.  Returns the CPU list, or None when NVML / the affinity
+    call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = local_rank
+        if vis:  # NVML enumerates physical devices: map the local rank through the visibility list when it is numeric
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                index = int(ids[local_rank])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def allreduce_sums(sums: torch.Tensor) -> torch.Tensor:
     """In-place SUM all-reduce of the six metric partial sums (no-op on a single process)."""
     if initialized() and world_size() > 1:
