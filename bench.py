@@ -231,8 +231,10 @@ def main():
         p.logits.copy_(2.0 * torch.randn(3, BATCH, generator=gen, device="cuda"))
     ns = max(1, min(args.streams, POOL))
     streams = [torch.cuda.Stream() for _ in range(ns)]
+    burst_us = None
     if pooled:
         pp.capture()
+        burst_us = round(pp.burst_us_per_step(), 1)  # 96 steps from a cool GPU, before the sustained timed region
 
     def step(i):  # 3 launches of ours; metric sums accumulate inside lmac_reduce.
         j = i % POOL
@@ -477,6 +479,7 @@ def main():
                    "batch_per_gpu": BATCH, "parallelism": f"dp{world}",
                    "l2": f"{POOL} rotating buffer sets (1.2 GB) > 126 MB L2", "cuda_graph": True,
                    "schedule": args.schedule, "streams": ns,
+                   "burst_us_per_step": burst_us,
                    "host_affinity": (f"{len(affinity)} cpus local to the GPU (NVML)" if affinity else "unbound")},
         "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": hp.h2d_bytes,
                 "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps},

@@ -136,6 +136,27 @@ class PipelinedPool:
         for p in self.pipes:
             p.sums.zero_()
 
+    def burst_us_per_step(self, replays=6):
+        """Per-step time of a short burst of replays (CUDA events), microseconds.  Measured on B200: bursts of ~100
+        steps run at 77 - 78 us per step on every instantiation of the graph, while runs of thousands of steps settle
+        at 81 - 88 us (occasionally > 100) with ``sw_power_cap`` reported - the fully overlapped schedule leaves no idle
+        tails, draws more power than the explain kernel alone (which stays at 86.5 us per launch hot or cold) and is
+        what the board's power management throttles.  Reported next to the sustained figure by ``bench.py``."""
+        if self.graph is None:
+            self.capture()
+        for _ in range(2):
+            self.graph.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(replays):
+            self.graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        for p in self.pipes:
+            p.sums.zero_()
+        return a.elapsed_time(b) * 1e3 / (replays * len(self.pipes))
+
     def replay(self):
         """``len(self.pipes)`` steps on the current stream (asynchronous)."""
         if self.graph is None:
