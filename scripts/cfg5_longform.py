@@ -68,8 +68,30 @@ try:
     peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
-t_td = timed(lambda i: ops.td_mask(wavs[i % POOL], attrs[i % POOL], want_mask=False))
-t_st = timed(lambda i: ap.compute_stft(wavs[i % POOL]))
+def graph_timed(fn, reps=10):
+    """device time per call: POOL calls captured in one CUDA graph (no host launch overhead between kernels)"""
+    fn(0)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    keep = []
+    with torch.cuda.graph(gr):
+        for i in range(POOL):
+            keep.append(fn(i))
+    for _ in range(2):
+        gr.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        gr.replay()
+    b.record()
+    torch.cuda.synchronize()
+    del keep
+    return a.elapsed_time(b) * 1e-3 / (reps * POOL)
+
+
+t_td = graph_timed(lambda i: ops.td_mask(wavs[i % POOL], attrs[i % POOL], want_mask=False))
+t_st = graph_timed(lambda i: ap.compute_stft(wavs[i % POOL]))
 if world > 1:
     dist.barrier()
 t_all = timed(step)

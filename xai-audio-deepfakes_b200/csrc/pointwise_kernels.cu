@@ -7,6 +7,7 @@
 //   band_swap             - complex row replacement            train_logReg_swapping.py:64-75, hifigan.py:206-214
 // All are single-pass streaming kernels: coalesced 128-bit accesses where alignment allows, fp64
 // partial sums reduced in a fixed order (bit-reproducible for a given launch shape).
+#include <cstdlib>
 #include "adv_internal.cuh"
 
 namespace adv {
@@ -284,6 +285,66 @@ td_mask_kernel(const float* __restrict__ wave, const float* __restrict__ attr, i
         if (mask_out != nullptr) mask_out[base + i] = m;
         rel[base + i] = w * m;
         irr[base + i] = w * (1.0f - m);
+    }
+}
+
+// 128-bit forms (n % 4 == 0, 16-byte aligned rows): a thread's 8 loads per array are all in flight at once
+__global__ void __launch_bounds__(kPwThreads)
+rowmax_abs4_kernel(const float* __restrict__ attr, int n, float* __restrict__ rowmax) {
+    const int b = blockIdx.y;
+    const float4* row = reinterpret_cast<const float4*>(attr + (size_t)b * n);
+    const int lo = blockIdx.x * (kRowChunk / 4), hi = min(n / 4, lo + kRowChunk / 4);
+    constexpr int kPer = kRowChunk / 4 / kPwThreads;
+    float4 v[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int i = lo + threadIdx.x + j * kPwThreads;
+        v[j] = i < hi ? __ldg(row + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float m = 0.f;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j)
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v[j].x), fabsf(v[j].y))), fmaxf(fabsf(v[j].z), fabsf(v[j].w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(rowmax + b), __float_as_int(m));
+}
+__global__ void __launch_bounds__(kPwThreads)
+td_mask4_kernel(const float* __restrict__ wave, const float* __restrict__ attr, int n,
+                const float* __restrict__ rowmax, float* __restrict__ mask_out, float* __restrict__ rel,
+                float* __restrict__ irr) {
+    const int b = blockIdx.y;
+    const float den = rowmax[b] + 1e-8f;
+    const size_t base = (size_t)b * n / 4;
+    const float4* a4 = reinterpret_cast<const float4*>(attr) + base;
+    const float4* w4 = reinterpret_cast<const float4*>(wave) + base;
+    float4* r4 = reinterpret_cast<float4*>(rel) + base;
+    float4* i4 = reinterpret_cast<float4*>(irr) + base;
+    float4* m4 = mask_out ? reinterpret_cast<float4*>(mask_out) + base : nullptr;
+    const int lo = blockIdx.x * (kRowChunk / 4), hi = min(n / 4, lo + kRowChunk / 4);
+    constexpr int kPer = kRowChunk / 4 / kPwThreads / 2;  // two rounds of 4 + 4 loads: 32 data registers in flight
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float4 av[kPer], wv[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int i = lo + threadIdx.x + (h * kPer + j) * kPwThreads;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            av[j] = i < hi ? __ldg(a4 + i) : z;
+            wv[j] = i < hi ? __ldg(w4 + i) : z;
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int i = lo + threadIdx.x + (h * kPer + j) * kPwThreads;
+            if (i >= hi) continue;
+            // (the reference divides: abs(attr) / (max + 1e-8), captum_saliency.py:139-140 - kept as an IEEE division)
+            const float4 m = make_float4(fabsf(av[j].x) / den, fabsf(av[j].y) / den, fabsf(av[j].z) / den,
+                                         fabsf(av[j].w) / den);
+            const float4 w = wv[j];
+            if (m4 != nullptr) m4[i] = m;
+            r4[i] = make_float4(w.x * m.x, w.y * m.y, w.z * m.z, w.w * m.w);
+            i4[i] = make_float4(w.x * (1.0f - m.x), w.y * (1.0f - m.y), w.z * (1.0f - m.z), w.w * (1.0f - m.w));
+        }
     }
 }
 
@@ -624,8 +685,16 @@ int adv_td_mask(const float* wave, const float* attr, int batch, int n, float* m
     cudaStream_t s = (cudaStream_t)stream;
     ADV_CUDA_CHECK(cudaMemsetAsync(rowmax, 0, sizeof(float) * batch, s));
     const int chunks = (n + kRowChunk - 1) / kRowChunk;
-    rowmax_abs_kernel<<<dim3(chunks, batch), kPwThreads, 0, s>>>(attr, n, rowmax);
-    td_mask_kernel<<<dim3(chunks, batch), kPwThreads, 0, s>>>(wave, attr, n, rowmax, mask_out, rel, irr);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(wave) | reinterpret_cast<uintptr_t>(attr) | reinterpret_cast<uintptr_t>(rel) |
+                         reinterpret_cast<uintptr_t>(irr) | reinterpret_cast<uintptr_t>(mask_out);
+    static const bool scalar = getenv("ADV_TD_MASK_SCALAR") != nullptr;
+    if (!scalar && n % 4 == 0 && al % 16 == 0) {
+        rowmax_abs4_kernel<<<dim3(chunks, batch), kPwThreads, 0, s>>>(attr, n, rowmax);
+        td_mask4_kernel<<<dim3(chunks, batch), kPwThreads, 0, s>>>(wave, attr, n, rowmax, mask_out, rel, irr);
+    } else {
+        rowmax_abs_kernel<<<dim3(chunks, batch), kPwThreads, 0, s>>>(attr, n, rowmax);
+        td_mask_kernel<<<dim3(chunks, batch), kPwThreads, 0, s>>>(wave, attr, n, rowmax, mask_out, rel, irr);
+    }
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }
