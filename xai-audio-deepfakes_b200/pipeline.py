@@ -137,11 +137,9 @@ class PipelinedPool:
             p.sums.zero_()
 
     def burst_us_per_step(self, replays=6):
-        """Per-step time of a short burst of replays (CUDA events), microseconds.  Measured on B200: bursts of ~100
-        steps run at 77 - 78 us per step on every instantiation of the graph, while runs of thousands of steps settle
-        at 81 - 88 us (occasionally > 100) with ``sw_power_cap`` reported - the fully overlapped schedule leaves no idle
-        tails, draws more power than the explain kernel alone (which stays at 86.5 us per launch hot or cold) and is
-        what the board's power management throttles.  Reported next to the sustained figure by ``bench.py``."""
+        """Per-step time of a short burst of replays (CUDA events), microseconds: 77 - 78 us on B200, and the same over
+        16 000 steps (``scripts/pool_burst.py``).  ``bench.py`` prints it next to the sustained figure as a cross-check
+        that nothing but the steps sits in its timed region."""
         if self.graph is None:
             self.capture()
         for _ in range(2):
