@@ -71,6 +71,9 @@ def statements_on_lines(path, func_name, line_ranges):
 
 
 def import_reference_audioprocessor():
+    if "audioprocessor" in sys.modules and "classifier_embedder" in sys.modules:
+        return sys.modules["audioprocessor"], sys.modules["classifier_embedder"]
+    from transformers import Wav2Vec2Model  # noqa: F401  (before the stub: transformers probes `accelerate` on import)
     acc = types.ModuleType("accelerate")
 
     class Accelerator:  # audioprocessor.py:15-16 only reads .device
@@ -246,6 +249,7 @@ def main():
                         mel=c2n(ap.mel_transform(wav)), fb=c2n(ap.mel_transform.mel_scale.fb),
                         params=np.array([4000, 1024, 322, 644, 80]))
     golden_align()
+    golden_cfg1()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("golden bytes:", total)
 
@@ -269,9 +273,115 @@ def golden_align():
     np.savez_compressed(os.path.join(OUT, "align.npz"), **out)
 
 
+def golden_cfg1():
+    """---- 10. BASELINE configs[0] / SURVEY 8(d) cfg-1: the 4 bundled wavs through the reference's own evaluation loop.
+
+    ``AudioProcessor()`` defaults (5 s, n_fft 1024 / hop 322 / win 644); classifier = seeded random-init 9-layer
+    XLS-R-2B-shaped ``Wav2Vec2Model`` (seed 0) behind the reference's ``extract_features`` + the lifted ``TorchLogReg``
+    with ``coef ~ N(0, 0.05^2)``, ``intercept = 0`` (seed 0); masks: (a) the lifted reference ``UNet`` with seeded weights
+    (``addvisor.seeded_init(net, 0)``: per-key generators, so the product's re-declared UNet gets the same weights) on
+    ``mag[:, :512, :248]``, zero-extended to 513 x 249, and (b) a full-size ``sigmoid(N(0, 1.5^2))`` mask (seed 0).
+    The loop body is the reference's: LMAC_metrics.py:130-131,136-157,160-162 exec'd unchanged; the five means come from
+    the lifted ``compute_*``.  Stored: the PCM of the wavs, every 8th sample of the masked waveforms + float64 sums,
+    a strided sample of the masks / spectrum, the per-clip probabilities and the five means, and the wall time of the
+    reference CPU path in this container."""
+    import importlib
+    import time
+    ap_mod, ce = import_reference_audioprocessor()
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    pkg = importlib.import_module("xai-audio-deepfakes_b200")
+    names = sorted(f[:-4] for f in os.listdir(os.path.join(REF, "audio_samples")) if f.endswith(".wav"))
+    pcm = []
+    for nm in names:
+        with wavmod.open(os.path.join(REF, "audio_samples", nm + ".wav"), "rb") as f:
+            assert f.getsampwidth() == 2 and f.getnchannels() == 1 and f.getframerate() == 16000
+            pcm.append(np.frombuffer(f.readframes(f.getnframes()), dtype="<i2").copy())
+    assert all(len(x) == 80000 for x in pcm)
+    pcm = np.stack(pcm)
+    wav = torch.from_numpy(pcm.astype(np.float32) / 32768.0)
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    ssl = pkg.classifier_embedder.random_init_wav2vec2(seed=0)
+    ap_mod.wav2vec2 = ssl                                   # the module global of audioprocessor.py:17-18
+    g0 = torch.Generator().manual_seed(0)
+    coef = 0.05 * torch.randn(1, 1920, generator=g0)
+    icpt = torch.zeros(1)
+    lenv = dict(torch=torch, nn=torch.nn, classifier=types.SimpleNamespace(coef_=c2n(coef), intercept_=c2n(icpt)))
+    lift(os.path.join(REF, "classifier_embedder.py"), ["TorchLogReg"], lenv)
+    torch_log_reg = lenv["TorchLogReg"]()
+    uenv = dict(torch=torch, nn=torch.nn)
+    lift(os.path.join(REF, "addvisor.py"), ["ConvBlock", "UNet"], uenv)
+    net = pkg.addvisor.seeded_init(uenv["UNet"](), 0).eval()
+    menv = dict(torch=torch, F=torch.nn.functional, device=torch.device("cpu"), eps=1e-10)
+    lift(os.path.join(REF, "LMAC_metrics.py"),
+         ["compute_fidelity", "get_score_for_predicted_class", "compute_faithfulness",
+          "compute_AD", "compute_AI", "compute_AG"], menv)
+    body, lines = statements_on_lines(os.path.join(REF, "LMAC_metrics.py"), "run_addvisor_metrics",
+                                      [(130, 131), (136, 157)])
+    tail, tl = statements_on_lines(os.path.join(REF, "LMAC_metrics.py"), "run_addvisor_metrics", [(160, 162)])
+    print("cfg1: LMAC_metrics lines", lines, tl)
+
+    ap = ap_mod.AudioProcessor()
+    out = {"names": np.array(names), "pcm": pcm, "coef": c2n(coef), "intercept": c2n(icpt),
+           "params": np.array([16000, 1024, 322, 644, 5])}
+    with torch.no_grad():
+        X, magnitude, phase = ap.compute_stft(wav)                    # collate_fn, LMAC_metrics.py:112
+        t0 = time.perf_counter()
+        features = ap.extract_features(wav)                           # collate_fn, LMAC_metrics.py:113
+        t_feat = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        m_unet = net(magnitude[:, :512, :248].unsqueeze(1))[:, 0]     # UNet call shape of addvisor.py:62-84
+        t_unet = time.perf_counter() - t0
+        masks = {"unet": torch.zeros_like(magnitude), "full": torch.sigmoid(1.5 * torch.randn(magnitude.shape, generator=g0))}
+        masks["unet"][:, :512, :248] = m_unet
+        out["X_s"] = c2n(X[:, ::8, ::8])
+        out["mask_unet_s"] = c2n(m_unet[:, ::4, ::4])
+        for tag, mask in masks.items():
+            env = dict(menv)
+            env.update(audio_processor=ap, torch_log_reg=torch_log_reg, mask=mask, features=features,
+                       magnitude=magnitude.clone(), phase=phase.clone(), theta_out=[], predictions=[],
+                       masked_predictions=[])
+            t0 = time.perf_counter()
+            exec(body, env)
+            t_loop = time.perf_counter() - t0
+            exec(tail, env)
+            # transform-only time of the same lines (no SSL forward): what the B200 path replaces
+            t0 = time.perf_counter()
+            for _ in range(3):
+                lm = torch.log1p(magnitude)
+                ap.compute_invert_stft(torch.expm1(mask * lm) * torch.exp(1j * phase))
+                ap.compute_invert_stft(torch.expm1((1 - mask) * lm) * torch.exp(1j * phase))
+            t_tr = (time.perf_counter() - t0) / 3
+            p, th, q = env["predictions"], env["theta_out"], env["masked_predictions"]
+            out[f"{tag}_p"], out[f"{tag}_theta"], out[f"{tag}_q"] = c2n(p), c2n(th), c2n(q)
+            out[f"{tag}_rel_s"] = c2n(env["istft_waveforms"][:, ::8])
+            out[f"{tag}_irr_s"] = c2n(env["istft_irr_waveform"][:, ::8])
+            out[f"{tag}_sums"] = np.stack([c2n(env[k].double().sum(dim=1)) for k in ("istft_waveforms", "istft_irr_waveform")] +
+                                          [c2n((env[k].double() ** 2).sum(dim=1)) for k in ("istft_waveforms", "istft_irr_waveform")])
+            means = [menv["compute_faithfulness"](p, q).mean().item(), menv["compute_fidelity"](th, p).float().mean().item(),
+                     menv["compute_AD"](th, p).mean().item(), menv["compute_AI"](th, p).mean().item(),
+                     menv["compute_AG"](th, p).mean().item()]
+            out[f"{tag}_means"] = np.array(means)
+            out[f"{tag}_seconds"] = np.array([t_loop, t_tr])
+            pc = menv["get_score_for_predicted_class"](p.squeeze(1))
+            oc = menv["get_score_for_predicted_class"](th.squeeze(1))
+            margin = min(float((p - 0.5).abs().min()), float((th - 0.5).abs().min()), float((oc - pc).abs().min()))
+            out[f"{tag}_margin"] = np.array(margin)
+            print(f"cfg1[{tag}] p={p.flatten().tolist()} theta={th.flatten().tolist()} q={q.flatten().tolist()}")
+            print(f"cfg1[{tag}] FF/Fid/AD/AI/AG = {means}  flip margin {margin:.2e}  loop {t_loop:.1f} s, transforms {t_tr*1e3:.1f} ms")
+        out["seconds_features_unet"] = np.array([t_feat, t_unet])
+    np.savez_compressed(os.path.join(OUT, "cfg1_wavs.npz"), **out)
+    print("cfg1_wavs.npz bytes:", os.path.getsize(os.path.join(OUT, "cfg1_wavs.npz")))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--only-align":   # adds one fixture without touching the others
         os.makedirs(OUT, exist_ok=True)
         golden_align()
+    elif len(sys.argv) > 1 and sys.argv[1] == "--only-cfg1":
+        os.makedirs(OUT, exist_ok=True)
+        golden_cfg1()
     else:
         main()

@@ -7,6 +7,8 @@ saliency masks).  ``ops`` is the tensor-level wrapper over the C ABI in include/
 
 The directory name contains a hyphen; import it with
 ``importlib.import_module("xai-audio-deepfakes_b200")`` or through the root-level ``adv_b200`` alias.
+Reference scripts keep their own import lines (``from audioprocessor import AudioProcessor``) by
+putting the repo's ``dropin/`` directory on ``sys.path``.
 """
 from . import _lib  # noqa: F401  (does not load the .so until first use)
 
@@ -16,6 +18,6 @@ __version__ = "0.1.0"
 def __getattr__(name):
     import importlib
     if name in ("ops", "audioprocessor", "addvisor", "LMAC_metrics", "classifier_embedder", "distributed",
-                "mel", "hifigan", "captum_saliency"):
+                "mel", "hifigan", "captum_saliency", "pipeline", "loss_function"):
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -79,3 +79,32 @@ def load_checkpoint(model, state_dict):
         state_dict = {k.replace("module.", ""): v for k, v in state_dict.items()}
     model.load_state_dict(state_dict)
     return model
+
+
+def seeded_init(model, seed=0):
+    """Fill every conv / transposed-conv weight and bias of ``model`` from a generator seeded per state_dict KEY
+    (He-scaled normal weights, N(0, 0.01^2) biases; BatchNorm keeps its identity affine and unit running stats).
+    The result depends only on the key names and shapes, not on module construction order, so the reference's
+    ``UNet`` and this module's re-declaration get bit-identical weights from the same seed (there is no trained
+    checkpoint offline; BASELINE configs[0] uses ``seed=0``)."""
+    import zlib
+    sd = model.state_dict()
+    with torch.no_grad():
+        for key in sorted(sd):
+            t = sd[key]
+            if not t.is_floating_point() or "running_" in key or t.dim() == 0:
+                continue
+            g = torch.Generator().manual_seed((int(seed) << 20) ^ zlib.crc32(key.encode()))
+            if t.dim() >= 3:     # Conv2d / ConvTranspose2d weight
+                fan_in = t[0].numel() if t.dim() == 4 else t.numel()
+                t.copy_(torch.randn(t.shape, generator=g) * (2.0 / max(fan_in, 1)) ** 0.5)
+            elif key.endswith(".bias") and not _is_bn(model, key):
+                t.copy_(0.01 * torch.randn(t.shape, generator=g))
+    return model
+
+
+def _is_bn(model, key):
+    mod = model
+    for part in key.split(".")[:-1]:
+        mod = getattr(mod, part) if not part.isdigit() else mod[int(part)]
+    return isinstance(mod, nn.BatchNorm2d)
