@@ -39,6 +39,10 @@ typedef enum adv_mask_mode {
     ADV_MASK_LOG1P = 0, /* LMAC_metrics.py:136-143,151-153: expm1(m * log1p(|X|)) * exp(i*phase) */
     ADV_MASK_LINEAR = 1 /* loss_function.py:36-45:          (m * |X|) * exp(i*phase)            */
 } adv_mask_mode;
+/* OR-ed into `mode`: bins outside a mask smaller than the spectrum ([Fm,Tm] < [F,T]) are removed from BOTH outputs,
+ * which is what the reference's crop of magnitude and phase to the mask's extent amounts to (LMAC_metrics.py:136-139,
+ * loss_function.py:36-41).  Without the flag the mask is zero-extended: out-of-mask bins go to the masked-out branch. */
+enum { ADV_MASK_DROP_OUTSIDE = 0x100 };
 
 typedef struct adv_plan adv_plan;
 typedef struct adv_c64 { float re, im; } adv_c64;
@@ -95,7 +99,8 @@ int adv_istft(const adv_plan* plan, const adv_c64* X, int64_t sb, int64_t st, in
 /* ---- fused explanation resynthesis: the LMAC_metrics.py:125-158 loop body without the classifier ------
  * wave + mask -> STFT -> mask / (1-mask) applied to the (log-)magnitude with the original phase ->
  * two iSTFTs.  Spectra never leave the SM.  mask: dev float [B][Fm][Tm] contiguous, Fm <= F, Tm <= T,
- * cells outside the mask count as mask = 0.  rel / irr: dev float [B][n_out].
+ * cells outside the mask count as mask = 0 (or are dropped from both outputs: mode | ADV_MASK_DROP_OUTSIDE).
+ * rel / irr: dev float [B][n_out].
  * stats (nullable): dev double [B][tiles][4] = per-tile (sum rel, sumsq rel, sum irr, sumsq irr). */
 int adv_explain(const adv_plan* plan, const float* wav, int64_t wav_stride, const float* mask, int Fm, int Tm,
                 int mode, int batch, float* rel, float* irr, double* stats, void* stream);

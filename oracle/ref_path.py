@@ -119,15 +119,27 @@ def mask_head(y1, weight, bias):
     return torch.sigmoid(F.conv2d(y1, weight, bias))
 
 
-def explain(wave, mask, *, mode="log1p", normalize=False, **cfg):
+def explain(wave, mask, *, mode="log1p", normalize=False, outside="drop", **cfg):
     """The LMAC_metrics.py:125-158 loop body without the classifier:
     STFT -> mask-apply (mask and 1-mask) -> 2 x iSTFT [-> normaliser].
 
+    A mask [B,F',T'] smaller than the grid: ``outside="drop"`` follows the reference's crop of magnitude and
+    phase to the mask's extent (LMAC_metrics.py:136-139, loss_function.py:36-41) - both masked spectra exist
+    on [F',T'] only and are zero-padded back to [F,T] so that torch.istft accepts them; ``"keep_irr"``
+    zero-extends the mask instead.
+
     Returns (rel_wave, irr_wave)."""
     _, mag, phase = compute_stft(wave, **cfg)
-    m = extend_mask(mask, mag.shape[-2], mag.shape[-1])
     fn = mask_apply_log1p if mode == "log1p" else mask_apply_linear
-    rel, irr = fn(mag, phase, m)
+    Fm, Tm = mask.shape[-2], mask.shape[-1]
+    if outside == "drop" and (Fm, Tm) != tuple(mag.shape[-2:]):
+        r, i = fn(mag[:, :Fm, :Tm], phase[:, :Fm, :Tm], mask)
+        rel = torch.zeros(mag.shape, dtype=r.dtype)
+        irr = torch.zeros(mag.shape, dtype=i.dtype)
+        rel[:, :Fm, :Tm], irr[:, :Fm, :Tm] = r, i
+    else:
+        m = extend_mask(mask, mag.shape[-2], mag.shape[-1])
+        rel, irr = fn(mag, phase, m)
     icfg = {k: v for k, v in cfg.items()}
     rel_w = compute_invert_stft(rel, **icfg)
     irr_w = compute_invert_stft(irr, **icfg)

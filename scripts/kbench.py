@@ -23,13 +23,14 @@ ap.add_argument("--n", type=int, default=64000)
 ap.add_argument("--pool", type=int, default=16)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--tag", default="")
+ap.add_argument("--winlen", type=int, default=0)
 args = ap.parse_args()
 
 pkg = importlib.import_module("xai-audio-deepfakes_b200")
 pkg._lib.build()
 ops = pkg.ops
 B, n, n_fft, hop = args.batch, args.n, args.nfft, args.hop
-win_len = n_fft if n_fft == 512 else 644
+win_len = args.winlen or (n_fft if n_fft == 512 else 644)
 window = None if args.win == "rect" else torch.hann_window(win_len)
 F, T = n_fft // 2 + 1, 1 + n // hop
 POOL = args.pool

@@ -55,3 +55,64 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_dropin_imports(pkg):
+    """With ``dropin/`` on sys.path the reference's import lines bind the package's own module objects."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from audioprocessor import AudioProcessor\n"
+            "from LMAC_metrics import compute_AD, compute_fidelity, run_addvisor_metrics\n"
+            "from loss_function import LMACLoss\n"
+            "from classifier_embedder import TorchLogReg, zero_mean_unit_var_norm\n"
+            "from captum_saliency import Wav2vec2LogReg\n"
+            "from addvisor import UNet\n"
+            "import importlib, audioprocessor, LMAC_metrics\n"
+            "pkg = importlib.import_module('xai-audio-deepfakes_b200')\n"
+            "assert audioprocessor is pkg.audioprocessor and LMAC_metrics is pkg.LMAC_metrics\n"
+            "assert AudioProcessor().hop_length == 322\n"
+            "print('ok')\n") % os.path.join(ROOT, "dropin")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_load_audio_matches_reference_semantics(pkg, tmp_path):
+    """AudioProcessor.load_audio (audioprocessor.py:49-63) on PCM16 wavs written here: scaling by 1/32768, channel
+    squeeze, zero-pad to audio_length * sr when short, crop when long; no GPU involved (host I/O)."""
+    import wave
+    import numpy as np
+    ap = pkg.audioprocessor.AudioProcessor(audio_length=1)
+    rng = np.random.default_rng(0)
+    for n in (12000, 16000, 20000):
+        pcm = rng.integers(-32768, 32767, size=n, dtype=np.int16)
+        path = str(tmp_path / f"clip{n}.wav")
+        with wave.open(path, "wb") as f:
+            f.setnchannels(1)
+            f.setsampwidth(2)
+            f.setframerate(16000)
+            f.writeframes(pcm.tobytes())
+        audio, sr = ap.load_audio(path)
+        assert sr == 16000 and audio.shape == (16000,) and audio.dtype == torch.float32
+        want = np.zeros(16000, dtype=np.float32)
+        m = min(n, 16000)
+        want[:m] = pcm[:m].astype(np.float32) / 32768.0
+        assert np.array_equal(audio.numpy(), want)
+
+
+def test_cfg1_fixture_transforms_match_oracle():
+    """BASELINE configs[0] on the CPU: the oracle restatement reproduces what the unmodified reference computed on the
+    4 bundled wavs (tests/golden/cfg1_wavs.npz) - spectrum sample, masked waveforms (full random mask), their sums."""
+    import numpy as np
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import cfg1_wavs
+    from oracle import ref_path as R
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cfg1_wavs.npz"))
+    wav = torch.from_numpy(g["pcm"].astype(np.float32) / 32768.0)
+    X, mag, _ = R.compute_stft(wav)
+    assert np.array_equal(X[:, ::8, ::8].numpy(), g["X_s"])
+    mask = cfg1_wavs.full_mask(tuple(mag.shape))
+    rel, irr = R.explain(wav, mask, outside="keep_irr")
+    assert np.array_equal(rel[:, ::8].numpy(), g["full_rel_s"]) and np.array_equal(irr[:, ::8].numpy(), g["full_irr_s"])
+    np.testing.assert_allclose(rel.double().sum(dim=1).numpy(), g["full_sums"][0], rtol=1e-12, atol=1e-12)

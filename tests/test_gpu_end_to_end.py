@@ -133,12 +133,15 @@ def test_saliency_path(pkg, built_lib):
 # training loss (loss_function.py:32-77): forward and backward of the linear mask path
 # ---------------------------------------------------------------------------------------------------
 def _torch_linear_path(mask, spec, n_fft, hop, win, window, n):
-    """loss_function.py:36-47 in plain torch on the CPU (mask zero-extended to the full grid)."""
+    """loss_function.py:36-47 in plain torch on the CPU: magnitude and phase cropped to the mask's extent (:38-45),
+    both masked spectra zero-padded back to the full grid so that torch.istft accepts them."""
     B, Fb, T = spec.shape
-    m = torch.nn.functional.pad(mask, (0, T - mask.shape[2], 0, Fb - mask.shape[1]))
+    pad = (0, T - mask.shape[2], 0, Fb - mask.shape[1])
+    m = torch.nn.functional.pad(mask, pad)
+    inside = torch.nn.functional.pad(torch.ones_like(mask), pad)
     w = torch.ones(win) if window is None else window
     ist = lambda s: torch.istft(s, n_fft, hop_length=hop, win_length=win, window=w, length=n)
-    return ist(m * spec), ist((1 - m) * spec)
+    return ist(m * spec), ist((inside - m) * spec)
 
 
 @pytest.mark.parametrize("n_fft,hop,win,hann,n,Fm,Tm", [
@@ -226,3 +229,58 @@ def test_lmac_loss_forward_backward(pkg, built_lib):
 def importlib_loss(pkg):
     import importlib
     return importlib.import_module(pkg.__name__ + ".loss_function")
+
+
+# ---------------------------------------------------------------------------------------------------
+# drop-in import lines and BASELINE configs[0]
+# ---------------------------------------------------------------------------------------------------
+def test_dropin_reference_import_lines(pkg, built_lib):
+    """The reference's own import lines (LMAC_metrics.py:4-6, loss_function.py:11-12, captum_saliency.py:1-2) with
+    only ``dropin/`` added to sys.path, then a call through the names they bind."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import torch\n"
+        "from audioprocessor import AudioProcessor\n"
+        "from classifier_embedder import TorchLogReg, zero_mean_unit_var_norm\n"
+        "from LMAC_metrics import compute_AD, compute_AI, compute_AG, compute_fidelity, compute_faithfulness\n"
+        "from loss_function import LMACLoss\n"
+        "from addvisor import UNet\n"
+        "ap = AudioProcessor()\n"
+        "x = 0.1 * torch.randn(2, 80000)\n"
+        "X, mag, ph = ap.compute_stft(x)\n"
+        "assert X.shape == (2, 513, 249) and X.is_cuda\n"
+        "y = ap.compute_invert_stft(X)\n"
+        "assert float((y.cpu() - x).abs().max()) < 1e-5\n"
+        "p = torch.tensor([[.9],[.2],[.5],[.7]]); th = torch.tensor([[.95],[.4],[.6],[.3]])\n"
+        "assert compute_AD(th, p).cpu().tolist()[1] == 25.0 and compute_fidelity(th, p, torch.Tensor([0.5])).shape == (4, 1)\n"
+        "print('dropin ok')\n") % os.path.join(root, "dropin")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and "dropin ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_cfg1_bundled_wavs_match_reference(pkg, built_lib):
+    """BASELINE configs[0]: the 4 bundled wavs, reference-default geometry, seeded U-Net mask (zero-extended) and a full
+    random mask, seeded XLS-R-shaped classifier + logistic head, against what the UNMODIFIED reference computed on the
+    CPU (tests/golden/cfg1_wavs.npz, oracle/make_golden.py --only-cfg1): transforms <= 1e-4, per-clip |dp| <= 1e-3,
+    the five means <= 1e-3 wherever no threshold can flip inside that tolerance."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "scripts"))
+    import cfg1_wavs
+    res = cfg1_wavs.run(pkg, timing_reps=3)
+    assert res["stft_relerr"] < 1e-4
+    assert res["unet_mask_maxabs_err"] < 1e-3      # cuDNN fp32 convolutions vs the CPU's
+    for tag in ("unet", "full"):
+        r = res[tag]
+        assert r["rel_wave_relerr"] < 1e-4 and r["irr_wave_relerr"] < 1e-4, r
+        assert r["max_abs_dp"] < 1e-3, r
+        got = np.array([r["means"][k] for k in pkg.LMAC_metrics.METRIC_NAMES])
+        want = np.array([r["reference_means"][k] for k in pkg.LMAC_metrics.METRIC_NAMES])
+        if r["flip_margin_reference"] > 2 * r["max_abs_dp"]:     # no label / AI decision can differ
+            np.testing.assert_allclose(got[:2], want[:2], atol=1e-3)          # FF, fidelity (fractions)
+            np.testing.assert_allclose(got[2:], want[2:], atol=0.1 + 1e-3)    # AD / AI / AG are percentages: 1e-3 * 100

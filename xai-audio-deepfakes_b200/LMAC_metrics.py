@@ -25,11 +25,18 @@ def _col(p, theta, q, col):
 
 @torch.no_grad()
 def compute_fidelity(theta_out, predictions, threshold=0.5):
-    """LMAC_metrics.py:31-38 -> float [N,1]: 1 where masked-in and original labels agree."""
-    thr = float(threshold.reshape(-1)[0]) if torch.is_tensor(threshold) else float(threshold)
-    if thr != 0.5:
-        raise ValueError("the fused metric kernel implements the reference's threshold of 0.5 only")
-    return _col(predictions, theta_out, predictions, 1).reshape(-1, 1)
+    """LMAC_metrics.py:31-38 -> float [N,1]: 1 where masked-in and original labels agree.  ``threshold`` may be a
+    float or a tensor (the reference's default is ``torch.Tensor([0.5])``).  The fused metric kernel bakes in 0.5;
+    any other threshold is the same three comparisons spelled with device ops (no host round trip)."""
+    if torch.is_tensor(threshold) and threshold.numel() != 1:
+        thr = threshold.to(ops._dev(), torch.float32)
+    else:
+        thr = float(threshold.reshape(-1)[0]) if torch.is_tensor(threshold) else float(threshold)
+        if thr == 0.5:
+            return _col(predictions, theta_out, predictions, 1).reshape(-1, 1)
+    dev = ops._dev()
+    p, th = predictions.to(dev, torch.float32), theta_out.to(dev, torch.float32)
+    return ((p > thr).long() == (th > thr).long()).float().reshape(-1, 1)
 
 
 def get_score_for_predicted_class(p):

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libaddvisor_sm100.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "transform_kernels.cu", "pointwise_kernels.cu", "gemm_kernels.cu", "conv_tma_kernels.cu",
+SOURCES = ["capi.cu", "transform_kernels.cu", "transform3_kernels.cu", "pointwise_kernels.cu", "gemm_kernels.cu", "conv_tma_kernels.cu",
            "resunit_kernels.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC"]
@@ -22,6 +22,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
 ADV_OK, ADV_ERR_INVALID, ADV_ERR_UNSUPPORTED, ADV_ERR_NOLA = 0, -1, -2, -3
 ADV_ERR_SHORT_INPUT, ADV_ERR_CUDA, ADV_ERR_SHAPE = -4, -5, -6
 MASK_LOG1P, MASK_LINEAR = 0, 1
+MASK_DROP_OUTSIDE = 0x100
 STFT_ZERO_PAD = 1
 
 

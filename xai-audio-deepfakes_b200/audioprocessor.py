@@ -109,7 +109,7 @@ class AudioProcessor:
         return out[0] if single else out
 
     # ------------------------------------------------------------------ fused path (ours)
-    def explain(self, waveforms, mask, mode="log1p", normalize=False):
+    def explain(self, waveforms, mask, mode="log1p", normalize=False, outside="drop"):
         """waveforms [B,n] + mask [B,F',T'] -> (relevant, irrelevant) waveforms [B, audio_length*sr].
 
         One kernel does compute_stft -> ``expm1(mask*log1p(mag)) * exp(1j*phase)`` (and the 1-mask
@@ -121,12 +121,12 @@ class AudioProcessor:
         n = int(self.audio_length * self.sampling_rate)
         wav = self._fit(waveforms, n)
         return ops.explain(wav, mask, self.n_fft, self.hop_length, self.win_length, length=n, mode=mode,
-                           normalize=normalize)
+                           normalize=normalize, outside=outside)
 
-    def explain_from_stft(self, spectrogram, mask, mode="log1p", normalize=False):
+    def explain_from_stft(self, spectrogram, mask, mode="log1p", normalize=False, outside="drop"):
         """Same, starting from ``compute_stft``'s complex output (collate_fn already has it)."""
         if not torch.is_complex(spectrogram):
             raise ValueError("ISTFT expects complex input!")
         n = int(self.audio_length * self.sampling_rate)
         return ops.explain_spec(spectrogram, mask, self.n_fft, self.hop_length, self.win_length, length=n,
-                                mode=mode, normalize=normalize)
+                                mode=mode, normalize=normalize, outside=outside)

@@ -17,6 +17,7 @@ struct PlanDev {
     const float* window;   // dev [n_fft], window centred in n_fft
     const float* inv_env;  // dev [n_out], 1 / (n_fft * sum_t w^2), 0 where no frame lands
     const float2* tw;      // dev [2][32][lanes]: exp(-2*pi*i*l*k1/n_fft), then the row-rotated variant
+    const float2* tw3;     // dev [f3::TW_TOTAL]: twiddle tables of the generation-3 warp FFT (fft3.cuh)
 };
 
 // Tiling of the output (sample) axis for the overlap-add kernels.
@@ -32,13 +33,26 @@ struct adv_plan {
     int win_length;
     int frames_per_tile;  // capacity of one CTA pass: 2 * units
     int max_hops;         // largest hops_per_tile whose frame span fits frames_per_tile
+    int max_hops_cap[2];  // the same for tiles of 16 / 32 frames (generation-3 kernels: 16 warps x 1 or 2 frames)
+    int gen3;             // generation-3 kernels usable for this geometry (n_fft 512, or n_fft 1024 with an even hop)
     int device;
     void* dev_block;      // single allocation holding window / inv_env / tw
 };
 
 namespace adv {
 void set_cuda_error(cudaError_t e);
-Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm, bool balanced = false);  // resident CTAs per SM of the consumer
+// slots_per_sm: resident CTAs per SM of the consumer; frames_cap: frames one CTA pass holds (0: the plan's default)
+Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm, bool balanced = false, int frames_cap = 0);
+// generation-3 launchers (transform3_kernels.cu); return ADV_ERR_UNSUPPORTED when the call is outside their domain
+bool gen3_enabled();
+int launch_stft3(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
+                 float* phase, int flags, cudaStream_t s);
+int launch_istft3(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
+                  double* stats, cudaStream_t s);
+int launch_explain3(const adv_plan* p, const float* wav, int64_t wav_stride, const float2* X, int64_t sb, int64_t st,
+                    int64_t sf, const float* mask, int Fm, int Tm, int mode, int batch, float* rel, float* irr,
+                    double* stats, cudaStream_t s);
+int istft3_frames_cap(const adv_plan* p);    // 32 when launch_istft3 takes the plan, else 0 (plan default)
 bool istft_balanced();  // tiling policy of the stand-alone iSTFT kernels (ADV_ISTFT_BALANCED=1 selects the round-balanced tile length; default: longest tile)
 int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
                 float* phase, int flags, cudaStream_t s);

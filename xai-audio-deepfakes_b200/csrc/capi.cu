@@ -6,6 +6,7 @@
 #include <vector>
 #include "adv_internal.cuh"
 #include "fft_core.cuh"
+#include "fft3.cuh"
 
 namespace adv {
 
@@ -54,7 +55,13 @@ bool istft_balanced() {
     return on;
 }
 
-Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm, bool balanced) {
+bool gen3_enabled() {
+    static const char* e = getenv("ADV_GEN3");   // A/B switch: ADV_GEN3=0 routes every call to the generation-2 kernels
+    static const bool on = !(e && e[0] == '0');
+    return on;
+}
+
+Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm, bool balanced, int frames_cap) {
     // A tile costs one CTA pass whose length grows with the frames it transforms (each unit with a live frame
     // runs its FFTs; idle units skip them), and the persistent kernels run ceil(tiles * batch / resident CTAs)
     // rounds.  Pick the tile length that minimises rounds x (frames + fixed cost) instead of simply the longest
@@ -79,8 +86,9 @@ Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm, bool balanc
     const bool longest = env_longest && !balanced;
     int best_k = 0;
     long best_cost = 0;
-    const int k_min = longest ? p->max_hops : (p->max_hops / 2 > 1 ? p->max_hops / 2 : 1);
-    for (int k0 = p->max_hops; k0 >= k_min; --k0) {
+    const int max_hops = frames_cap == 16 ? p->max_hops_cap[0] : (frames_cap == 32 ? p->max_hops_cap[1] : p->max_hops);
+    const int k_min = longest ? max_hops : (max_hops / 2 > 1 ? max_hops / 2 : 1);
+    for (int k0 = max_hops; k0 >= k_min; --k0) {
         const int tiles = (total_hops + k0 - 1) / k0;
         const int k = (total_hops + tiles - 1) / tiles;  // even split of the same number of tiles
         const long rounds = ((long)tiles * (batch < 1 ? 1 : batch) + slots - 1) / slots;
@@ -166,9 +174,14 @@ int adv_plan_create(adv_plan** out, int n_fft, int hop, int win_length, const fl
 
     adv_plan* p = (adv_plan*)calloc(1, sizeof(adv_plan));
     if (!p) return ADV_ERR_INVALID;
+    std::vector<float2> tw3(f3::TW_TOTAL);
+    f3::build_tables(tw3.data());
     const size_t b_win = sizeof(float) * n_fft, b_env = sizeof(float) * (size_t)n_out, b_tw = sizeof(float2) * tw.size();
+    const size_t b_tw3 = sizeof(float2) * tw3.size();
     const size_t o_env = (b_win + 255) / 256 * 256, o_tw = o_env + (b_env + 255) / 256 * 256;
-    cudaError_t e = cudaMalloc(&p->dev_block, o_tw + b_tw);
+    const size_t o_tw3 = o_tw + (b_tw + 255) / 256 * 256;
+    cudaError_t e = cudaMalloc(&p->dev_block, o_tw3 + b_tw3);
+    if (e == cudaSuccess) e = cudaMemcpy((char*)p->dev_block + o_tw3, tw3.data(), b_tw3, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy((char*)p->dev_block, win.data(), b_win, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy((char*)p->dev_block + o_env, inv_env.data(), b_env, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy((char*)p->dev_block + o_tw, tw.data(), b_tw, cudaMemcpyHostToDevice);
@@ -193,6 +206,8 @@ int adv_plan_create(adv_plan** out, int n_fft, int hop, int win_length, const fl
     p->d.window = (const float*)p->dev_block;
     p->d.inv_env = (const float*)((char*)p->dev_block + o_env);
     p->d.tw = (const float2*)((char*)p->dev_block + o_tw);
+    p->d.tw3 = (const float2*)((char*)p->dev_block + o_tw3);
+    p->gen3 = (n_fft == 512 || (n_fft == 1024 && hop % 2 == 0)) ? 1 : 0;
     p->win_length = win_length;
     p->frames_per_tile = 2 * (kThreads / lanes);
     p->max_hops = n_out == 0 ? 1 : 0;  // n_out == 0: forward-only plan, no overlap-add tiling
@@ -201,6 +216,15 @@ int adv_plan_create(adv_plan** out, int n_fft, int hop, int win_length, const fl
             p->max_hops = k;
             break;
         }
+    for (int c = 0; c < 2; ++c) {
+        const int cap = c == 0 ? 16 : 32;
+        p->max_hops_cap[c] = 0;
+        for (int k = cap; k >= 1 && n_out > 0; --k)
+            if (tile_frame_span(p->d, k) <= cap) {
+                p->max_hops_cap[c] = k;
+                break;
+            }
+    }
     if (p->max_hops == 0) {  // hop so small that even a one-hop tile needs more frames than a CTA holds
         adv_plan_destroy(p);
         return ADV_ERR_UNSUPPORTED;
@@ -223,7 +247,7 @@ int adv_plan_tiles(const adv_plan* plan, int batch) {
 }
 int adv_plan_tiles_istft(const adv_plan* plan, int batch) {
     if (!plan || batch <= 0 || plan->d.n_out <= 0) return ADV_ERR_INVALID;
-    return choose_tiling(plan, batch, 2, istft_balanced()).tiles;
+    return choose_tiling(plan, batch, 2, istft_balanced(), istft3_frames_cap(plan)).tiles;
 }
 
 int adv_stft(const adv_plan* plan, const float* wav, int64_t wav_stride, int batch, adv_c64* X, float* mag,
@@ -257,7 +281,7 @@ int adv_explain(const adv_plan* plan, const float* wav, int64_t wav_stride, cons
     if (!plan || !wav || !mask || !rel || !irr || batch <= 0 || plan->d.n_in <= 0 || wav_stride < plan->d.n_in ||
         plan->d.n_out <= 0)
         return ADV_ERR_INVALID;
-    if (mode != ADV_MASK_LOG1P && mode != ADV_MASK_LINEAR) return ADV_ERR_INVALID;
+    if ((mode & ~ADV_MASK_DROP_OUTSIDE) != ADV_MASK_LOG1P && (mode & ~ADV_MASK_DROP_OUTSIDE) != ADV_MASK_LINEAR) return ADV_ERR_INVALID;
     if (Fm <= 0 || Tm <= 0 || Fm > plan->d.n_fft / 2 + 1 || Tm > plan->d.T) return ADV_ERR_SHAPE;
     return launch_explain(plan, wav, wav_stride, nullptr, 0, 0, 0, mask, Fm, Tm, mode, batch, rel, irr, stats,
                           (cudaStream_t)stream);
@@ -266,7 +290,7 @@ int adv_explain(const adv_plan* plan, const float* wav, int64_t wav_stride, cons
 int adv_explain_spec(const adv_plan* plan, const adv_c64* X, int64_t sb, int64_t st, int64_t sf, const float* mask,
                      int Fm, int Tm, int mode, int batch, float* rel, float* irr, double* stats, void* stream) {
     if (!plan || !X || !mask || !rel || !irr || batch <= 0 || plan->d.n_out <= 0) return ADV_ERR_INVALID;
-    if (mode != ADV_MASK_LOG1P && mode != ADV_MASK_LINEAR) return ADV_ERR_INVALID;
+    if ((mode & ~ADV_MASK_DROP_OUTSIDE) != ADV_MASK_LOG1P && (mode & ~ADV_MASK_DROP_OUTSIDE) != ADV_MASK_LINEAR) return ADV_ERR_INVALID;
     if (Fm <= 0 || Tm <= 0 || Fm > plan->d.n_fft / 2 + 1 || Tm > plan->d.T) return ADV_ERR_SHAPE;
     return launch_explain(plan, nullptr, 0, (const float2*)X, sb, st, sf, mask, Fm, Tm, mode, batch, rel, irr, stats,
                           (cudaStream_t)stream);

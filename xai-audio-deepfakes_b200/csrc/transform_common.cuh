@@ -1,0 +1,378 @@
+// Helpers shared by the transform kernel translation units (transform_kernels.cu: generations 1 - 2,
+// transform3_kernels.cu: generation 3): index arithmetic, mbarrier / bulk-async / cp.async wrappers, waveform
+// staging, block reductions, shared-memory carving, tile geometry, mask gains, launch bookkeeping.
+#pragma once
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+#include "adv_internal.cuh"
+#include "fft_core.cuh"
+
+namespace adv {
+
+
+// (a float-reciprocal quotient with a one-step correction was measured here: slower - 31.2 vs 29.7 us for the wide
+// iSTFT, 89 vs 87 us for the fused kernel - the MUFU / conversion pipe is the scarcer resource)
+__device__ __forceinline__ int floordiv(int a, int b) {  // b > 0
+    int q = a / b;
+    return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+__device__ __forceinline__ int ceildiv(int a, int b) { return floordiv(a + b - 1, b); }
+
+template <int LANES>
+struct TwSmem {
+    const float2* p;
+    int l;
+    __device__ __forceinline__ float2 operator()(int k1) const { return p[k1 * LANES + l]; }
+};
+
+template <int NF>
+__device__ __forceinline__ void split_regs(const float2* v, int l, float2* xa, float2* xb) {
+    if constexpr (NF == 512) {
+        split512(v, l, xa, xb);
+    } else {
+        float2 send[16], recv[16];
+        split1024_pre(v, send);
+        const int src = (32 - l) & 31;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            recv[i].x = __shfl_sync(0xffffffffu, send[i].x, src);
+            recv[i].y = __shfl_sync(0xffffffffu, send[i].y, src);
+        }
+        split1024_post(v, l, recv, xa, xb);
+    }
+}
+template <int NF>
+__device__ __forceinline__ void merge_regs(float2* v, int l, const float2* ya, const float2* yb) {
+    if constexpr (NF == 512) {
+        merge512(v, l, ya, yb);
+    } else {
+        float2 send[16], recv[16];
+        merge1024_pre(v, l, ya, yb, send);
+        const int src = (32 - l) & 31;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            recv[i].x = __shfl_sync(0xffffffffu, send[i].x, src);
+            recv[i].y = __shfl_sync(0xffffffffu, send[i].y, src);
+        }
+        merge1024_post(v, l, recv);
+    }
+}
+
+// ---- mbarrier + bulk-async copy (TMA 1-D) -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// ---- cp.async (LDGSTS): global -> shared without a register round trip ----------------------------
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// ---- bulk-async store (TMA 1-D, shared -> global) of a unit's finished rows ---------------------------
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// `nbytes` (multiple of 4) staged at stage + (g & 15) go to global address g: the 16-byte aligned body by one
+// bulk copy issued by the elected lane, the <= 3 words before / after it by lanes 0..2 of the unit.  Call after
+// every writer lane has executed fence_async_smem() and the unit has synchronised.
+__device__ __forceinline__ void unit_store_bulk(const unsigned char* stage, unsigned char* g, uint32_t nbytes, int l,
+                                                bool elected) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
+    uint32_t head = mis ? 16 - mis : 0;
+    if (head > nbytes) head = nbytes;
+    const uint32_t body = (nbytes - head) & ~15u, tail = nbytes - head - body;
+    const float* sw = reinterpret_cast<const float*>(stage + mis);
+    float* gw = reinterpret_cast<float*>(g);
+    if ((uint32_t)l < head / 4) gw[l] = sw[l];
+    if ((uint32_t)l < tail / 4) gw[(head + body) / 4 + l] = sw[(head + body) / 4 + l];
+    if (elected && body) {
+        bulk_s2g(g + head, stage + mis + head, body);
+        bulk_commit();
+    }
+}
+// plan tables (twiddles, window): 16-byte async copies; wait + __syncthreads before the first use
+template <int NT>
+__device__ __forceinline__ void stage_tables(float2* tw_s, int n_tw, float* win_s, int n_win, const PlanDev& P) {
+    for (int i = threadIdx.x; i < n_tw / 2; i += NT) cp_async16(tw_s + 2 * i, P.tw + 2 * i);
+    for (int i = threadIdx.x; i < n_win / 4; i += NT) cp_async16(win_s + 4 * i, P.window + 4 * i);
+}
+// reciprocal-envelope tile for the epilogue: lands while the FFTs run
+template <int NT>
+__device__ __forceinline__ void stage_env(float* env_s, const float* __restrict__ env, int S) {
+    for (int i = threadIdx.x; i < S; i += NT) cp_async4(env_s + i, env + i);
+}
+
+// Stage `seglen` waveform samples starting at original index `base` into shared memory and return the
+// offset (0..3 floats) at which the data starts inside `seg`.  Interior tiles: thread 0 issues ONE bulk
+// copy that lands asynchronously (complete on `bar`, phase 0); the caller overlaps its other loads and
+// then calls stage_wait().  Tiles that touch the clip edges (torch.stft's centre=True reflect padding)
+// or an unaligned row use plain loads.  `bulk` is CTA-uniform.
+template <int NT = kThreads>
+__device__ __forceinline__ int stage_segment(float* seg, int seglen, const float* __restrict__ row, int base,
+                                             int n_in, uint64_t* bar, bool& bulk) {
+    const int a0 = base & ~3;
+    const int shift = base - a0;
+    const uint32_t bytes = (uint32_t)(((seglen + shift) * 4 + 15) & ~15);
+    bulk = base >= 0 && (a0 + (int)(bytes / 4)) <= n_in && ((reinterpret_cast<uintptr_t>(row + a0) & 15) == 0);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(seg, row + a0, bytes, bar);
+        }
+        return shift;
+    }
+    for (int i = threadIdx.x; i < seglen; i += NT) {
+        int idx = base + i;
+        if (idx < 0) idx = -idx;
+        else if (idx >= n_in) idx = 2 * (n_in - 1) - idx;
+        seg[i] = (idx >= 0 && idx < n_in) ? __ldg(row + idx) : 0.0f;
+    }
+    return 0;
+}
+// after a __syncthreads() (makes the barrier init / the plain stores visible)
+__device__ __forceinline__ void stage_wait(uint64_t* bar, bool bulk) {
+    if (bulk) mbar_wait(bar, 0);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Sum NQ doubles per thread over the CTA; result valid in thread 0.  red: >= NQ * 8 doubles of smem.
+template <int NQ, int NT = kThreads>
+__device__ __forceinline__ void block_sum(double (&q)[NQ], double* red) {
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        q[i] = warp_sum(q[i]);
+        if (ln == 0) red[i * (NT / 32) + w] = q[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < NT / 32; ++k) s += red[i * (NT / 32) + k];
+            q[i] = s;
+        }
+    }
+}
+
+// shared-memory carving (all offsets 16-byte aligned)
+struct Carver {
+    unsigned char* p;
+    template <class T>
+    __device__ __forceinline__ T* take(size_t n) {
+        T* r = reinterpret_cast<T*>(p);
+        p += (n * sizeof(T) + 15) & ~size_t(15);
+        return r;
+    }
+};
+static size_t al16(size_t b) { return (b + 15) & ~size_t(15); }
+
+// Request samples [base, base + seglen) of `row` (reflect-padded outside [0, n_in)) into seg; sample
+// idx lands at seg[idx - base + shift], shift = base mod 4 (returned).  Thread 0 arms `bar` with the
+// bulk byte count (possibly 0) - one phase per call.  All threads must call it.
+template <int NT>
+__device__ __forceinline__ int stage_segment_async(float* seg, int seglen, const float* __restrict__ row, int base,
+                                                   int n_in, uint64_t* bar, int gtid = -1, bool pad_zero = false) {
+    if (gtid < 0) gtid = threadIdx.x;  // index inside the cooperating group of NT threads (CTA or warp)
+    const int shift = base & 3;
+    const int lo = max(base, 0), hi = min(base + seglen, n_in);
+    int a0 = (lo + 3) & ~3, a1 = hi & ~3;
+    if ((reinterpret_cast<uintptr_t>(row) & 15) != 0 || a1 <= a0) a0 = a1 = base;  // no bulk part
+    if (gtid == 0) {
+        const uint32_t bytes = (uint32_t)(a1 - a0) * 4u;
+        mbar_expect_tx(bar, bytes);
+        if (bytes) bulk_g2s(seg + (a0 - base + shift), row + a0, bytes, bar);
+    }
+    const int nL = a0 - base, nP = nL + (base + seglen - a1);
+    for (int i = gtid; i < nP; i += NT) {
+        const int pos = i < nL ? base + i : a1 + (i - nL);
+        int idx = pos;
+        if (!pad_zero) {
+            if (idx < 0) idx = -idx;
+            else if (idx >= n_in) idx = 2 * (n_in - 1) - idx;
+        }
+        seg[pos - base + shift] = (idx >= 0 && idx < n_in) ? __ldg(row + idx) : 0.0f;
+    }
+    return shift;
+}
+
+// atan2 for the phase output: odd minimax polynomial on [0, 1] (max abs error 1.3e-7 rad before the
+// quadrant fix-up, i.e. fp32 round-off of a result up to pi) - a third of libm atan2f's instructions
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+    const float s = a * a;
+    float p = -0.004355369135737419f;
+    p = fmaf(p, s, 0.023040004074573517f);
+    p = fmaf(p, s, -0.0577734000980854f);
+    p = fmaf(p, s, 0.09794221073389053f);
+    p = fmaf(p, s, -0.13976576924324036f);
+    p = fmaf(p, s, 0.19962702691555023f);
+    p = fmaf(p, s, -0.3333165943622589f);
+    float r = fmaf(p * s, a, a);
+    if (ay > ax) r = 1.57079632679489662f - r;
+    if (x < 0.0f) r = 3.14159265358979324f - r;
+    return copysignf(r, y);
+}
+
+struct TileGeom {
+    int s0, s1;      // output samples [s0, s1)
+    int p0;          // padded position of s0
+    int t_lo, t_hi;  // frames overlapping the tile (inclusive)
+};
+template <int NF>
+__device__ __forceinline__ TileGeom tile_geom(const PlanDev& P, const Tiling& TL, int tile) {
+    TileGeom g;
+    const int S = TL.hops_per_tile * P.hop;
+    g.s0 = tile * S;
+    g.s1 = min(g.s0 + S, P.n_out);
+    g.p0 = g.s0 + NF / 2;
+    const int p1 = g.s1 + NF / 2;
+    g.t_lo = max(0, ceildiv(g.p0 - P.whi + 1, P.hop));
+    g.t_hi = min(P.T - 1, floordiv(p1 - 1 - P.wlo, P.hop));
+    return g;
+}
+
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using T = float; };
+template <> struct VecT<2> { using T = float2; };
+template <> struct VecT<4> { using T = float4; };
+__device__ __forceinline__ void vadd(float& a, float b) { a += b; }
+__device__ __forceinline__ void vadd(float2& a, float2 b) { a.x += b.x; a.y += b.y; }
+__device__ __forceinline__ void vadd(float4& a, float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ float vmul_stats(float& a, float e, float& sq) { a *= e; sq = a * a; return a; }
+__device__ __forceinline__ float vmul_stats(float2& a, float2 e, float& sq) {
+    a.x *= e.x; a.y *= e.y;
+    sq = fmaf(a.x, a.x, a.y * a.y);
+    return a.x + a.y;
+}
+__device__ __forceinline__ float vmul_stats(float4& a, float4 e, float& sq) {
+    a.x *= e.x; a.y *= e.y; a.z *= e.z; a.w *= e.w;
+    sq = fmaf(a.x, a.x, a.y * a.y) + fmaf(a.z, a.z, a.w * a.w);
+    return (a.x + a.y) + (a.z + a.w);
+}
+template <class V> __device__ __forceinline__ V vzero();
+template <> __device__ __forceinline__ float vzero<float>() { return 0.0f; }
+template <> __device__ __forceinline__ float2 vzero<float2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ float4 vzero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Gains that turn X into the masked-in / masked-out spectra with the ORIGINAL phase:
+//   log1p mode (LMAC_metrics.py:138-143,151-153): expm1(m*log1p(a)) * e^{i phi} = X * expm1(m*log1p(a)) / a
+//   linear mode (loss_function.py:38-45):          m*a*e^{i phi} = m*X
+// With er = expm1(m*log1p(a)) the complementary term needs no second exponential:
+//   expm1((1-m)*log1p(a)) = (1+a)/(1+er) - 1 = (a - er)/(1 + er).
+// a >= 1/16: (1+a)^m through MUFU lg2/ex2 (abs. error of lg2.approx 2^-22.6 => error relative to the bin
+// magnitude <= 5e-6); a < 1/16: Taylor series of log1p and expm1 (truncation < 1e-8 relative).
+template <int MODE>
+__device__ __forceinline__ void mask_gains(float2 x, float m, float& g_rel, float& g_irr) {
+    if (MODE == ADV_MASK_LINEAR) {
+        g_rel = m;
+        g_irr = 1.0f - m;
+        return;
+    }
+    // |X|^2 clamped away from 0: for a -> 0 the gains tend to (m, 1 - m) and the product with X vanishes either
+    // way, so the clamp replaces a branch per bin (1e-30 keeps rsqrt and a = r2 * ia normal numbers)
+    const float r2 = fmaxf(fmaf(x.x, x.x, x.y * x.y), 1e-30f);
+    const float ia = rsqrtf(r2);
+    const float a = r2 * ia;
+    float er;
+    if (a >= 0.0625f) {
+        er = ex2_approx(m * lg2_approx(1.0f + a)) - 1.0f;
+    } else {
+        // log1p(a)/a = 1 - a(1/2 - a(1/3 - a(1/4 - a(1/5 - a/6)))), next term a^6/7 < 1e-8
+        float L = fmaf(a, -1.0f / 6.0f, 0.2f);
+        L = fmaf(-a, L, 0.25f);
+        L = fmaf(-a, L, 1.0f / 3.0f);
+        L = fmaf(-a, L, 0.5f);
+        L = fmaf(-a, L, 1.0f);
+        L *= a;
+        const float y = m * L;
+        float e = fmaf(y, 1.0f / 120.0f, 1.0f / 24.0f);
+        e = fmaf(y, e, 1.0f / 6.0f);
+        e = fmaf(y, e, 0.5f);
+        e = fmaf(y, e, 1.0f);
+        er = y * e;
+    }
+    const float ei = __fdividef(a - er, 1.0f + er);
+    g_rel = er * ia;
+    g_irr = ei * ia;
+}
+
+// cudaFuncSetAttribute once per (kernel, size high-water mark): keeps the launch path free of
+// attribute calls in steady state (and inside CUDA-graph capture)
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, size_t> high;
+    if (bytes > 227 * 1024) return ADV_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = high[reinterpret_cast<const void*>(kernel)];
+    if (bytes > cur) {
+        ADV_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return ADV_OK;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace adv

@@ -14,6 +14,14 @@ from . import _lib
 from ._lib import check, get_plan, lib, ptr, stream_ptr
 
 MODES = {"log1p": _lib.MASK_LOG1P, "linear": _lib.MASK_LINEAR}
+# bins outside a mask smaller than the spectrum: "drop" removes them from BOTH outputs - what the reference's crop of
+# magnitude and phase to the mask's extent amounts to (LMAC_metrics.py:136-139, loss_function.py:36-41); "keep_irr"
+# zero-extends the mask, i.e. out-of-mask bins pass to the masked-out branch with gain 1
+OUTSIDE = {"drop": _lib.MASK_DROP_OUTSIDE, "keep_irr": 0}
+
+
+def _mode_flags(mode, outside):
+    return MODES[mode] | OUTSIDE[outside]
 
 
 def _dev():
@@ -100,9 +108,12 @@ def normalize_(x, stats=None, width=2, col=0, out=None):
 
 
 def explain(wave, mask, n_fft, hop, win_length, length=None, mode="log1p", window=None, normalize=False,
-            out=None):
+            out=None, outside="drop"):
     """Fused wave + mask -> (masked-in wave, masked-out wave) [B, length] (LMAC_metrics.py:136-157).
-    ``out=(rel, irr, stats)`` reuses caller-owned buffers (stats: float64 [B, tiles, 4])."""
+    ``out=(rel, irr, stats)`` reuses caller-owned buffers (stats: float64 [B, tiles, 4]).
+    A mask smaller than the [F, T] grid (the U-Net's 512 x 248 against 513 x 249) covers its top-left corner;
+    ``outside`` says what happens to the other bins: ``"drop"`` (default, the reference's crop: gone from both
+    outputs) or ``"keep_irr"`` (zero extension: they stay in the masked-out waveform)."""
     wave = _f32_rows(wave, "waveform")
     mask = _mask3(mask)
     B, n = wave.shape
@@ -118,7 +129,7 @@ def explain(wave, mask, n_fft, hop, win_length, length=None, mode="log1p", windo
         irr = torch.empty_like(rel)
         stats = torch.empty((B, plan.tiles(B), 4), dtype=torch.float64, device=wave.device) if normalize else None
     check(lib().adv_explain(plan.handle, ptr(wave), wave.stride(0), ptr(mask), mask.shape[1], mask.shape[2],
-                            MODES[mode], B, ptr(rel), ptr(irr), ptr(stats), stream_ptr()), "adv_explain")
+                            _mode_flags(mode, outside), B, ptr(rel), ptr(irr), ptr(stats), stream_ptr()), "adv_explain")
     if normalize:
         check(lib().adv_normalize_pair(ptr(rel), ptr(irr), B, n_out, ptr(stats), stats.shape[1], stream_ptr()),
               "adv_normalize_pair")
@@ -141,7 +152,8 @@ def explain_tiles(n_fft, hop, win_length, n, batch, length=None, window=None):
     return get_plan(n_fft, hop, win_length, window, T, n, n_out).tiles(batch)
 
 
-def explain_spec(spec, mask, n_fft, hop, win_length, length=None, mode="log1p", window=None, normalize=False):
+def explain_spec(spec, mask, n_fft, hop, win_length, length=None, mode="log1p", window=None, normalize=False,
+                 outside="drop"):
     """Same as :func:`explain` starting from an STFT (complex [B,F,T])."""
     spec, sb, st, sf = _spec_strides(spec)
     mask = _mask3(mask)
@@ -154,7 +166,7 @@ def explain_spec(spec, mask, n_fft, hop, win_length, length=None, mode="log1p", 
     irr = torch.empty_like(rel)
     stats = torch.empty((B, plan.tiles(B), 4), dtype=torch.float64, device=spec.device) if normalize else None
     check(lib().adv_explain_spec(plan.handle, ptr(spec), sb, st, sf, ptr(mask), mask.shape[1], mask.shape[2],
-                                 MODES[mode], B, ptr(rel), ptr(irr), ptr(stats), stream_ptr()), "adv_explain_spec")
+                                 _mode_flags(mode, outside), B, ptr(rel), ptr(irr), ptr(stats), stream_ptr()), "adv_explain_spec")
     if normalize:
         check(lib().adv_normalize_pair(ptr(rel), ptr(irr), B, n_out, ptr(stats), stats.shape[1], stream_ptr()),
               "adv_normalize_pair")
@@ -170,9 +182,10 @@ class _ExplainLinearFn(torch.autograd.Function):
     one fused conj-multiply + transpose.  ``spec`` gets no gradient (it is data on this path)."""
 
     @staticmethod
-    def forward(ctx, mask, spec, n_fft, hop, win_length, length, window):
+    def forward(ctx, mask, spec, n_fft, hop, win_length, length, window, outside):
         spec_d, sb, st, sf = _spec_strides(spec.detach())
-        rel, irr = explain_spec(spec_d, mask.detach(), n_fft, hop, win_length, length=length, mode="linear", window=window)
+        rel, irr = explain_spec(spec_d, mask.detach(), n_fft, hop, win_length, length=length, mode="linear", window=window,
+                                outside=outside)
         ctx.save_for_backward(spec_d)
         ctx.geom = (n_fft, hop, win_length, length, window, tuple(mask.shape))
         return rel, irr
@@ -199,14 +212,16 @@ class _ExplainLinearFn(torch.autograd.Function):
         gm = torch.empty(m3, dtype=torch.float32, device=dev)
         check(lib().adv_mask_grad_linear(ptr(spec), spec.stride(0), spec.stride(2), spec.stride(1), ptr(A), B, Fb, T,
                                          m3[1], m3[2], ptr(gm), stream_ptr()), "adv_mask_grad_linear")
-        return gm.reshape(mshape), None, None, None, None, None, None
+        return gm.reshape(mshape), None, None, None, None, None, None, None
 
 
-def explain_linear(spec, mask, n_fft, hop, win_length, length=None, window=None):
-    """Linear-mode explain from an STFT, differentiable w.r.t. ``mask`` (training callers: loss_function.py)."""
+def explain_linear(spec, mask, n_fft, hop, win_length, length=None, window=None, outside="drop"):
+    """Linear-mode explain from an STFT, differentiable w.r.t. ``mask`` (training callers: loss_function.py).
+    Out-of-mask bins (``outside``, see :func:`explain`) are constants of the mask either way, so the gradient formula
+    does not depend on the choice."""
     if torch.is_grad_enabled() and mask.requires_grad:
-        return _ExplainLinearFn.apply(mask, spec, n_fft, hop, win_length, length, window)
-    return explain_spec(spec, mask, n_fft, hop, win_length, length=length, mode="linear", window=window)
+        return _ExplainLinearFn.apply(mask, spec, n_fft, hop, win_length, length, window, outside)
+    return explain_spec(spec, mask, n_fft, hop, win_length, length=length, mode="linear", window=window, outside=outside)
 
 
 def mask_apply(mag, phase, mask, mode="log1p"):
