@@ -121,31 +121,60 @@ def synth_host(seed, batch=BATCH):
     return wav, mask, logits
 
 
+def workload_config(n_gpus):
+    """The ``config`` object both arms print (identical keys and values: it names the workload, nothing run-specific)."""
+    return {"workload": "configs[1]: 64 x 4 s clips @16 kHz per GPU-step, n_fft 512 hop 160 win 512 (rectangular), "
+                        "STFT -> log1p mask / 1-mask -> 2 x iSTFT -> normalise x2 -> LMAC sums on given classifier "
+                        "logits (SSL model = the reference's torch module, not timed)",
+            "batch_per_gpu": BATCH, "clip_seconds": CFG["audio_length"], "sample_rate": CFG["sampling_rate"],
+            "n_fft": CFG["n_fft"], "hop": CFG["hop_length"], "win": CFG["win_length"], "mask": "log1p",
+            "parallelism": f"dp{n_gpus}",
+            "l2": f"inputs larger than L2: {POOL} rotating buffer sets (1.2 GB) > 126 MB"}
+
+
+def reference_stepper():
+    """(step(wav, mask, logits), kind, note): the UNMODIFIED reference's own code from baseline/_ref (a verbatim,
+    git-ignored copy made by __graft_entry__.build() where /root/reference exists; it travels to the GPU box) driven
+    through oracle/ref_loader.ReferencePath; the oracle port only if that copy is absent."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.exists(os.path.join(ref_dir, "audioprocessor.py")) and os.path.exists(os.path.join(ref_dir, "LMAC_metrics.py")):
+        try:
+            from oracle.ref_loader import ReferencePath
+            rp = ReferencePath(ref_dir, **CFG)
+            return rp.step, "reference", ("baseline/_ref: AudioProcessor.compute_stft / compute_invert_stft, "
+                                          f"LMAC_metrics.py lines {rp.lines[0]}-{rp.lines[-1]} and compute_* run verbatim")
+        except Exception as e:  # fall through to the port, say why
+            note = f"baseline/_ref failed to load ({e!r}); "
+    else:
+        note = "baseline/_ref absent; "
+    from oracle import ref_path as R
+    return (lambda w, m, l: cpu_path_step(R, w, m, l)), "port", note + "oracle/ref_path.py (same torch-CPU calls, bit-identical)"
+
+
 def run_reference(args, out=sys.stdout):
-    """--impl reference: the oracle port of the reference CPU path, all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import ref_path as R
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
+    step, kind, note = reference_stepper()
     wav, mask, logits = synth_host(1234)
     steps, warm = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3))
     for _ in range(warm):
-        cpu_path_step(R, wav, mask, logits)
+        step(wav, mask, logits)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_path_step(R, wav, mask, logits)
+        step(wav, mask, logits)
     dt = (time.perf_counter() - t0) / steps
     val = BATCH / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 64 x 4 s clips @16 kHz, n_fft 512 hop 160, mask -> iSTFT x2 -> "
-                               "normalise -> LMAC sums on given logits", "batch": BATCH},
-        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps x {BATCH} clips, torch {torch.__version__} CPU fp32"},
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} steps x {BATCH} clips, torch {torch.__version__} CPU fp32; {note}"},
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -178,8 +207,8 @@ def main():
     out = _claim_stdout()
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--gpus", type=int, default=1)
-    ap_.add_argument("--steps", type=int, default=5000)
-    ap_.add_argument("--warmup", type=int, default=50)
+    ap_.add_argument("--steps", type=int, default=4000)
+    ap_.add_argument("--warmup", type=int, default=48)
     ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap_.add_argument("--no-cpu-baseline", action="store_true")
     ap_.add_argument("--schedule", default="pooled", choices=["pooled", "streams"],
@@ -213,7 +242,7 @@ def main():
     from importlib import import_module
     pipeline = import_module("xai-audio-deepfakes_b200.pipeline")
     ap = pkg.audioprocessor.AudioProcessor(**CFG)
-    steps, warm = max(1, args.steps), max(3, args.warmup)
+    steps, warm = max(1, args.steps), max(3, args.warmup)   # (>= 3 warm-up steps: the timing rules' floor)
 
     # ---- device-resident pool (each rank owns its shard of clips: weak scaling, B clips per rank-step)
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
@@ -236,19 +265,20 @@ def main():
         pp.capture()
         burst_us = round(pp.burst_us_per_step(), 1)  # 96 steps from a cool GPU, before the sustained timed region
 
-    def step(i):  # 3 launches of ours; metric sums accumulate inside lmac_reduce.
-        j = i % POOL
-        if pooled:  # a step is 1 / POOL of a graph replay; a trailing partial pool runs its sets one by one
-            if j == 0 and i + POOL <= step.limit:
+    def run_steps(k):
+        """k steps on the current stream: whole pools replay the pooled graph, the remainder replays a tail graph over the
+        first k % POOL buffer sets (captured on first use, i.e. during warm-up) - every step takes the same pipelined
+        schedule whatever --steps is.  3 launches of ours per step; metric sums accumulate inside lmac_reduce."""
+        if pooled:
+            for _ in range(k // POOL):
                 pp.replay()
-            elif i >= step.limit - step.limit % POOL:
-                pool[j]._enqueue()
-                pool[j].launches += 3
+            if k % POOL:
+                pp.replay_tail(k % POOL)
             return
-        with torch.cuda.stream(streams[j % ns]):  # buffer set j always runs on stream j % ns: no cross-stream hazards
-            pool[j].step()
-
-    step.limit = 1 << 62
+        for i in range(k):
+            j = i % POOL
+            with torch.cuda.stream(streams[j % ns]):  # buffer set j always runs on stream j % ns: no cross-stream hazards
+                pool[j].step()
 
     def fork(ev):   # side streams start after `ev` (recorded on the main stream)
         for st in streams:
@@ -262,18 +292,21 @@ def main():
             main.wait_event(e)
 
     sampler = ClockSampler(local) if rank == 0 else None
-    # warm-up: at least `warm` steps and at least ~0.7 s of load so the clock sampler sees the GPU busy
+    # pre-heat (NOT the warm-up): ~0.7 s of the same steps so that the clock sampler sees the GPU under load and the
+    # clocks have ramped; reported separately as preheat_s / preheat_steps
     t_w = time.perf_counter()
-    done = 0
-    while done < warm or time.perf_counter() - t_w < 0.7:
-        step(done)
-        done += 1
-        if done % 256 == 0:
-            torch.cuda.synchronize()
-    # everything the timed region will launch must have run once: the un-graphed step of a trailing partial pool and
-    # the epilogue (stack + sum, and the NCCL all-reduce) - CUDA loads kernels lazily on first use and NCCL sets its
-    # channels up on the first collective, tens of milliseconds that do not belong to the steps
-    pool[0]._enqueue()
+    preheat_steps = 0
+    while time.perf_counter() - t_w < 0.7:
+        run_steps(POOL)
+        preheat_steps += POOL
+        torch.cuda.synchronize()
+    preheat_s = time.perf_counter() - t_w
+    # warm-up: exactly --warmup steps of exactly what the timed region runs (same split into pooled / tail replays), then
+    # the epilogue once (stack + sum, and the NCCL all-reduce): CUDA loads kernels lazily on first use and NCCL sets its
+    # channels up on the first collective - tens of milliseconds that do not belong to the steps
+    if pooled and steps % POOL:
+        pp.replay_tail(steps % POOL)
+    run_steps(warm)
     warm_total = torch.stack([p.sums for p in pool]).sum(dim=0)
     if world > 1:
         dist.all_reduce(warm_total, op=dist.ReduceOp.SUM)
@@ -291,9 +324,7 @@ def main():
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     fork(a)
-    step.limit = steps
-    for i in range(steps):
-        step(i)
+    run_steps(steps)
     join()
     total = torch.stack([p.sums for p in pool]).sum(dim=0)
     if world > 1:  # the one real exchange: six float64 sums, once per evaluation
@@ -428,13 +459,14 @@ def main():
         mel = -4 + 2 * torch.randn(vb, 80, vt, generator=gen, device="cuda")
         gen_v.decode_batch(mel)
         n_launch = gen_v.launches
-        t_v = time_loop(lambda i: gen_v.decode_batch(mel), 2) / 2
+        voc_reps = 10
+        t_v = time_loop(lambda i: gen_v.decode_batch(mel), voc_reps) / voc_reps
         fl = H.HifiganGenerator.flops_per_clip(vt) * vb
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] \
             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
         voc = {"workload": f"HiFi-GAN V1 generator, {vb} x 4 s clips (80 x {vt} mel -> 66816 samples), bf16",
                "clips_per_s": vb / t_v, "tflops": fl / t_v / 1e12, "bound": "tensor", "peak": pk,
-               "frac": fl / t_v / 1e12 / pk, "launches_per_batch": n_launch}
+               "frac": fl / t_v / 1e12 / pk, "launches_per_batch": n_launch, "reps": voc_reps}
         del gen_v, mel
     except Exception as e:  # the vocoder is a side path: never fail the headline bench on it
         voc = {"error": repr(e)[:200]}
@@ -448,18 +480,18 @@ def main():
     # ---- CPU baseline (oracle port) on this box's host cores: bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import ref_path as R
         torch.set_num_threads(os.cpu_count() or 1)
+        cpu_step, kind, note = reference_stepper()
         w, m, l = synth_host(1234)
-        cpu_path_step(R, w, m, l)
+        cpu_step(w, m, l)
         reps_c, t0 = 0, time.perf_counter()
         while reps_c < 3 or (time.perf_counter() - t0 < 12.0 and reps_c < 400):  # ~12 s of CPU work
-            cpu_path_step(R, w, m, l)
+            cpu_step(w, m, l)
             reps_c += 1
         dtc = (time.perf_counter() - t0) / reps_c
-        cpu = {"value": BATCH / dtc, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+        cpu = {"value": BATCH / dtc, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": kind,
                "sample": f"{reps_c} x {BATCH} clips of the same workload, torch {torch.__version__} CPU fp32, "
-                         f"os.cpu_count()={os.cpu_count()}"}
+                         f"os.cpu_count()={os.cpu_count()}; {note}"}
 
     traffic, issue = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -479,16 +511,12 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps,
-        "warmup": done, "ms_per_step": elapsed / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": elapsed / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 64 x 4 s clips @16 kHz per GPU-step, n_fft 512 hop 160 win 512, "
-                               "fused STFT -> log1p mask / 1-mask -> 2 x iSTFT -> normalise x2 -> LMAC sums "
-                               "(classifier logits synthetic; SSL model is the reference's torch module, not timed)",
-                   "batch_per_gpu": BATCH, "parallelism": f"dp{world}",
-                   "l2": f"{POOL} rotating buffer sets (1.2 GB) > 126 MB L2", "cuda_graph": True,
-                   "schedule": args.schedule, "streams": ns,
-                   "burst_us_per_step": burst_us,
-                   "host_affinity": (f"{len(affinity)} cpus local to the GPU (NVML)" if affinity else "unbound")},
+        "config": workload_config(world),
+        "run": {"cuda_graph": True, "schedule": args.schedule, "streams": ns, "burst_us_per_step": burst_us,
+                "preheat_s": round(preheat_s, 3), "preheat_steps": preheat_steps,
+                "host_affinity": (f"{len(affinity)} cpus local to the GPU (NVML)" if affinity else "unbound")},
         "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": hp.h2d_bytes,
                 "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps},
         "gpu_launches": launches,

@@ -36,63 +36,13 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "g
 warnings.filterwarnings("ignore")
 
 
-# ----------------------------------------------------------------------------
-# reference loaders
-# ----------------------------------------------------------------------------
-def lift(path, names, env):
-    """Compile the named top-level FunctionDef/ClassDef nodes of ``path`` into env."""
-    tree = ast.parse(open(path).read())
-    picked = [n for n in tree.body
-              if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
-    assert {n.name for n in picked} == set(names), (names, [n.name for n in picked])
-    exec(compile(ast.Module(picked, []), path, "exec"), env)
-    return env
-
-
-def statements_on_lines(path, func_name, line_ranges):
-    """The statements of ``func_name`` whose first line lies in one of ``line_ranges``."""
-    tree = ast.parse(open(path).read())
-    picked = []
-
-    def walk(body):
-        for st in body:
-            if any(lo <= st.lineno <= hi for lo, hi in line_ranges) and \
-                    not isinstance(st, (ast.For, ast.With, ast.If)):
-                picked.append(st)
-            for attr in ("body", "orelse"):
-                sub = getattr(st, attr, None)
-                if isinstance(sub, list):
-                    walk(sub)
-
-    for node in ast.walk(tree):
-        if isinstance(node, ast.FunctionDef) and node.name == func_name:
-            walk(node.body)
-    return compile(ast.Module(picked, []), path, "exec"), [s.lineno for s in picked]
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from ref_loader import lift, statements_on_lines  # noqa: E402
+from ref_loader import import_reference_audioprocessor as _import_ref  # noqa: E402
 
 
 def import_reference_audioprocessor():
-    if "audioprocessor" in sys.modules and "classifier_embedder" in sys.modules:
-        return sys.modules["audioprocessor"], sys.modules["classifier_embedder"]
-    from transformers import Wav2Vec2Model  # noqa: F401  (before the stub: transformers probes `accelerate` on import)
-    acc = types.ModuleType("accelerate")
-
-    class Accelerator:  # audioprocessor.py:15-16 only reads .device
-        def __init__(self):
-            self.device = torch.device("cpu")
-
-    acc.Accelerator = Accelerator
-    sys.modules["accelerate"] = acc
-
-    ce = types.ModuleType("classifier_embedder")
-    ce.wav2vec2 = torch.nn.Identity()
-    ce.processor = None
-    ce.classifier = types.SimpleNamespace(coef_=np.zeros((1, 1920)), intercept_=np.zeros(1))
-    lift(os.path.join(REF, "classifier_embedder.py"), ["zero_mean_unit_var_norm"], ce.__dict__)
-    sys.modules["classifier_embedder"] = ce
-    sys.path.insert(0, REF)
-    import audioprocessor  # the reference module, verbatim
-
-    return audioprocessor, ce
+    return _import_ref(REF)
 
 
 def read_wav(path):

@@ -256,7 +256,7 @@ def test_dropin_reference_import_lines(pkg, built_lib):
         "y = ap.compute_invert_stft(X)\n"
         "assert float((y.cpu() - x).abs().max()) < 1e-5\n"
         "p = torch.tensor([[.9],[.2],[.5],[.7]]); th = torch.tensor([[.95],[.4],[.6],[.3]])\n"
-        "assert compute_AD(th, p).cpu().tolist()[1] == 25.0 and compute_fidelity(th, p, torch.Tensor([0.5])).shape == (4, 1)\n"
+        "assert abs(compute_AD(th, p).cpu().tolist()[1] - 25.0) < 1e-4 and compute_fidelity(th, p, torch.Tensor([0.5])).shape == (4, 1)\n"
         "print('dropin ok')\n") % os.path.join(root, "dropin")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0 and "dropin ok" in out.stdout, out.stdout + out.stderr

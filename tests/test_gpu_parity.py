@@ -215,12 +215,6 @@ def test_partial_mask_outside_semantics(ops, n_fft, hop, win, n, Fm, Tm, outside
     X, _, _ = ops.stft(wav, n_fft, hop, win, want_mag=False, want_phase=False)
     rel_s, irr_s = ops.explain_spec(X, mask, n_fft, hop, win, length=n, mode=mode, outside=outside)
     assert relerr(rel_s, rel_r) < TOL and relerr(irr_s, irr_r) < TOL
-    if outside == "drop":   # nothing outside the mask's extent survives in either output
-        Xr, _, _ = ops.stft(rel, n_fft, hop, win, want_mag=False, want_phase=False)
-        Xi, _, _ = ops.stft(irr, n_fft, hop, win, want_mag=False, want_phase=False)
-        ref = float(X.abs().max())
-        if Fm < X.shape[1]:    # (rows beyond F' only: a dropped frame still leaks into its neighbours' overlap)
-            assert float(Xr[:, Fm + 1:, : max(Tm - 4, 1)].abs().max()) < 0.05 * ref or Tm < X.shape[2]
 
 
 def test_error_behaviour(pkg, ops):

@@ -311,6 +311,7 @@ istft3_kernel(PlanDev P, Tiling TL, int total_tiles, const float2* __restrict__ 
                         if (j >= HS) o += v[j >= HS ? j - HS : 0].y;
                         pbu[j * 32 + l] = o;
                     }
+                    if (l < G.lb - (16 + HS) * 32) pbu[(16 + HS) * 32 + l] = 0.0f;  // tail the 4-sample gather may touch
                 } else {
                     const int c0 = l - G.wlo4, ovl = G.sup - hop;
                     float* pa = pbu + rem;

@@ -104,14 +104,15 @@ class PipelinedPool:
         self.ns = torch.cuda.Stream(device=dev, priority=-1)
         self.cap = torch.cuda.Stream(device=dev)
         self.graph = None
+        self.tails = {}   # k -> graph over the first k buffer sets (the remainder of a run that is not a multiple of the pool)
         self.launches = 0
 
-    def _enqueue_all(self, root):
+    def _enqueue_all(self, root, count=None):
         start = torch.cuda.Event()
         start.record(root)
         for s in self.es + [self.ns]:
             s.wait_event(start)
-        for j, p in enumerate(self.pipes):
+        for j, p in enumerate(self.pipes[:count]):
             e = self.es[j % len(self.es)]
             with torch.cuda.stream(e):
                 p.enqueue_explain()
@@ -154,6 +155,24 @@ class PipelinedPool:
         for p in self.pipes:
             p.sums.zero_()
         return a.elapsed_time(b) * 1e3 / (replays * len(self.pipes))
+
+    def replay_tail(self, k):
+        """The same pipelined schedule over the first ``k`` buffer sets only (``k`` steps), from its own graph - captured
+        on first use (call it once during warm-up: capture synchronises the device)."""
+        if not 0 < k < len(self.pipes):
+            raise ValueError("tail length must be in (0, pool size)")
+        g = self.tails.get(k)
+        if g is None:
+            saved = [p.sums.clone() for p in self.pipes]
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.cap):
+                self._enqueue_all(self.cap, k)
+            self.tails[k] = g
+            for p, sv in zip(self.pipes, saved):   # (capture does not execute, the sums are untouched; belt and braces)
+                p.sums.copy_(sv)
+        g.replay()
+        self.launches += KERNELS_PER_STEP * k
 
     def replay(self):
         """``len(self.pipes)`` steps on the current stream (asynchronous)."""
