@@ -224,7 +224,15 @@ class Plan:
             pass
 
 
-_plans = {}
+import collections
+
+# Plans are cached per (geometry, clip length, device) in a bounded LRU: the variable-length callers
+# (hifigan.align_waveforms / band_swapped_waveforms over a corpus of files) would otherwise create - and never
+# free - one device table set per distinct length.  An evicted plan is destroyed when the last
+# caller still holding it lets go (Plan.__del__), never while a launch that uses it is being issued.
+PLAN_CACHE_SIZE = int(os.environ.get("ADV_PLAN_CACHE", "64"))
+_plans = collections.OrderedDict()
+_plans_lock = threading.Lock()
 
 
 def get_plan(n_fft, hop, win_length, window, n_frames, n_in, n_out):
@@ -234,7 +242,19 @@ def get_plan(n_fft, hop, win_length, window, n_frames, n_in, n_out):
         window = window.detach().float().cpu().numpy() if hasattr(window, "detach") else window
         wkey = window.tobytes()
     key = (n_fft, hop, win_length, wkey, n_frames, n_in, n_out, torch.cuda.current_device())
-    p = _plans.get(key)
-    if p is None:
-        p = _plans[key] = Plan(n_fft, hop, win_length, window, n_frames, n_in, n_out)
+    with _plans_lock:
+        p = _plans.get(key)
+        if p is not None:
+            _plans.move_to_end(key)
+            return p
+    p = Plan(n_fft, hop, win_length, window, n_frames, n_in, n_out)
+    with _plans_lock:
+        _plans[key] = p
+        while len(_plans) > max(1, PLAN_CACHE_SIZE):
+            _plans.popitem(last=False)
     return p
+
+
+def plan_cache_info():
+    """(entries, capacity) of the plan cache."""
+    return len(_plans), PLAN_CACHE_SIZE
