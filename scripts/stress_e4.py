@@ -1,0 +1,48 @@
+"""Race hunt for the streaming explain kernel: many launches over a pool of inputs, each result compared BITWISE with the
+first result for the same input (the kernel is deterministic by construction), under varying co-running load."""
+import importlib, sys, os, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pkg = importlib.import_module("xai-audio-deepfakes_b200"); ops = pkg.ops
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+g = torch.Generator(device="cuda").manual_seed(1)
+bad_total = 0
+for hop, B, n in [(128, 64, 64000), (160, 64, 64000), (256, 64, 64000), (160, 7, 30000), (128, 200, 8000)]:
+    T = 1 + n // hop
+    pool = [(0.1 * torch.randn(B, n, generator=g, device="cuda"), torch.rand(B, 257, T, generator=g, device="cuda")) for _ in range(4)]
+    tiles = ops.explain_tiles(512, hop, 512, n, B, length=n)
+    ref = []
+    for w, m in pool:
+        out = (torch.empty(B, n, device="cuda"), torch.empty(B, n, device="cuda"), torch.empty(B, tiles, 4, dtype=torch.float64, device="cuda"))
+        ops.explain(w, m, 512, hop, 512, length=n, out=out)
+        ref.append(out)
+    side = torch.cuda.Stream()
+    junk = torch.empty(64 << 20, device="cuda")
+    bad = 0
+    for it in range(iters):
+        k = it % 4
+        out = (torch.empty(B, n, device="cuda"), torch.empty(B, n, device="cuda"), torch.empty(B, tiles, 4, dtype=torch.float64, device="cuda"))
+        if it % 3 == 1:   # a co-running memory-bound kernel on another stream perturbs the timing
+            with torch.cuda.stream(side):
+                junk.add_(1.0)
+        ops.explain(pool[k][0], pool[k][1], 512, hop, 512, length=n, out=out)
+        if not (torch.equal(out[0], ref[k][0]) and torch.equal(out[1], ref[k][1]) and torch.equal(out[2], ref[k][2])):
+            bad += 1
+            d = (out[0] - ref[k][0]).abs()
+            idx = torch.nonzero(d > 0)
+            print("MISMATCH hop", hop, "B", B, "iter", it, "n_bad", idx.shape[0], "first", idx[0].tolist() if idx.numel() else None,
+                  "last", idx[-1].tolist() if idx.numel() else None, "irr bad", int(((out[1] - ref[k][1]).abs() > 0).sum()))
+            if bad <= 3 and idx.numel():
+                b0, s0 = idx[0].tolist()
+                s0 = s0 // 32 * 32
+                scale = float(ref[k][0][b0].abs().max())
+                rows = []
+                for r in range(-2, 24):
+                    seg_ = slice(max(0, s0 + 32 * r), max(0, s0 + 32 * r + 32))
+                    rows.append("%.1e/%.1e" % (float(d[b0, seg_].max()) / scale if seg_.stop > seg_.start else 0.0,
+                                               float((out[1] - ref[k][1]).abs()[b0, seg_].max()) / scale if seg_.stop > seg_.start else 0.0))
+                print("   per-row max |diff|/max (rel/irr), rows -2..23 from the first bad row:", " ".join(rows))
+                print("   stats diff:", (out[2] - ref[k][2]).abs().sum(dim=(1, 2)).nonzero().flatten().tolist())
+    torch.cuda.synchronize()
+    print("hop", hop, "B", B, "n", n, "iters", iters, "mismatches", bad)
+    bad_total += bad
+print("TOTAL MISMATCHES", bad_total)

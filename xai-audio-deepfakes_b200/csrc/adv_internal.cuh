@@ -52,6 +52,11 @@ int launch_istft3(const adv_plan* p, const float2* X, int64_t sb, int64_t st, in
 int launch_explain3(const adv_plan* p, const float* wav, int64_t wav_stride, const float2* X, int64_t sb, int64_t st,
                     int64_t sf, const float* mask, int Fm, int Tm, int mode, int batch, float* rel, float* irr,
                     double* stats, cudaStream_t s);
+// generation-4 streaming explain kernel (transform4_kernels.cu): n_fft 512, rectangular full window, hop 128 / 160 / 256,
+// waveform input.  explain4_slots(): statistics slots per clip of such a launch, 0 when the plan is outside its domain.
+int launch_explain4(const adv_plan* p, const float* wav, int64_t wav_stride, const float* mask, int Fm, int Tm,
+                    int mode_flags, int batch, float* rel, float* irr, double* stats, cudaStream_t s);
+int explain4_slots(const adv_plan* p, int batch);
 int istft3_frames_cap(const adv_plan* p);    // 32 when launch_istft3 takes the plan, else 0 (plan default)
 bool istft_balanced();  // tiling policy of the stand-alone iSTFT kernels (ADV_ISTFT_BALANCED=1 selects the round-balanced tile length; default: longest tile)
 int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,

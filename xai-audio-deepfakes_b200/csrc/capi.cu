@@ -243,7 +243,8 @@ int adv_plan_bins(const adv_plan* plan) { return plan ? plan->d.n_fft / 2 + 1 : 
 int adv_plan_frames(const adv_plan* plan) { return plan ? plan->d.T : ADV_ERR_INVALID; }
 int adv_plan_tiles(const adv_plan* plan, int batch) {
     if (!plan || batch <= 0 || plan->d.n_out <= 0) return ADV_ERR_INVALID;
-    return choose_tiling(plan, batch, 1).tiles;
+    const int s4 = explain4_slots(plan, batch);   // statistics slots per clip of the generation-4 explain kernel
+    return s4 > 0 ? s4 : choose_tiling(plan, batch, 1).tiles;
 }
 int adv_plan_tiles_istft(const adv_plan* plan, int batch) {
     if (!plan || batch <= 0 || plan->d.n_out <= 0) return ADV_ERR_INVALID;

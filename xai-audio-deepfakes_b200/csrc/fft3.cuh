@@ -237,11 +237,16 @@ template <bool VEC> struct X {
 #ifdef __CUDACC__
 // Device-side composition.  `tw` = the shared-memory copy of the plan's generation-3 table, `scr` = the warp's private
 // scratch (Scr<VEC>::FLOATS floats).  Both begin with a __syncwarp so that a previous exchange has been fully read.
-template <bool VEC>
-__device__ __forceinline__ void fft_forward(float2* v, int l, const float2* tw, float* scr) {
+// `after_inputs_consumed()` runs once every lane of the warp has USED all 16 of its input values (stage A reads them
+// all, the warp sync joins the lanes): the place to let an asynchronous copy overwrite the buffer the inputs were
+// loaded from.  A sync alone does not do that - a shared-memory load may still be queued when the next instruction
+// issues - and a bulk copy landing before a queued load was seen on B200 as one stale 32-sample row per ~4000 units.
+template <bool VEC, class Hook>
+__device__ __forceinline__ void fft_forward(float2* v, int l, const float2* tw, float* scr, Hook&& after_inputs_consumed) {
     using E = X<VEC>;
     fwd_a(v, l, tw);
     __syncwarp();
+    after_inputs_consumed();
     E::x1_store_cols(v, l, scr, false);
     __syncwarp();
     E::x1_load_rows(v, l, scr, false);
@@ -263,6 +268,10 @@ __device__ __forceinline__ void fft_forward(float2* v, int l, const float2* tw, 
         E::x2_load_cols(v, l, scr, true);
     }
     fwd_c(v);
+}
+template <bool VEC>
+__device__ __forceinline__ void fft_forward(float2* v, int l, const float2* tw, float* scr) {
+    fft_forward<VEC>(v, l, tw, scr, [] {});
 }
 template <bool VEC>
 __device__ __forceinline__ void fft_inverse(float2* v, int l, const float2* tw, float* scr) {

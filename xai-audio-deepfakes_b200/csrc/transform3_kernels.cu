@@ -105,8 +105,7 @@ stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int t
         const int cur_b = b, fa = t0, cur_shift = shift;
         const bool active = first + it * stride + w < total_items;
         const bool more = it + 1 < n_iter;  // (CTA-uniform)
-        auto request_next = [&]() {
-            __syncwarp();  // every lane holds its samples: the slice buffer is free for the next item
+        auto request_next = [&]() {   // (called from inside the forward transform: every lane has consumed its samples)
             if (more) {
                 item = min(first + (it + 1) * stride + w, total_items - 1);
                 b = item / items_per_clip;
@@ -126,8 +125,7 @@ stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int t
                     v[j] = make_float2(sa[32 * j] * ww, sb[32 * j] * ww);
                 }
             }
-            request_next();
-            f3::fft_forward<VEC>(v, l, tw_s, my);
+            f3::fft_forward<VEC>(v, l, tw_s, my, request_next);
             float2 xa[9], xb[9];
             f3::split(v, l, xa, xb);
 #pragma unroll
@@ -159,9 +157,8 @@ stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int t
                         }
                     }
                 }
-                if (half == 1) request_next();
                 const int t = fa + half;
-                f3::fft_forward<VEC>(v, l, tw_s, my);
+                f3::fft_forward<VEC>(v, l, tw_s, my, [&] { if (half == 1) request_next(); });
                 float2 xk[9], xm[9];
                 f3::r1024_post(v, l, tw_s, xk, xm);
                 if (active && t < P.T) {
@@ -577,6 +574,7 @@ explain3_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restrict__
             }
         }
         const int next = tile + gridDim.x;
+        if constexpr (!FROM_SPEC) __threadfence_block();  // the sample loads above have returned (a barrier alone does not wait for them)
         __syncthreads();  // every thread holds its samples: the segment buffer is free
         if (next < total_tiles) {
             b = next / TL.tiles;

@@ -1,0 +1,506 @@
+// Generation-4 fused explain kernel for sm_100a: STFT -> mask / (1 - mask) -> 2 x iSTFT as a STREAMING, barrier-free
+// pipeline of warps (reference call sites: LMAC_metrics.py:136-157 log1p, loss_function.py:36-47 linear).
+//
+// What the ncu captures of the generation-3 kernel (profiles/r02c_*) say bounds it: 50.3 M warp-instructions per
+// 64 clips at 59 % issue utilisation while an SM is busy, and SMs busy only 80 % of the launch:
+//   * tiles of 32 frames deliver 29 hops (halo frames are transformed twice) and 896 tiles on 148 SMs bill 7 rounds
+//     for 6.05 rounds of work;
+//   * two CTA-wide barriers per tile keep the 16 warps of an SM in lock-step phases (LDS/STS bursts, then FMA bursts);
+//   * 39 % of the instructions are FFT work; gains (28 %), the strip gather (13 %) and mask / segment staging and
+//     index arithmetic (20 %) are the rest.
+// Here (n_fft 512, rectangular full window, hop = 32 HS: the benchmark geometry):
+//   * the batch is ONE list of units (unit = two adjacent frames of a clip); CTA c owns a contiguous run of it and walks
+//     it in passes of 16 units, one unit per warp.  No tile halo: a unit's overlap into later samples (its "tail",
+//     16 - HS rows of 32 samples) is handed to the next NB units through shared memory; only the first NB units of a
+//     run that does not begin a clip are transformed for their tails alone (148 x 2 units per launch instead of 10 %);
+//   * overlap-add is register-local: inverse transform 1 carries the masked-in waveforms of frames a and b as real /
+//     imaginary part, transform 2 the masked-out ones; frame b's sample 32 j + l lands on strip row j + HS of the SAME
+//     lane.  A unit's first 2 HS rows ("head") are final once the tails of units u-1 .. u-NB are added - they go from
+//     registers straight to global memory (128-byte rows); no strips, no gather pass, no index search;
+//   * every hand-off is an mbarrier between the warps concerned (tail full / empty per unit slot, per-warp waveform
+//     slices by bulk-async copy, the double-buffered mask tile by cp.async + mbarrier.arrive.noinc): there is NO
+//     CTA-wide barrier in steady state and the warps drift apart, so one warp's shared-memory exchange overlaps
+//     another's butterflies;
+//   * gains: MUFU .approx.ftz forms without the denormal fix-ups, the small-magnitude series only where a frame has
+//     such a bin (warp vote), out-of-mask handling hoisted out of the bin loop.
+// Normaliser statistics: every warp keeps (sum, sum of squares) of what it stores per clip and writes them to slot
+// (CTA's rank among the CTAs touching the clip) * 16 + warp of stats[B][slots][4]; unused slots are zeroed, the fold
+// order of the normaliser stays fixed (bit-reproducible run to run).
+#include "transform_common.cuh"
+#include "fft3.cuh"
+
+namespace adv {
+
+template <int HS>
+struct E4Cfg {
+    static constexpr int UNITS = 16, NT = 512, F = 257, MP = 33;
+    static constexpr int HOP = 32 * HS, USTEP = 2 * HOP;
+    static constexpr int ROWS = 16 + HS;                  // strip rows (32 samples each) of a unit: frame a, frame b HS rows later
+    static constexpr int HEAD = 2 * HS;                   // rows a unit owns (its two hops)
+    static constexpr int TAIL = ROWS - HEAD;              // rows handed to later units
+    static constexpr int NB = (TAIL + HEAD - 1) / HEAD;   // earlier units reaching into a unit's head
+    static constexpr int SEG = (HOP + 512 + 8 + 3) & ~3;  // floats of a warp's waveform slice
+    static constexpr int MASK_TILE = (F * MP + 3) & ~3;
+    static constexpr int NBARS = 3 * UNITS + 4;
+    static_assert(TAIL > 0 && HEAD <= 16 && NB >= 1 && NB <= 2, "hop must be 128, 160 or 256");
+    static size_t bytes() {
+        return al16(sizeof(float2) * TW3N) + al16(sizeof(float) * UNITS * f3::Scr<false>::FLOATS) +
+               al16(sizeof(float) * UNITS * 2 * TAIL * 32) + al16(sizeof(float) * UNITS * SEG) +
+               2 * al16(sizeof(float) * MASK_TILE) + al16(sizeof(uint64_t) * NBARS);
+    }
+    static constexpr int TW3N = f3::TW1024_OFF;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the executing thread's earlier cp.async copies arrive on `bar` when they have landed (no pending-count increment:
+// the barrier's expected count includes one such arrival per thread)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// er = expm1(m log1p(a)) through MUFU (a >= 1/16) - see mask_gains() in transform_common.cuh for the error analysis
+__device__ __forceinline__ float er_mufu(float a, float m) { return ex2_approx(m * lg2_approx(1.0f + a)) - 1.0f; }
+__device__ __forceinline__ float er_series(float a, float m) {
+    float L = fmaf(a, -1.0f / 6.0f, 0.2f);
+    L = fmaf(-a, L, 0.25f);
+    L = fmaf(-a, L, 1.0f / 3.0f);
+    L = fmaf(-a, L, 0.5f);
+    L = fmaf(-a, L, 1.0f);
+    const float y = m * (L * a);
+    float e = fmaf(y, 1.0f / 120.0f, 1.0f / 24.0f);
+    e = fmaf(y, e, 1.0f / 6.0f);
+    e = fmaf(y, e, 0.5f);
+    e = fmaf(y, e, 1.0f);
+    return y * e;
+}
+
+// One frame: one-sided spectrum x[9] (slot layout of fft3.cuh) and its mask column -> masked-in / masked-out spectra.
+template <int MODE>
+__device__ __forceinline__ void frame_gains(const float2* x, const float* m, float2* yr, float2* yi) {
+    if constexpr (MODE == ADV_MASK_LINEAR) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const float gi = 1.0f - m[i];
+            yr[i] = make_float2(x[i].x * m[i], x[i].y * m[i]);
+            yi[i] = make_float2(x[i].x * gi, x[i].y * gi);
+        }
+    } else {
+        float a[9], ia[9], amin = 1.0f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const float r2 = fmaxf(fmaf(x[i].x, x[i].x, x[i].y * x[i].y), 1e-30f);
+            ia[i] = rsqrt_ftz(r2);
+            a[i] = r2 * ia[i];
+            amin = fminf(amin, a[i]);
+        }
+        float er[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) er[i] = er_mufu(a[i], m[i]);
+        if (__any_sync(0xffffffffu, amin < 0.0625f)) {  // (warp-uniform) some bin of the frame needs the series
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const float es = er_series(a[i], m[i]);
+                er[i] = a[i] < 0.0625f ? es : er[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const float ei = (a[i] - er[i]) * rcp_ftz(1.0f + er[i]);
+            const float gr = er[i] * ia[i], gi = ei * ia[i];
+            yr[i] = make_float2(x[i].x * gr, x[i].y * gr);
+            yi[i] = make_float2(x[i].x * gi, x[i].y * gi);
+        }
+    }
+}
+
+struct UnitPos {   // position of a unit in the batch-wide unit list
+    int b, u;      // clip, unit inside the clip
+    __device__ __forceinline__ void advance(int step, int upc) {
+        u += step;
+        while (u >= upc) { u -= upc; ++b; }
+    }
+};
+
+template <int MODE, int HS>
+__global__ void __launch_bounds__(512, 1)
+explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ wav, int64_t wav_stride,
+                const float* __restrict__ mask, int Fm, int Tm, int drop, float* __restrict__ rel, float* __restrict__ irr,
+                double* __restrict__ stats, int slots) {
+    using C = E4Cfg<HS>;
+    constexpr int UNITS = C::UNITS, NT = C::NT, F = C::F, MP = C::MP, HOP = C::HOP, USTEP = C::USTEP;
+    constexpr int ROWS = C::ROWS, HEAD = C::HEAD, TAIL = C::TAIL, NB = C::NB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(C::TW3N);
+    float* scratch = cv.take<float>(UNITS * f3::Scr<false>::FLOATS);
+    float* tails = cv.take<float>(UNITS * 2 * TAIL * 32);
+    float* seg_all = cv.take<float>(UNITS * C::SEG);
+    float* mask_all = cv.take<float>(2 * C::MASK_TILE);
+    uint64_t* bars = cv.take<uint64_t>(C::NBARS);
+    uint64_t* full = bars;                 // [16] tail of unit slot w written (1 arrival per pass)
+    uint64_t* empty = bars + UNITS;        // [16] tail of unit slot w read by its NB consumers
+    uint64_t* segbar = bars + 2 * UNITS;   // [16] waveform slice of warp w landed
+    uint64_t* mfull = bars + 3 * UNITS;    // [2]  mask tile landed (512 cp.async arrivals)
+    uint64_t* mempty = mfull + 2;          // [2]  mask tile read by all 16 warps
+
+    const int tid = threadIdx.x, l = tid & 31;
+    const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);  // (tells the compiler the warp index is warp-uniform)
+
+    // this CTA's run of the unit list: [g_begin, g_end), preceded by `halo` units transformed for their tails only
+    const long G = gridDim.x;
+    const int g_begin = (int)(((long)blockIdx.x * total_units) / G);
+    const int g_end = (int)(((long)(blockIdx.x + 1) * total_units) / G);
+    const int b0 = g_begin / upc, u0 = g_begin - b0 * upc;
+    const int halo = u0 < NB ? u0 : NB;
+    const int start = g_begin - halo;
+    const int n_pass = (g_end - start + UNITS - 1) / UNITS;
+    const int T_eff = drop ? (Tm < P.T ? Tm : P.T) : P.T;  // frames past the mask are dropped from both outputs
+    const int f_lim = drop ? Fm : F;
+
+    if (tid == 0) {
+        for (int i = 0; i < UNITS; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, NB);
+            mbar_init(segbar + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(mfull + i, NT);
+            mbar_init(mempty + i, UNITS);
+        }
+    }
+    for (int i = tid; i < C::TW3N / 2; i += NT) cp_async16(tw_s + 2 * i, P.tw3 + 2 * i);
+    cp_async_commit();
+    pdl_launch_dependents();
+    cp_async_wait_all();
+    __syncthreads();  // tables staged, barriers initialised (the only CTA-wide barrier of the kernel)
+    pdl_wait();
+
+    // ---- statistics slots: zero this warp's slot of every clip the run touches; the first CTA of a clip also zeroes
+    // the slots no CTA owns
+    if (stats != nullptr && g_end > g_begin) {
+        const int b_last = (g_end - 1) / upc;
+        for (int b = b0; b <= b_last; ++b) {
+            const long gb = (long)b * upc;
+            const int c_first = (int)(((gb + 1) * G - 1) / total_units);
+            const int c_last = (int)(((gb + upc) * G - 1) / total_units);
+            double* row = stats + (size_t)b * slots * 4;
+            if (l < 4) row[(((int)blockIdx.x - c_first) * UNITS + w) * 4 + l] = 0.0;
+            if ((int)blockIdx.x == c_first)
+                for (int i = (c_last - c_first + 1) * UNITS * 4 + tid; i < slots * 4; i += NT) row[i] = 0.0;
+        }
+    }
+
+    float* my = scratch + w * f3::Scr<false>::FLOATS;
+    float* seg = seg_all + w * C::SEG;
+    float* tail_w = tails + w * (2 * TAIL * 32);
+    const int q1 = l == 0 ? 32 : 64 - l;
+    constexpr int seglen = HOP + 512;
+
+    // ---- per-thread mask staging: column c of the tile <-> frame (c & 1) of unit slot c >> 1; rows f0 + 16 k
+    const int mc = tid & 31, mf0 = tid >> 5;
+    UnitPos mpos{b0, u0};           // unit of this thread's mask column in the pass being requested
+    {
+        int g = start + (mc >> 1);  // may precede g_begin (halo units have mask columns too)
+        mpos.b = g / upc;
+        mpos.u = g - mpos.b * upc;
+    }
+    auto request_mask = [&](int pass, float* dst_tile) {
+        const int g = start + pass * UNITS + (mc >> 1);
+        const int t = 2 * mpos.u + (mc & 1);
+        const bool col_ok = g < g_end && t < Tm;
+        const float* mrow = mask + (size_t)mpos.b * Fm * Tm;
+        const float* src = col_ok ? mrow + (size_t)mf0 * Tm + t : mask;
+        const size_t step = col_ok ? (size_t)16 * Tm : 0;
+        uint32_t dst = smem_u32(dst_tile + mf0 * MP + mc);
+        const int full_rows = col_ok ? (Fm - mf0 + 15) / 16 : 0;   // trips whose row exists in the mask
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int sz = k < full_rows ? 4 : 0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + k * 16 * MP * 4), "l"(src), "r"(sz) : "memory");
+            src += step;
+        }
+        if (mf0 == 0) {  // row 256
+            const int sz = 16 < full_rows ? 4 : 0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 256 * MP * 4), "l"(src), "r"(sz) : "memory");
+        }
+        cp_async_arrive_noinc(mfull + (pass & 1));
+        mpos.advance(UNITS, upc);
+    };
+
+    // ---- this warp's unit, pass by pass
+    UnitPos pos;
+    {
+        const int g = start + w;
+        pos.b = g / upc;
+        pos.u = g - pos.b * upc;
+    }
+    auto request_seg = [&](const UnitPos& q, bool live) -> int {
+        // (a unit past the run still arms the barrier: zero-byte request)
+        const int base = 2 * q.u * HOP - 256;
+        if (live) return stage_segment_async<32>(seg, seglen, wav + (size_t)q.b * wav_stride, base, P.n_in, segbar + w, l);
+        if (l == 0) mbar_expect_tx(segbar + w, 0);
+        return 0;
+    };
+
+    request_mask(0, mask_all);
+    int shift = request_seg(pos, start + w < g_end);
+
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};   // (sum, sum sq) of rel, irr stored by this lane for clip acc_b
+    int acc_b = -1;
+    auto flush = [&]() {   // warp-uniform call sites
+        double q[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = warp_sum((double)acc[i]);
+        if (stats != nullptr && acc_b >= 0 && l == 0) {
+            const int c_first = (int)((((long)acc_b * upc + 1) * G - 1) / total_units);
+            double* row = stats + ((size_t)acc_b * slots + ((int)blockIdx.x - c_first) * UNITS + w) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) row[i] = q[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = 0.f;
+    };
+
+    for (int p = 0; p < n_pass; ++p) {
+        const int g = start + p * UNITS + w;
+        const bool active = g < g_end;
+        const bool is_out = active && g >= g_begin;
+        const UnitPos cur = pos;
+        const int cur_shift = shift;
+        const int fa = 2 * cur.u;
+
+        // -- 1. samples of frames a (real part) and b (imaginary part)
+        float2 v[16], vi[16];
+        __syncwarp();
+        mbar_wait(segbar + w, p & 1);
+        if (active) {
+            const float* sa = seg + cur_shift + l;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = make_float2(sa[32 * j], sa[HOP + 32 * j]);
+            if (fa + 1 >= T_eff) {   // (warp-uniform, last unit of a clip) frames that do not exist / are dropped
+                const bool ka = fa < T_eff;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = make_float2(ka ? v[j].x : 0.f, 0.f);
+            }
+        } else {   // a unit past the end of the run (last pass only): transformed as silence, nothing stored.  No branch
+                   // encloses the transforms: a thread-index-derived condition around a __syncwarp() costs a WARPSYNC /
+                   // ENDCOLLECTIVE sequence per sync even when it is warp-uniform.
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
+        }
+        pos.advance(UNITS, upc);
+
+        {
+            // -- 2. forward transform, both frames at once
+            //    (the next pass's slice is requested from inside the transform, once every lane has consumed its samples)
+            f3::fft_forward<false>(v, l, tw_s, my, [&] { if (p + 1 < n_pass) shift = request_seg(pos, g + UNITS < g_end); });
+            float2 xa[9], xb[9];
+            f3::split(v, l, xa, xb);
+            if (f_lim < F) {   // (uniform) outside="drop" with a mask narrower than the spectrum
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    const int bin = i < 4 ? l + 64 * i : (i < 8 ? q1 + 64 * (i - 4) : 256);
+                    if (bin >= f_lim) xa[i] = xb[i] = make_float2(0.f, 0.f);
+                }
+            }
+            // -- 3. mask columns of the two frames, gains, the two inverse-transform inputs
+            const float* mask_s = mask_all + (p & 1) * C::MASK_TILE;
+            mbar_wait(mfull + (p & 1), (p >> 1) & 1);
+            float ma[9], mb[9];
+            {
+                const float* p0 = mask_s + l * MP + 2 * w;
+                const float* p1 = mask_s + q1 * MP + 2 * w;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ma[i] = p0[64 * MP * i];
+                    mb[i] = p0[64 * MP * i + 1];
+                    ma[4 + i] = p1[64 * MP * i];
+                    mb[4 + i] = p1[64 * MP * i + 1];
+                }
+                ma[8] = mask_s[256 * MP + 2 * w];
+                mb[8] = mask_s[256 * MP + 2 * w + 1];
+            }
+            float2 yra[9], yia[9], yrb[9], yib[9];
+            frame_gains<MODE>(xa, ma, yra, yia);
+            frame_gains<MODE>(xb, mb, yrb, yib);
+            f3::merge(v, l, yra, yrb);    // masked-in:  Z = Ya + i Yb
+            f3::merge(vi, l, yia, yib);   // masked-out
+        }
+        __syncwarp();
+        if (l == 0) mbar_arrive(mempty + (p & 1));
+        // -- 4. this thread's share of the next pass's mask tile (its buffer was last read in pass p - 1)
+        if (p + 1 < n_pass) {
+            if (p >= 1) mbar_wait(mempty + ((p + 1) & 1), ((p - 1) >> 1) & 1);
+            request_mask(p + 1, mask_all + ((p + 1) & 1) * C::MASK_TILE);
+        }
+
+        // -- 5. inverse transforms; overlap-add of the unit's two frames in registers: strip row r (32 samples, lane l)
+        //       = frame a row r (r < 16) + frame b row r - HS (r >= HS).  Rows < HEAD stay in registers, the tail rows go
+        //       to shared memory for the next NB units.
+        float head_r[HEAD], head_i[HEAD];
+        if (p >= 1) mbar_wait(empty + w, (p - 1) & 1);   // the previous pass's tail of this slot has been consumed
+        {
+            f3::fft_inverse<false>(v, l, tw_s, my);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                float o = r < 16 ? v[r < 16 ? r : 0].x : 0.0f;
+                if (r >= HS) o += v[r >= HS ? r - HS : 0].y;
+                if (r < HEAD) head_r[r < HEAD ? r : 0] = o;
+                else tail_w[(r - HEAD) * 32 + l] = o;
+            }
+            f3::fft_inverse<false>(vi, l, tw_s, my);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                float o = r < 16 ? vi[r < 16 ? r : 0].x : 0.0f;
+                if (r >= HS) o += vi[r >= HS ? r - HS : 0].y;
+                if (r < HEAD) head_i[r < HEAD ? r : 0] = o;
+                else tail_w[TAIL * 32 + (r - HEAD) * 32 + l] = o;
+            }
+        }
+        __syncwarp();
+        if (l == 0) mbar_arrive(full + w);
+
+        // reciprocal envelope of the head rows (requested before the waits below)
+        const int s_base = USTEP * cur.u - 256 + l;   // output sample of head row 0
+        float env[HEAD];
+        if (is_out) {
+#pragma unroll
+            for (int r = 0; r < HEAD; ++r) {
+                const int sidx = s_base + 32 * r;
+                env[r] = (sidx >= 0 && sidx < P.n_out) ? __ldg(P.inv_env + sidx) : 0.0f;
+            }
+        }
+
+        // -- 6. tails of the previous NB units (unit slot w - k; the slots before slot 0 belong to the previous pass).
+        //       Farthest neighbour first: the arrival on the nearest slot's `empty` barrier is this warp's last access to
+        //       any tail of the pass.  The waits are unconditional so that barrier phases advance in lock-step.
+#pragma unroll
+        for (int k = NB; k >= 1; --k) {
+            const int slot = (w - k) & (UNITS - 1);
+            const int pp = w >= k ? p : p - 1;
+            {
+                if (pp >= 0) mbar_wait(full + slot, pp & 1);
+                if (is_out && cur.u >= k) {
+                    const float* tn = tails + slot * (2 * TAIL * 32) + l;
+                    constexpr int r0 = 0;
+#pragma unroll
+                    for (int r = (k - 1) * HEAD; r < k * HEAD && r < TAIL; ++r) {
+                        head_r[r - (k - 1) * HEAD + r0] += tn[r * 32];
+                        head_i[r - (k - 1) * HEAD + r0] += tn[TAIL * 32 + r * 32];
+                    }
+                }
+                __syncwarp();
+                if (l == 0 && pp >= 0) mbar_arrive(empty + slot);
+            }
+        }
+
+        // -- 7. scale, statistics, store (rows of 32 consecutive samples: 128-byte stores)
+        if (is_out) {
+            if (cur.b != acc_b) {   // (warp-uniform)
+                if (acc_b >= 0) flush();
+                acc_b = cur.b;
+            }
+            float* rrow = rel + (size_t)cur.b * P.n_out;
+            float* irow = irr + (size_t)cur.b * P.n_out;
+#pragma unroll
+            for (int r = 0; r < HEAD; ++r) {
+                const int sidx = s_base + 32 * r;
+                const float a = head_r[r] * env[r], c = head_i[r] * env[r];   // (env = 0 outside [0, n_out))
+                acc[0] += a;
+                acc[1] = fmaf(a, a, acc[1]);
+                acc[2] += c;
+                acc[3] = fmaf(c, c, acc[3]);
+                if (sidx >= 0 && sidx < P.n_out) {
+                    rrow[sidx] = a;
+                    irow[sidx] = c;
+                }
+            }
+        }
+    }
+    if (acc_b >= 0) flush();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+static bool gen4_enabled() {
+    static const char* e = getenv("ADV_GEN4");   // A/B switch: ADV_GEN4=0 routes the call to the generation-3 kernel
+    static const bool on = !(e && e[0] == '0');
+    return on;
+}
+
+static int sm_count4() {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    static int cache[64] = {0};
+    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev] = n;
+    return n;
+}
+
+struct Run4 { int hs, upc, grid, slots; long total; };
+// geometry of a generation-4 launch (hs = 0: outside the kernel's domain)
+static Run4 plan_run4(const adv_plan* p, int batch) {
+    Run4 r = {0, 0, 0, 0, 0};
+    const PlanDev& d = p->d;
+    if (!gen4_enabled() || d.n_fft != 512 || !d.rect_full || d.n_in <= 0 || d.n_out <= 0 || batch <= 0) return r;
+    if (d.hop != 128 && d.hop != 160 && d.hop != 256) return r;
+    r.upc = (d.n_out + 256 + 2 * d.hop - 1) / (2 * d.hop);   // units whose heads cover every output sample
+    r.total = (long)r.upc * batch;
+    if (r.total > 0x3fffffffL) return r;
+    const long by_work = r.total / 8 > 0 ? r.total / 8 : 1;   // at least 8 units per CTA (2 of a run are halo)
+    r.grid = (int)(by_work < sm_count4() ? by_work : sm_count4());
+    // CTAs that can touch one clip: its first and last unit are upc - 1 apart in a list cut into `grid` equal runs
+    const long span = ((long)(r.upc - 1) * r.grid + r.total - 1) / r.total;
+    r.slots = 16 * (int)(span + 1);
+    r.hs = d.hop / 32;
+    return r;
+}
+
+int explain4_slots(const adv_plan* p, int batch) {
+    const Run4 r = plan_run4(p, batch);
+    return r.hs ? r.slots : 0;
+}
+
+template <int MODE, int HS>
+static int launch_explain4_t(const adv_plan* p, const Run4& r, const float* wav, int64_t wav_stride, const float* mask,
+                             int Fm, int Tm, int drop, float* rel, float* irr, double* stats, cudaStream_t s) {
+    const size_t smem = E4Cfg<HS>::bytes();
+    auto kernel = explain4_kernel<MODE, HS>;
+    int rc = set_smem(kernel, smem);
+    if (rc != ADV_OK) return rc;
+    ADV_CUDA_CHECK(launch_pdl(kernel, r.grid, 512, smem, s, p->d, r.upc, (int)r.total, wav, wav_stride, mask, Fm, Tm, drop,
+                              rel, irr, stats, r.slots));
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int launch_explain4(const adv_plan* p, const float* wav, int64_t wav_stride, const float* mask, int Fm, int Tm,
+                    int mode_flags, int batch, float* rel, float* irr, double* stats, cudaStream_t s) {
+    const Run4 r = plan_run4(p, batch);
+    if (!r.hs || wav == nullptr) return ADV_ERR_UNSUPPORTED;
+    const int mode = mode_flags & 0xff, drop = (mode_flags & ADV_MASK_DROP_OUTSIDE) ? 1 : 0;
+#define ADV_E4(HS)                                                                                                        \
+    return mode == ADV_MASK_LOG1P                                                                                         \
+               ? launch_explain4_t<ADV_MASK_LOG1P, HS>(p, r, wav, wav_stride, mask, Fm, Tm, drop, rel, irr, stats, s)     \
+               : launch_explain4_t<ADV_MASK_LINEAR, HS>(p, r, wav, wav_stride, mask, Fm, Tm, drop, rel, irr, stats, s)
+    if (r.hs == 4) ADV_E4(4);
+    if (r.hs == 5) ADV_E4(5);
+    ADV_E4(8);
+#undef ADV_E4
+}
+
+}  // namespace adv

@@ -193,6 +193,7 @@ stft_p_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int 
         }
         const int cur_b = b, fa = t0 + 2 * u;
         const int next = tile + gridDim.x;
+        __threadfence_block();  // the sample loads have returned: a sync alone does not wait for queued shared-memory loads
         __syncthreads();  // every thread holds its samples: the buffer is free for the next tile
         if (next < total_tiles) {
             b = next / tiles_per_clip;
@@ -320,6 +321,7 @@ stft_w_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int 
         }
         const int cur_b = b, fa = t0 + 2 * uw;
         const int next = item + stride;
+        __threadfence_block();  // the sample loads have returned: a sync alone does not wait for queued shared-memory loads
         __syncwarp();  // every lane holds its samples: the slice buffer is free for the next item
         if (next < total_items) {
             b = next / items_per_clip;
@@ -1308,6 +1310,7 @@ explain_p512_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restri
         const int cur_b = b, cur_tile = tile - b * TL.tiles;
         const TileGeom cg = g;
         const int next = tile + gridDim.x;
+        __threadfence_block();  // the sample loads have returned: a sync alone does not wait for queued shared-memory loads
         __syncthreads();  // every thread holds its samples: the segment buffer is free
         if (next < total_tiles) {
             b = next / TL.tiles;
@@ -1520,6 +1523,7 @@ stft_ww_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int
         }
         const int cur_b = b, fa = t0;
         const int next = item + stride;
+        __threadfence_block();  // the sample loads have returned: a sync alone does not wait for queued shared-memory loads
         __syncwarp();  // every lane holds its samples: the slice buffer is free for the next item
         if (next < total_items) {
             b = next / items_per_clip;
@@ -2035,6 +2039,10 @@ static int launch_explain_wide(const adv_plan* p, const Tiling& tl, const float*
 int launch_explain(const adv_plan* p, const float* wav, int64_t wav_stride, const float2* X, int64_t sb,
                    int64_t st, int64_t sf, const float* mask, int Fm, int Tm, int mode, int batch, float* rel,
                    float* irr, double* stats, cudaStream_t s) {
+    if (explain4_slots(p, batch) > 0) {   // the plan's statistics layout is the generation-4 kernel's (adv_plan_tiles)
+        if (X == nullptr) return launch_explain4(p, wav, wav_stride, mask, Fm, Tm, mode, batch, rel, irr, stats, s);
+        if (stats != nullptr) return ADV_ERR_INVALID;   // spectrum input wants a plan created with n_in = 0
+    }
     {
         const int rc3 = launch_explain3(p, wav, wav_stride, X, sb, st, sf, mask, Fm, Tm, mode, batch, rel, irr, stats, s);
         if (rc3 != ADV_ERR_UNSUPPORTED) return rc3;
