@@ -95,9 +95,11 @@ row_stats4_kernel(const float* __restrict__ in, int n, int parts, double* __rest
 // ---- (x - mean) / (std_unbiased + 1e-7) -----------------------------------------------------------
 // blockIdx.z selects one of up to two arrays that share a stats buffer (the explain kernel's rel / irr
 // outputs: (sum, sumsq) pairs at columns col and col + 2), so both normalisers are one launch.
-// (<= 32 registers: two CTAs fit next to a resident explain CTA, so the normaliser of batch i streams through L2 /
-//  HBM while the issue-bound explain kernel of batch i+1 owns the SMs)
-__global__ void __launch_bounds__(kPwThreads, 8)
+// (<= 32 registers per thread: CTAs of this kernel fit next to a resident explain CTA of generation 2 / 3 - 96
+//  registers x 512 threads - so the normaliser of batch i streams through L2 while the issue-bound explain kernel of
+//  batch i+1 owns the issue slots.  The generation-4 explain kernel takes all registers of an SM, see its register cap.)
+template <int NT>
+__global__ void __launch_bounds__(NT, 2048 / NT)
 normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const float* __restrict__ in1,
                  float* __restrict__ out1, int n, const double* __restrict__ stats, int parts, int width, int col) {
     __shared__ float s_mean, s_den;
@@ -135,24 +137,24 @@ normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const 
         const float4* r4 = reinterpret_cast<const float4*>(row);
         float4* o4 = reinterpret_cast<float4*>(orow);
         constexpr int U = 4;
-        for (int i = lo / 4 + threadIdx.x; i < hi / 4; i += kPwThreads * U) {
+        for (int i = lo / 4 + threadIdx.x; i < hi / 4; i += NT * U) {
             float4 v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (i + u * kPwThreads < hi / 4) v[u] = __ldg(r4 + i + u * kPwThreads);
+                if (i + u * NT < hi / 4) v[u] = __ldg(r4 + i + u * NT);
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (i + u * kPwThreads < hi / 4) {
+                if (i + u * NT < hi / 4) {
                     float4 y;
                     y.x = (v[u].x - mean) * inv;
                     y.y = (v[u].y - mean) * inv;
                     y.z = (v[u].z - mean) * inv;
                     y.w = (v[u].w - mean) * inv;
-                    o4[i + u * kPwThreads] = y;
+                    o4[i + u * NT] = y;
                 }
         }
     } else {
-        for (int i = lo + threadIdx.x; i < hi; i += kPwThreads) orow[i] = (__ldg(row + i) - mean) * inv;
+        for (int i = lo + threadIdx.x; i < hi; i += NT) orow[i] = (__ldg(row + i) - mean) * inv;
     }
 }
 
@@ -682,16 +684,23 @@ int adv_normalize(const float* in, float* out, int batch, int n, const double* s
     if (!in || !out || !stats || batch <= 0 || n <= 1 || parts <= 0 || width < 2 || col < 0 || col + 2 > width)
         return ADV_ERR_INVALID;
     const int chunks = (n + kRowChunk - 1) / kRowChunk;
-    ADV_CUDA_CHECK(launch_pdl(normalize_kernel, dim3(chunks, batch, 1), dim3(kPwThreads), 0, (cudaStream_t)stream, in, out,
-                              in, out, n, stats, parts, width, col));
+    ADV_CUDA_CHECK(launch_pdl(normalize_kernel<kPwThreads>, dim3(chunks, batch, 1), dim3(kPwThreads), 0, (cudaStream_t)stream,
+                              in, out, in, out, n, stats, parts, width, col));
     return ADV_OK;
 }
 
 int adv_normalize_pair(float* rel, float* irr, int batch, int n, const double* stats, int parts, void* stream) {
     if (!rel || !irr || !stats || batch <= 0 || n <= 1 || parts <= 0) return ADV_ERR_INVALID;
     const int chunks = (n + kRowChunk - 1) / kRowChunk;
-    ADV_CUDA_CHECK(launch_pdl(normalize_kernel, dim3(chunks, batch, 2), dim3(kPwThreads), 0, (cudaStream_t)stream, rel, rel,
-                              irr, irr, n, stats, parts, 4, 0));
+    // 256-thread CTAs by default; ADV_NORM_THREADS=128 selects 128-thread CTAs (one fits next to an explain kernel
+    // capped at 120 registers - measured: the cap costs the explain kernel more than the overlap returns)
+    static const char* nt_env = getenv("ADV_NORM_THREADS");
+    if (nt_env && nt_env[0] == '1')
+        ADV_CUDA_CHECK(launch_pdl(normalize_kernel<128>, dim3(chunks, batch, 2), dim3(128), 0, (cudaStream_t)stream, rel, rel,
+                                  irr, irr, n, stats, parts, 4, 0));
+    else
+        ADV_CUDA_CHECK(launch_pdl(normalize_kernel<256>, dim3(chunks, batch, 2), dim3(256), 0, (cudaStream_t)stream, rel, rel,
+                                  irr, irr, n, stats, parts, 4, 0));
     return ADV_OK;
 }
 

@@ -884,6 +884,11 @@ static int launch_stft3_t(const adv_plan* p, const float* wav, int64_t wav_strid
 int launch_stft3(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
                  float* phase, int flags, cudaStream_t s) {
     if (!p->gen3 || !gen3_enabled()) return ADV_ERR_UNSUPPORTED;
+    // n_fft 1024: the generation-2 warp-autonomous kernel (a warp per frame, 32 values per lane) measures faster than the
+    // half-size complex transform with its twiddle pass here - 64 x 5 s clips, hop 322: X only 22.4 vs 27.4 us,
+    // X + |X| + angle 39.5 vs 43.4 us (profiles/r02c_kbench_gen3_vs_gen2.jsonl).  ADV_STFT3_1024=1 keeps this kernel.
+    static const char* e1024 = getenv("ADV_STFT3_1024");
+    if (p->d.n_fft == 1024 && !(e1024 && e1024[0] == '1')) return ADV_ERR_UNSUPPORTED;
     const bool vec = stft3_vec();
     if (p->d.n_fft == 512) {
         if (p->d.rect_full)

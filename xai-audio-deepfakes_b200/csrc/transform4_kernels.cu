@@ -41,12 +41,16 @@ struct E4Cfg {
     static constexpr int NB = (TAIL + HEAD - 1) / HEAD;   // earlier units reaching into a unit's head
     static constexpr int SEG = (HOP + 512 + 8 + 3) & ~3;  // floats of a warp's waveform slice
     static constexpr int MASK_TILE = (F * MP + 3) & ~3;
-    static constexpr int NBARS = 3 * UNITS + 4;
+    static constexpr int NBARS = 3 * UNITS + 2;
+    // 64-bit exchanges in the transforms (half the shared-memory instructions of the planar form, and register pairs
+    // arrive aligned for the packed f32x2 butterflies); their 4.6 KB of scratch per warp is paid for by keeping ONE mask
+    // tile: the next tile is requested once all 16 warps have read the current one, a stage and a half ahead of its use
+    static constexpr bool VEC = true;
     static_assert(TAIL > 0 && HEAD <= 16 && NB >= 1 && NB <= 2, "hop must be 128, 160 or 256");
     static size_t bytes() {
-        return al16(sizeof(float2) * TW3N) + al16(sizeof(float) * UNITS * f3::Scr<false>::FLOATS) +
+        return al16(sizeof(float2) * TW3N) + al16(sizeof(float) * UNITS * f3::Scr<VEC>::FLOATS) +
                al16(sizeof(float) * UNITS * 2 * TAIL * 32) + al16(sizeof(float) * UNITS * SEG) +
-               2 * al16(sizeof(float) * MASK_TILE) + al16(sizeof(uint64_t) * NBARS);
+               al16(sizeof(float) * MASK_TILE) + al16(sizeof(uint64_t) * NBARS);
     }
     static constexpr int TW3N = f3::TW1024_OFF;
 };
@@ -133,8 +137,16 @@ struct UnitPos {   // position of a unit in the batch-wide unit list
     }
 };
 
+#ifndef ADV_EXPLAIN4_MAXREG
+// Register cap, measured on B200 (64 x 4 s clips; kernel alone / pooled step with the normaliser and the metric
+// reduction): 128 -> 59.7 / 70.9 us; 120 (leaves room for one 128-thread normaliser CTA per SM, which then overlaps
+// the next batch's explain) -> 63.9 / 72.5 us; 112 (one 256-thread normaliser CTA) -> 68.6 / 76.4 us: below 128 the
+// transforms pay in spills and register-pair moves more than the overlap returns.
+#define ADV_EXPLAIN4_MAXREG 128
+#endif
+
 template <int MODE, int HS>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __maxnreg__(ADV_EXPLAIN4_MAXREG)
 explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ wav, int64_t wav_stride,
                 const float* __restrict__ mask, int Fm, int Tm, int drop, float* __restrict__ rel, float* __restrict__ irr,
                 double* __restrict__ stats, int slots) {
@@ -144,16 +156,16 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Carver cv{smem_raw};
     float2* tw_s = cv.take<float2>(C::TW3N);
-    float* scratch = cv.take<float>(UNITS * f3::Scr<false>::FLOATS);
+    float* scratch = cv.take<float>(UNITS * f3::Scr<C::VEC>::FLOATS);
     float* tails = cv.take<float>(UNITS * 2 * TAIL * 32);
     float* seg_all = cv.take<float>(UNITS * C::SEG);
-    float* mask_all = cv.take<float>(2 * C::MASK_TILE);
+    float* mask_s = cv.take<float>(C::MASK_TILE);
     uint64_t* bars = cv.take<uint64_t>(C::NBARS);
     uint64_t* full = bars;                 // [16] tail of unit slot w written (1 arrival per pass)
     uint64_t* empty = bars + UNITS;        // [16] tail of unit slot w read by its NB consumers
     uint64_t* segbar = bars + 2 * UNITS;   // [16] waveform slice of warp w landed
-    uint64_t* mfull = bars + 3 * UNITS;    // [2]  mask tile landed (512 cp.async arrivals)
-    uint64_t* mempty = mfull + 2;          // [2]  mask tile read by all 16 warps
+    uint64_t* mfull = bars + 3 * UNITS;    // mask tile landed (512 cp.async arrivals per pass)
+    uint64_t* mempty = mfull + 1;          // mask tile read by all 16 warps
 
     const int tid = threadIdx.x, l = tid & 31;
     const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);  // (tells the compiler the warp index is warp-uniform)
@@ -175,10 +187,8 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
             mbar_init(empty + i, NB);
             mbar_init(segbar + i, 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(mfull + i, NT);
-            mbar_init(mempty + i, UNITS);
-        }
+        mbar_init(mfull, NT);
+        mbar_init(mempty, UNITS);
     }
     for (int i = tid; i < C::TW3N / 2; i += NT) cp_async16(tw_s + 2 * i, P.tw3 + 2 * i);
     cp_async_commit();
@@ -202,7 +212,7 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
         }
     }
 
-    float* my = scratch + w * f3::Scr<false>::FLOATS;
+    float* my = scratch + w * f3::Scr<C::VEC>::FLOATS;
     float* seg = seg_all + w * C::SEG;
     float* tail_w = tails + w * (2 * TAIL * 32);
     const int q1 = l == 0 ? 32 : 64 - l;
@@ -216,14 +226,14 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
         mpos.b = g / upc;
         mpos.u = g - mpos.b * upc;
     }
-    auto request_mask = [&](int pass, float* dst_tile) {
+    auto request_mask = [&](int pass) {
         const int g = start + pass * UNITS + (mc >> 1);
         const int t = 2 * mpos.u + (mc & 1);
         const bool col_ok = g < g_end && t < Tm;
         const float* mrow = mask + (size_t)mpos.b * Fm * Tm;
         const float* src = col_ok ? mrow + (size_t)mf0 * Tm + t : mask;
         const size_t step = col_ok ? (size_t)16 * Tm : 0;
-        uint32_t dst = smem_u32(dst_tile + mf0 * MP + mc);
+        uint32_t dst = smem_u32(mask_s + mf0 * MP + mc);
         const int full_rows = col_ok ? (Fm - mf0 + 15) / 16 : 0;   // trips whose row exists in the mask
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
@@ -235,7 +245,7 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
             const int sz = 16 < full_rows ? 4 : 0;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 256 * MP * 4), "l"(src), "r"(sz) : "memory");
         }
-        cp_async_arrive_noinc(mfull + (pass & 1));
+        cp_async_arrive_noinc(mfull);
         mpos.advance(UNITS, upc);
     };
 
@@ -254,7 +264,7 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
         return 0;
     };
 
-    request_mask(0, mask_all);
+    request_mask(0);
     int shift = request_seg(pos, start + w < g_end);
 
     float acc[4] = {0.f, 0.f, 0.f, 0.f};   // (sum, sum sq) of rel, irr stored by this lane for clip acc_b
@@ -305,7 +315,7 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
         {
             // -- 2. forward transform, both frames at once
             //    (the next pass's slice is requested from inside the transform, once every lane has consumed its samples)
-            f3::fft_forward<false>(v, l, tw_s, my, [&] { if (p + 1 < n_pass) shift = request_seg(pos, g + UNITS < g_end); });
+            f3::fft_forward<C::VEC>(v, l, tw_s, my, [&] { if (p + 1 < n_pass) shift = request_seg(pos, g + UNITS < g_end); });
             float2 xa[9], xb[9];
             f3::split(v, l, xa, xb);
             if (f_lim < F) {   // (uniform) outside="drop" with a mask narrower than the spectrum
@@ -316,8 +326,7 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
                 }
             }
             // -- 3. mask columns of the two frames, gains, the two inverse-transform inputs
-            const float* mask_s = mask_all + (p & 1) * C::MASK_TILE;
-            mbar_wait(mfull + (p & 1), (p >> 1) & 1);
+            mbar_wait(mfull, p & 1);
             float ma[9], mb[9];
             {
                 const float* p0 = mask_s + l * MP + 2 * w;
@@ -339,12 +348,7 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
             f3::merge(vi, l, yia, yib);   // masked-out
         }
         __syncwarp();
-        if (l == 0) mbar_arrive(mempty + (p & 1));
-        // -- 4. this thread's share of the next pass's mask tile (its buffer was last read in pass p - 1)
-        if (p + 1 < n_pass) {
-            if (p >= 1) mbar_wait(mempty + ((p + 1) & 1), ((p - 1) >> 1) & 1);
-            request_mask(p + 1, mask_all + ((p + 1) & 1) * C::MASK_TILE);
-        }
+        if (l == 0) mbar_arrive(mempty);   // (the gains above consumed the mask values: the loads have returned)
 
         // -- 5. inverse transforms; overlap-add of the unit's two frames in registers: strip row r (32 samples, lane l)
         //       = frame a row r (r < 16) + frame b row r - HS (r >= HS).  Rows < HEAD stay in registers, the tail rows go
@@ -352,7 +356,7 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
         float head_r[HEAD], head_i[HEAD];
         if (p >= 1) mbar_wait(empty + w, (p - 1) & 1);   // the previous pass's tail of this slot has been consumed
         {
-            f3::fft_inverse<false>(v, l, tw_s, my);
+            f3::fft_inverse<C::VEC>(v, l, tw_s, my);
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 float o = r < 16 ? v[r < 16 ? r : 0].x : 0.0f;
@@ -360,7 +364,7 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
                 if (r < HEAD) head_r[r < HEAD ? r : 0] = o;
                 else tail_w[(r - HEAD) * 32 + l] = o;
             }
-            f3::fft_inverse<false>(vi, l, tw_s, my);
+            f3::fft_inverse<C::VEC>(vi, l, tw_s, my);
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 float o = r < 16 ? vi[r < 16 ? r : 0].x : 0.0f;
@@ -371,6 +375,13 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
         }
         __syncwarp();
         if (l == 0) mbar_arrive(full + w);
+        // -- this thread's share of the next pass's mask tile, once every warp has read the current one (the slowest warp
+        //    finished its gains about two transforms ago; the copy has the rest of this pass and the next forward
+        //    transform to land)
+        if (p + 1 < n_pass) {
+            mbar_wait(mempty, p & 1);
+            request_mask(p + 1);
+        }
 
         // reciprocal envelope of the head rows (requested before the waits below)
         const int s_base = USTEP * cur.u - 256 + l;   // output sample of head row 0

@@ -108,19 +108,30 @@ class PipelinedPool:
         self.launches = 0
 
     def _enqueue_all(self, root, count=None):
+        """``count`` steps (default: one per buffer set); step i runs on buffer set i % len(pipes) - a set that is used
+        again waits for the normaliser / metric reduction of its previous step."""
+        n = len(self.pipes)
+        count = n if count is None else count
         start = torch.cuda.Event()
         start.record(root)
         for s in self.es + [self.ns]:
             s.wait_event(start)
-        for j, p in enumerate(self.pipes[:count]):
-            e = self.es[j % len(self.es)]
+        post_done = {}
+        for i in range(count):
+            p = self.pipes[i % n]
+            e = self.es[i % len(self.es)]
             with torch.cuda.stream(e):
+                if i >= n:
+                    e.wait_event(post_done[i - n])
                 p.enqueue_explain()
                 done = torch.cuda.Event()
                 done.record(e)
             with torch.cuda.stream(self.ns):
                 self.ns.wait_event(done)
                 p.enqueue_post()
+                if i + n < count:
+                    post_done[i] = torch.cuda.Event()
+                    post_done[i].record(self.ns)
         for s in self.es + [self.ns]:
             ev = torch.cuda.Event()
             ev.record(s)
@@ -157,10 +168,11 @@ class PipelinedPool:
         return a.elapsed_time(b) * 1e3 / (replays * len(self.pipes))
 
     def replay_tail(self, k):
-        """The same pipelined schedule over the first ``k`` buffer sets only (``k`` steps), from its own graph - captured
-        on first use (call it once during warm-up: capture synchronises the device)."""
-        if not 0 < k < len(self.pipes):
-            raise ValueError("tail length must be in (0, pool size)")
+        """The same pipelined schedule over exactly ``k`` steps (buffer set i % pool for step i), from its own graph -
+        captured on first use (call it once during warm-up: capture synchronises the device).  Used for the remainder of
+        a run that is not a multiple of the pool and, for short runs, for the whole run (one graph launch)."""
+        if k <= 0:
+            raise ValueError("step count must be positive")
         g = self.tails.get(k)
         if g is None:
             saved = [p.sums.clone() for p in self.pipes]
@@ -219,3 +231,55 @@ class HostFedPipeline:
     @property
     def launches(self):
         return sum(p.launches for p in self.pipes)
+
+
+class WaveFedPipeline:
+    """End-to-end stepping at the reference's own device boundary (LMAC_metrics.py:106,132): only the WAVEFORMS (and the
+    classifier logits) arrive from the host; the mask is produced on the device - here by the U-Net's mask head
+    (``adv_mask_head``: 1x1 conv 32 -> 1 + sigmoid, addvisor.py:57-60,82) from a device-resident decoder activation
+    ``y1`` [B, 32, F', T'] standing in for the (reference, torch) U-Net body - and covers the top-left [F', T'] corner
+    of the spectrum with the reference's crop semantics (``outside="drop"``).  Two buffer sets alternate so that the
+    H2D copy of step i+1 overlaps the kernels of step i."""
+
+    def __init__(self, audio_processor, batch, y1, head_weight, head_bias, mode="log1p"):
+        ap = audio_processor
+        self.ap, self.batch, self.mode = ap, batch, mode
+        self.dev = ops._dev()
+        self.n = int(ap.audio_length * ap.sampling_rate)
+        self.y1, self.hw, self.hb = y1, head_weight, head_bias
+        tiles = ops.explain_tiles(ap.n_fft, ap.hop_length, ap.win_length, self.n, batch, length=self.n)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.sets = []
+        for _ in range(2):
+            d = dict(wav=torch.zeros((batch, self.n), **f32), logits=torch.zeros((3, batch), **f32),
+                     rel=torch.empty((batch, self.n), **f32), irr=torch.empty((batch, self.n), **f32),
+                     stats=torch.empty((batch, tiles, 4), dtype=torch.float64, device=self.dev),
+                     ws=ops.LmacWorkspace(batch, self.dev), copied=torch.cuda.Event(), done=torch.cuda.Event(),
+                     host_sums=torch.empty(6, dtype=torch.float64).pin_memory())
+            d["done"].record()
+            self.sets.append(d)
+        self.copy_stream = torch.cuda.Stream()
+        self.i = 0
+        self.launches = 0
+        self.h2d_bytes = 4 * (batch * self.n + 3 * batch)
+        self.d2h_bytes = 8 * 6
+
+    def step_host(self, wav_pinned, logits_pinned):
+        ap, d = self.ap, self.sets[self.i & 1]
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(d["done"])
+            d["wav"].copy_(wav_pinned, non_blocking=True)
+            d["logits"].copy_(logits_pinned, non_blocking=True)
+            d["copied"].record()
+        main.wait_event(d["copied"])
+        mask = ops.mask_head(self.y1, self.hw, self.hb)
+        ops.explain(d["wav"], mask, ap.n_fft, ap.hop_length, ap.win_length, length=self.n, mode=self.mode, normalize=True,
+                    out=(d["rel"], d["irr"], d["stats"]), outside="drop")
+        ops.lmac(d["logits"][0], d["logits"][1], d["logits"][2], is_logit=True, want_scores=False, workspace=d["ws"])
+        d["host_sums"].copy_(d["ws"].sums, non_blocking=True)
+        d["done"].record(main)
+        self.launches += KERNELS_PER_STEP + 1
+        self.i += 1
+        return d["host_sums"]
+
