@@ -505,7 +505,8 @@ def main():
         fl = H.HifiganGenerator.flops_per_clip(vt) * vb
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] \
             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
-        voc = {"workload": f"HiFi-GAN V1 generator, {vb} x 4 s clips (80 x {vt} mel -> 66816 samples), bf16",
+        voc = {"workload": f"HiFi-GAN V1 generator, {vb} x 4 s clips (80 x {vt} mel -> 66816 samples), bf16, "
+                           f"{'reflect' if H.HifiganConfig.pad_reflect else 'zero'} 'same' padding",
                "clips_per_s": vb / t_v, "tflops": fl / t_v / 1e12, "bound": "tensor", "peak": pk,
                "frac": fl / t_v / 1e12 / pk, "launches_per_batch": n_launch, "reps": voc_reps}
         del gen_v, mel

@@ -197,6 +197,17 @@ int adv_resunit_bf16(const void* x, const void* w1, const float* b1, const void*
 int adv_mel_to_channels_last(const float* mel, int batch, int C, int T, int pad, int Cpad, void* out, void* stream);
 /* MRF average of the three resblock outputs (bf16, n elements), then LeakyReLU(act_slope) (1 = identity) */
 int adv_avg3_bf16(const void* a, const void* b, const void* c, int64_t n, float act_slope, void* out, void* stream);
+/* Halo layout for reflect "same" padding on the TMA conv kernels (SpeechBrain's nnet.CNN.Conv1d default padding_mode,
+ * i.e. what hifi_gan.decode_batch computes at hifigan.py:180): an activation is [B][L + 2 H][C] with its L rows at
+ * offset H; the conv kernels run over all L + 2 H rows with zero padding and adv_halo_fix_bf16 rewrites the halo rows of
+ * a produced tensor in place - mode 1: reflection of the interior (row -j := row j, row L-1+j := row L-1-j), mode 0:
+ * zeros (input of a transposed conv).  C % 8 == 0; mode 1 needs H < L. */
+int adv_halo_fix_bf16(void* buf, int batch, int L, int C, int H, int mode, void* stream);
+/* out interior = LeakyReLU_slope(mean of a [, b [, c]] interiors) (the MRF average of HifiganGenerator.forward, or a
+ * plain re-layout with one input); inputs [B][L + 2 h_in][C], out [B][L + 2 h_out][C] with zero (mode 0) / reflected
+ * (mode 1) halo rows. */
+int adv_avg_relayout_bf16(const void* a, const void* b, const void* c, int batch, int L, int C, int h_in, int h_out, int mode,
+                          float act_slope, void* out, void* stream);
 /* LeakyReLU(slope) -> conv_post (C=32 -> 1, 7 taps, w [taps][C] fp32) -> tanh; out dev float [B][L] */
 int adv_post_conv_tanh(const void* in, const float* w, const float* bias, int batch, int L, int C, int taps, float slope,
                        int pad_reflect, float* out, void* stream);

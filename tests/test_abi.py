@@ -116,3 +116,30 @@ def test_cfg1_fixture_transforms_match_oracle():
     rel, irr = R.explain(wav, mask, outside="keep_irr")
     assert np.array_equal(rel[:, ::8].numpy(), g["full_rel_s"]) and np.array_equal(irr[:, ::8].numpy(), g["full_irr_s"])
     np.testing.assert_allclose(rel.double().sum(dim=1).numpy(), g["full_sums"][0], rtol=1e-12, atol=1e-12)
+
+
+def test_speechbrain_checkpoint_loader_folds_weight_norm():
+    """hifigan.load_speechbrain_state_dict on CPU tensors: ``.conv.`` wrappers stripped, both weight-norm spellings folded"""
+    import importlib
+    import torch
+    H = importlib.import_module("xai-audio-deepfakes_b200").hifigan
+    W = H.init_weights(seed=7, std=0.03)
+    sd = {}
+    for k, v in W.items():
+        name, kind = k.rsplit(".", 1)
+        wrapped = name + ".conv"
+        if kind == "bias":
+            sd[wrapped + ".bias"] = v
+            continue
+        gnorm = torch.linalg.vector_norm(v, dim=[d for d in range(v.dim()) if d != 0], keepdim=True)
+        if name.startswith("resblocks"):
+            sd[wrapped + ".parametrizations.weight.original0"] = gnorm
+            sd[wrapped + ".parametrizations.weight.original1"] = 3.0 * v
+        else:
+            sd[wrapped + ".weight_g"] = gnorm
+            sd[wrapped + ".weight_v"] = 0.5 * v
+    back = H.load_speechbrain_state_dict(sd)
+    assert set(back) == set(W)
+    assert all(torch.allclose(back[k], W[k], rtol=1e-5, atol=1e-7) for k in W)
+    assert H.HifiganConfig.pad_reflect   # SpeechBrain's Conv1d default
+

@@ -215,7 +215,8 @@ def test_mel_against_reference_golden(pkg):
 
 
 @pytest.mark.parametrize("reflect,pipeline,fuse", [(False, "tma", "always"), (False, "tma", "auto"), (False, "tma", "never"),
-                                                   (False, "gather", "never"), (True, "gather", "never")])
+                                                   (False, "gather", "never"), (True, "gather", "never"),
+                                                   (True, "tma", "auto")])
 def test_hifigan_generator_matches_oracle(pkg, H, reflect, pipeline, fuse):
     """Whole generator (61 conv launches), seeded weights.  std 0.03 gives per-layer gains near 1 (the original
     N(0, 0.01^2) init lets biases dominate); larger scales saturate tanh and make the comparison chaotic."""
@@ -233,9 +234,80 @@ def test_hifigan_generator_matches_oracle(pkg, H, reflect, pipeline, fuse):
     # vs the oracle with bf16 storage of activations modelled: tighter
     refq = V.generator(mel, Wq, reflect=reflect, quantize=bf16r)
     assert rel_l2(wav, refq) < 1e-2, rel_l2(wav, refq)
-    if fuse == "always":   # 64- and 32-channel stages: fused residual units (k 11 at 64 channels stays unfused)
+    if reflect and pipeline == "tma":   # halo layout: every conv output that feeds a conv gets its halo rewritten
+        assert gen.launches == 1 + 1 + 4 * (1 + 1 + 18 + 15 + 1)   # conv_pre, relayout, 4 x (up, fix, 18 convs, 15 fixes, average)
+    elif fuse == "always":   # 64- and 32-channel stages: fused residual units (k 11 at 64 channels stays unfused)
         assert gen.launches == 1 + 2 * (1 + 18) + (1 + 3 + 3 + 6) + (1 + 9)
     elif fuse == "auto":   # fused only where four CTAs share an SM: the 3-tap branch of the 32-channel stage
         assert gen.launches == 1 + 3 * (1 + 18) + (1 + 3 + 6 + 6)
     else:
         assert gen.launches == 1 + 4 * (1 + 18)   # conv_pre + 4 x (upsample + 3 resblocks x 3 x 2 convs)
+
+
+
+def test_hifigan_generator_full_length_reflect(pkg, H):
+    """BASELINE configs[2] clip length (251 mel frames = 4 s) through the default (reflect-padded, SpeechBrain's Conv1d)
+    generator on the TMA kernels, 8 clips, against the fp32 oracle and its bf16-storage variant; the gather pipeline
+    (reflection on load, no halo rows) must agree with the halo pipeline."""
+    cfg = H.HifiganConfig
+    assert cfg.pad_reflect
+    W = H.init_weights(cfg, seed=3, std=0.03)
+    g = torch.Generator().manual_seed(4)
+    mel = -4 + 2 * torch.randn(8, 80, 251, generator=g)
+    gen = H.HifiganGenerator(W, cfg)
+    wav = gen.decode_batch(mel)
+    assert wav.shape == (8, 1, (251 + 10) * 256)
+    Wq = {k: (bf16r(v) if k.endswith("weight") and not k.startswith("conv_post") else v) for k, v in W.items()}
+    ref = V.generator(mel, Wq, reflect=True)
+    assert rel_l2(wav, ref) < 1e-2, rel_l2(wav, ref)
+    # the edges are where reflect and zero padding differ: hold the first / last 2048 samples to the same bar
+    for sl in (slice(0, 2048), slice(-2048, None)):
+        assert rel_l2(wav[..., sl], ref[..., sl]) < 1e-2
+    zero = V.generator(mel[:1], Wq, reflect=False)
+    assert rel_l2(zero[..., :2048], ref[:1, :, :2048]) > 5e-2    # (the test can tell the two paddings apart)
+    wav_g = H.HifiganGenerator(W, cfg, pipeline="gather").decode_batch(mel[:2])
+    assert rel_l2(wav[:2], wav_g.cpu()) < 1e-2
+
+
+def test_hifigan_generator_batch_256_spot_check(pkg, H):
+    """BASELINE configs[2] batch (256 x 4 s): clips of the full batch equal the same clips decoded in a batch of two
+    (tile lists, persistent-grid sizing and halo handling do not depend on the batch), and one of them matches the
+    oracle."""
+    cfg = H.HifiganConfig
+    W = H.init_weights(cfg, seed=5, std=0.03)
+    g = torch.Generator().manual_seed(6)
+    mel = -4 + 2 * torch.randn(256, 80, 251, generator=g)
+    gen = H.HifiganGenerator(W, cfg)
+    wav = gen.decode_batch(mel)
+    pick = [0, 255]
+    small = gen.decode_batch(mel[pick])
+    assert torch.equal(wav[pick], small)
+    Wq = {k: (bf16r(v) if k.endswith("weight") and not k.startswith("conv_post") else v) for k, v in W.items()}
+    ref = V.generator(mel[255:256], Wq, reflect=True)
+    assert rel_l2(wav[255:256], ref) < 1e-2
+
+
+def test_load_speechbrain_state_dict(pkg, H):
+    """weight_norm'd, ``.conv.``-wrapped names (both torch weight-norm spellings) fold back to the plain weights"""
+    W = H.init_weights(seed=7, std=0.03)
+    sd = {}
+    for k, v in W.items():
+        name, kind = k.rsplit(".", 1)
+        wrapped = name + ".conv"
+        if kind == "bias":
+            sd[wrapped + ".bias"] = v
+            continue
+        dims = [d for d in range(v.dim()) if d != 0]
+        gnorm = torch.linalg.vector_norm(v, dim=dims, keepdim=True)
+        if name.startswith("resblocks"):
+            sd[wrapped + ".parametrizations.weight.original0"] = gnorm
+            sd[wrapped + ".parametrizations.weight.original1"] = 3.0 * v      # any positive rescaling of v folds away
+        else:
+            sd[wrapped + ".weight_g"] = gnorm
+            sd[wrapped + ".weight_v"] = 0.5 * v
+    back = H.load_speechbrain_state_dict(sd)
+    assert set(back) == set(W)
+    for k in W:
+        assert torch.allclose(back[k], W[k], rtol=1e-5, atol=1e-7), k
+    with pytest.raises(KeyError):
+        H.load_speechbrain_state_dict({"foo.weight": torch.zeros(1)})

@@ -392,6 +392,59 @@ __global__ void avg3_kernel(const __nv_bfloat162* __restrict__ a, const __nv_bfl
         out[i] = __floats2bfloat162_rn(m.x > 0.f ? m.x : m.x * slope, m.y > 0.f ? m.y : m.y * slope);
     }
 }
+// ---- halo layout for REFLECT "same" padding on the TMA conv kernels (SpeechBrain's Conv1d default, which the
+// reference's HIFIGAN uses for conv_pre, the ResBlock convs and conv_post).  An activation is stored as
+// [B][L + 2 H][C] with its L real rows at offset H; the conv kernels run over all L + 2 H rows with their zero (TMA
+// out-of-bounds) padding - what they compute in the halo rows is never used - and the kernel below rewrites the halo
+// rows of a produced tensor IN PLACE with the reflection of its interior (mode 1) or with zeros (mode 0, the input of a
+// transposed conv) before a conv reads it: interior results then see exactly F.pad(x, mode="reflect").
+__global__ void halo_fix_kernel(__nv_bfloat16* __restrict__ buf, int B, int L, int C8, int H, int mode) {
+    const long total = (long)B * 2 * H * C8;   // 16-byte groups in the halo rows
+    int4* p = reinterpret_cast<int4*>(buf);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8);
+        const long r = i / C8;
+        const int hr = (int)(r % (2 * H)), b = (int)(r / (2 * H));
+        // halo row hr < H: position -(H - hr) .. -1; else position L + (hr - H)
+        const int pos = hr < H ? hr - H : L + (hr - H);
+        int src = pos < 0 ? -pos : 2 * (L - 1) - pos;
+        const size_t row0 = (size_t)b * (L + 2 * H);
+        int4 v = make_int4(0, 0, 0, 0);
+        if (mode == 1 && src >= 0 && src < L) v = p[(row0 + H + src) * C8 + c];
+        p[(row0 + H + pos) * C8 + c] = v;
+    }
+}
+// out interior = LeakyReLU_slope(bf16(mean of the n_in inputs' interiors)); inputs [B][L + 2 h_in][C], output
+// [B][L + 2 h_out][C] with zero (mode 0) or reflected (mode 1) halo rows: the MRF average and the change of halo width
+// between generator stages in one pass
+__global__ void avg_relayout_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                    const __nv_bfloat16* __restrict__ c, int B, int L, int C2, int h_in, int h_out, int mode,
+                                    float slope, __nv_bfloat16* __restrict__ out) {
+    const int Lo = L + 2 * h_out, Li = L + 2 * h_in;
+    const long total = (long)B * Lo * C2;
+    const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162*>(a), *b2 = reinterpret_cast<const __nv_bfloat162*>(b),
+                         *c2 = reinterpret_cast<const __nv_bfloat162*>(c);
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(out);
+    const float inv = c2 ? 1.0f / 3.0f : (b2 ? 0.5f : 1.0f);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % C2);
+        const long r = i / C2;
+        const int row = (int)(r % Lo), bb = (int)(r / Lo);
+        int pos = row - h_out;
+        if (pos < 0 || pos >= L) {
+            if (mode == 0) { o2[i] = __floats2bfloat162_rn(0.f, 0.f); continue; }
+            pos = pos < 0 ? -pos : 2 * (L - 1) - pos;
+            if (pos < 0 || pos >= L) { o2[i] = __floats2bfloat162_rn(0.f, 0.f); continue; }
+        }
+        const size_t src = ((size_t)bb * Li + h_in + pos) * C2 + ch;
+        float2 x = __bfloat1622float2(a2[src]);
+        if (b2) { const float2 y = __bfloat1622float2(b2[src]); x.x += y.x; x.y += y.y; }
+        if (c2) { const float2 z = __bfloat1622float2(c2[src]); x.x += z.x; x.y += z.y; }
+        // the mean is rounded to bf16 first (it is the tensor the reference would hold), then activated
+        const float2 m = c2 || b2 ? __bfloat1622float2(__floats2bfloat162_rn(x.x * inv, x.y * inv)) : x;
+        o2[i] = __floats2bfloat162_rn(m.x > 0.f ? m.x : m.x * slope, m.y > 0.f ? m.y : m.y * slope);
+    }
+}
 // conv_post: LeakyReLU(slope) -> conv1d(C -> 1, taps) -> tanh; in channels-last bf16, out fp32 [B][L]
 template <int C, int TAPS>
 __global__ void post_conv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w /*[TAPS][C]*/,
@@ -527,6 +580,33 @@ int adv_avg3_bf16(const void* a, const void* b, const void* c, int64_t n, float 
     if (gx > 148 * 16) gx = 148 * 16;
     avg3_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat162*)a, (const __nv_bfloat162*)b,
                                                      (const __nv_bfloat162*)c, n / 2, act_slope, (__nv_bfloat162*)out);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int adv_halo_fix_bf16(void* buf, int batch, int L, int C, int H, int mode, void* stream) {
+    if (!buf || batch <= 0 || L <= 0 || C <= 0 || (C & 7) || H <= 0 || (mode != 0 && mode != 1)) return ADV_ERR_INVALID;
+    if (mode == 1 && H >= L) return ADV_ERR_SHAPE;   // reflect padding needs pad < length (torch raises too)
+    const long total = (long)batch * 2 * H * (C / 8);
+    int gx = (int)((total + 255) / 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    halo_fix_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, batch, L, C / 8, H, mode);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int adv_avg_relayout_bf16(const void* a, const void* b, const void* c, int batch, int L, int C, int h_in, int h_out, int mode,
+                          float act_slope, void* out, void* stream) {
+    if (!a || !out || batch <= 0 || L <= 0 || C <= 0 || (C & 1) || h_in < 0 || h_out < 0 || (mode != 0 && mode != 1) ||
+        (c && !b))
+        return ADV_ERR_INVALID;
+    if (mode == 1 && h_out >= L) return ADV_ERR_SHAPE;
+    const long total = (long)batch * (L + 2 * h_out) * (C / 2);
+    int gx = (int)((total + 255) / 256);
+    if (gx > 148 * 16) gx = 148 * 16;
+    avg_relayout_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+                                                             (const __nv_bfloat16*)c, batch, L, C / 2, h_in, h_out, mode,
+                                                             act_slope, (__nv_bfloat16*)out);
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }

@@ -5,9 +5,12 @@ SpeechBrain is not vendored in the reference and not installed here, and the che
 the published V1 design that SpeechBrain's ``HifiganGenerator`` implements: conv_pre(80->512, k7);
 4 x [LeakyReLU(0.1) -> ConvTranspose1d (x8, x8, x2, x2; k16, k16, k4, k4) -> mean of 3 ResBlock1
 (k 3/7/11, dilations 1/3/5, two convs each)]; LeakyReLU(0.01) -> conv_post(32->1, k7) -> tanh;
-``inference_padding`` = 5 replicate-padded mel frames per side.  Weights here are seeded random
-(N(0, 0.01^2), like the original init) with weight-norm already folded; a real checkpoint loads through
-``load_state_dict``-style tensors with the same shapes.  **Parity for this module is unpinned by the
+``inference_padding`` = 5 replicate-padded mel frames per side.  conv_pre, the ResBlock convs and conv_post are
+``speechbrain.nnet.CNN.Conv1d`` modules, whose "same" padding is REFLECT by default (``padding_mode="reflect"``); the
+transposed convs pad with zeros.  ``HifiganConfig.pad_reflect = True`` (the default) follows that; ``False`` is the
+original HiFi-GAN's zero padding.  Weights here are seeded random (N(0, 0.01^2), like the original init) with
+weight-norm already folded; a SpeechBrain checkpoint loads through ``load_speechbrain_state_dict`` (weight_g / weight_v
+folded, ``.conv.`` wrapper names stripped).  **Parity for this module is unpinned by the
 reference** (see oracle/vocoder.py); it is checked against a torch-fp32 restatement with the same weights.
 
 Execution: activations are channels-last bf16 [B][L][C]; every conv is ``adv_conv1d_bf16`` - an implicit
@@ -37,7 +40,13 @@ class HifiganConfig:
     resblock_dilation_sizes = ((1, 3, 5), (1, 3, 5), (1, 3, 5))
     inference_padding = 5
     conv_post_kernel = 7
-    pad_reflect = False  # zero "same" padding as in the original HiFi-GAN; see oracle/vocoder.py header
+    pad_reflect = True   # SpeechBrain's Conv1d default ("same" padding with padding_mode="reflect"); False = zeros
+    halo = 32            # rows of materialised reflection either side of an activation (>= 5 * (11 - 1) / 2 = 25)
+
+
+class HifiganConfigZeroPad(HifiganConfig):
+    """The original HiFi-GAN's zero "same" padding (round-1 default; TMA out-of-bounds fill, no halo rows)."""
+    pad_reflect = False
 
 
 def init_weights(cfg=HifiganConfig, seed=0, std=0.01):
@@ -64,6 +73,34 @@ def fold_weight_norm(g, v, dim=0):
     """weight = g * v / ||v|| (norm over every dim but ``dim``), as torch.nn.utils.weight_norm stores it."""
     dims = [d for d in range(v.dim()) if d != dim]
     return g * v / torch.linalg.vector_norm(v, dim=dims, keepdim=True)
+
+
+def load_speechbrain_state_dict(state_dict):
+    """SpeechBrain ``HifiganGenerator.state_dict()`` (the ``generator.ckpt`` of tts-hifigan-libritts-16kHz) -> the flat
+    weight dict this module consumes.  SpeechBrain wraps every layer (``conv_pre.conv.*``, ``ups.N.conv.*``,
+    ``resblocks.N.convs1.M.conv.*``, ``conv_post.conv.*``) and applies ``torch.nn.utils.weight_norm``, which stores
+    ``weight_g`` / ``weight_v`` (or ``parametrizations.weight.original0 / original1`` with the newer API); both are
+    folded to plain weights here.  Raises KeyError on a checkpoint that lacks a layer."""
+    sd = {k.replace(".conv.", "."): v.detach().float().cpu() for k, v in state_dict.items()}
+    W = {}
+    layers = sorted({k.rsplit(".", 1)[0].replace(".parametrizations.weight", "") for k in sd
+                     if k.split(".")[0] in ("conv_pre", "ups", "resblocks", "conv_post")})
+    for name in layers:
+        if f"{name}.weight" in sd:
+            w = sd[f"{name}.weight"]
+        elif f"{name}.weight_g" in sd:
+            w = fold_weight_norm(sd[f"{name}.weight_g"], sd[f"{name}.weight_v"])
+        elif f"{name}.parametrizations.weight.original0" in sd:
+            w = fold_weight_norm(sd[f"{name}.parametrizations.weight.original0"],
+                                 sd[f"{name}.parametrizations.weight.original1"])
+        else:
+            continue
+        W[f"{name}.weight"] = w
+        W[f"{name}.bias"] = sd[f"{name}.bias"] if f"{name}.bias" in sd else torch.zeros(w.shape[1] if name.startswith("ups") else w.shape[0])
+    for need in ("conv_pre.weight", "ups.0.weight", "resblocks.0.convs1.0.weight", "conv_post.weight"):
+        if need not in W:
+            raise KeyError(f"not a HifiganGenerator state_dict: {need} missing")
+    return W
 
 
 def _gemm_weight(w):
@@ -110,9 +147,12 @@ class _Layer:
 class HifiganGenerator:
     """``decode_batch(mel[B,80,T]) -> waveform [B,1,(T+10)*256]`` (SpeechBrain HIFIGAN.decode_batch).
 
-    ``pipeline="tma"`` (default with zero padding): TMA-fed warp-specialised persistent conv kernel; LeakyReLU is
-    applied by the producing layer's epilogue.  ``pipeline="gather"``: first-generation kernel (operands gathered
-    with ordinary loads, activation on load) - required for reflect padding."""
+    ``pipeline="tma"`` (default): TMA-fed warp-specialised persistent conv kernels; LeakyReLU is applied by the
+    producing layer's epilogue.  With reflect padding (the default, see the module docstring) activations carry
+    ``cfg.halo`` rows of materialised reflection either side (``adv_halo_fix_bf16``), so the same kernels - whose only
+    padding is the TMA unit's zero fill - compute SpeechBrain's reflect "same" convs; the MRF average
+    (``adv_avg_relayout_bf16``) switches to the zero halo the next transposed conv needs.  ``pipeline="gather"``:
+    first-generation kernel (operands gathered with ordinary loads, activation and reflection on load)."""
 
     def __init__(self, weights=None, cfg=HifiganConfig, device=None, seed=0, pipeline=None, fuse="auto"):
         self.cfg = cfg
@@ -120,9 +160,9 @@ class HifiganGenerator:
         # kernel supports the shape, "never" = every conv is its own launch
         self.fuse = {True: "auto", False: "never"}.get(fuse, fuse)
         self.dev = device or ops._dev()
-        self.pipeline = pipeline or ("gather" if cfg.pad_reflect else "tma")
-        if self.pipeline == "tma" and cfg.pad_reflect:
-            raise ValueError("the TMA pipeline implements zero padding only")
+        self.pipeline = pipeline or "tma"
+        if cfg.pad_reflect and any(cfg.halo % s for s in cfg.upsample_factors):
+            raise ValueError("cfg.halo must be a multiple of every upsample factor")
         W = weights if weights is not None else init_weights(cfg, seed)
         self.master = W
         L = lambda name, dil=1: _Layer(W[name + ".weight"], W[name + ".bias"], dil, self.dev)
@@ -251,6 +291,53 @@ class HifiganGenerator:
                 o_act = self._avg3(outs, LRELU_SLOPE)      # next stage's transposed conv reads it activated
         return o, L
 
+    def _halo_fix(self, x, B, L, C, mode=1):
+        check(lib().adv_halo_fix_bf16(ptr(x), B, L, C, self.cfg.halo, mode, stream_ptr()), "adv_halo_fix_bf16")
+        self.launches += 1
+
+    def _relayout(self, srcs, B, L, C, h_in, h_out, slope=1.0, mode=0):
+        out = self._buf(B, L + 2 * h_out, C)
+        a, b, c = (list(srcs) + [None, None])[:3]
+        check(lib().adv_avg_relayout_bf16(ptr(a), ptr(b), ptr(c), B, L, C, h_in, h_out, mode, float(slope), ptr(out),
+                                          stream_ptr()), "adv_avg_relayout_bf16")
+        self.launches += 1
+        return out
+
+    def _stages_tma_reflect(self, o_act, B, L):
+        """Reflect-padded generator on the TMA kernels.  ``o_act`` = LeakyReLU(conv_pre) [B][L][C], contiguous.  Inside a
+        stage every tensor is [B][L + 2 H][C] (H = cfg.halo); a conv runs over all L + 2 H rows and the halo rows of
+        what it wrote for the NEXT conv are replaced by the reflection of the interior.  The transposed conv wants zeros
+        outside its input, so a stage's input carries a zero halo of H / stride rows - which the stride turns into
+        exactly H output rows."""
+        H = self.cfg.halo
+        n_stage = len(self.ups)
+        h = H // self.ups[0][1]
+        x_in = self._relayout([o_act], B, L, self.conv_pre.cout, 0, h)
+        o = None
+        for si, ((up, s), stage) in enumerate(zip(self.ups, self.blocks)):
+            x_raw, x_act = self._conv_tma(x_in, up, B, L + 2 * h, act_slope=LRELU_SLOPE)
+            L, ch = L * s, up.cout // s
+            Lp = L + 2 * H
+            x_raw, x_act = x_raw.view(B, Lp, ch), x_act.view(B, Lp, ch)
+            self._halo_fix(x_act, B, L, ch)
+            outs = []
+            for branch in stage:
+                xb_raw, xb_act = x_raw, x_act
+                for d, (c1, c2) in enumerate(branch):
+                    _, xt_act = self._conv_tma(xb_act, c1, B, Lp, want_raw=False, act_slope=LRELU_SLOPE)
+                    self._halo_fix(xt_act, B, L, ch)
+                    last = d == len(branch) - 1
+                    xb_raw, xb_act = self._conv_tma(xt_act, c2, B, Lp, resid=xb_raw, act_slope=None if last else LRELU_SLOPE)
+                    if xb_act is not None:
+                        self._halo_fix(xb_act, B, L, ch)
+                outs.append(xb_raw)
+            if si == n_stage - 1:
+                o = self._relayout(outs, B, L, ch, H, 0)                        # raw mean, no halo: conv_post reflects itself
+            else:
+                h = H // self.ups[si + 1][1]
+                x_in = self._relayout(outs, B, L, ch, H, h, slope=LRELU_SLOPE)  # activated mean with the next stage's zero halo
+        return o, L
+
     @torch.no_grad()
     def forward_padded(self, mel):
         """mel [B, 80, T] fp32 -> waveform [B, (T + 2*pad) * prod(upsample_factors)] fp32."""
@@ -263,7 +350,7 @@ class HifiganGenerator:
         check(lib().adv_mel_to_channels_last(ptr(mel), B, C, T, pad, C, ptr(x), stream_ptr()), "adv_mel_to_channels_last")
         if self.pipeline == "tma":   # conv_pre (C_in = 80) runs on the gather kernel and hands over lrelu(o)
             _, o = self._conv(x, self.conv_pre, B, L, want_raw=False, act_slope=LRELU_SLOPE)
-            o, L = self._stages_tma(o, B, L)
+            o, L = self._stages_tma_reflect(o, B, L) if cfg.pad_reflect else self._stages_tma(o, B, L)
         else:
             o, L = self._stages_gather(self._conv(x, self.conv_pre, B, L), B, L)
         wav = torch.empty((B, L), dtype=torch.float32, device=self.dev)
