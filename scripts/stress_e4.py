@@ -45,4 +45,17 @@ for hop, B, n in [(128, 64, 64000), (160, 64, 64000), (256, 64, 64000), (160, 7,
     torch.cuda.synchronize()
     print("hop", hop, "B", B, "n", n, "iters", iters, "mismatches", bad)
     bad_total += bad
+# streaming iSTFT: same hunt
+for hop, B, n in [(128, 64, 64000), (160, 64, 64000), (256, 64, 64000), (160, 200, 8000)]:
+    specs = [ops.stft(0.1 * torch.randn(B, n, generator=g, device="cuda"), 512, hop, 512, want_mag=False, want_phase=False)[0] for _ in range(4)]
+    ref = [ops.istft(x, 512, hop, 512, length=n).clone() for x in specs]
+    bad = 0
+    for it in range(iters):
+        k = it % 4
+        y = ops.istft(specs[k], 512, hop, 512, length=n)
+        if not torch.equal(y, ref[k]):
+            bad += 1
+    torch.cuda.synchronize()
+    print("istft hop", hop, "B", B, "n", n, "iters", iters, "mismatches", bad)
+    bad_total += bad
 print("TOTAL MISMATCHES", bad_total)

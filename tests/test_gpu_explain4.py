@@ -121,3 +121,46 @@ def test_streaming_explain_strided_rows_and_unaligned_outputs(ops):
     ops.explain(wide[:, 3:3 + n], mask, 512, hop, 512, length=n, out=(rel, irr, None))
     assert relerr(rel, rel_r) < TOL and relerr(irr, irr_r) < TOL
     assert float(big[0]) == 0.0 and float(big[B * n + 1:B * n + 5].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# streaming iSTFT (istft4_kernel): same geometry domain, spectrum input with any strides
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hop", [128, 160, 256])
+@pytest.mark.parametrize("B,n", [(1, 16000), (3, 6400), (37, 3200), (64, 64000), (200, 8000)])
+def test_streaming_istft_matches_torch(ops, hop, B, n):
+    if B == 64 and hop != 160:
+        pytest.skip("full size once")
+    g = torch.Generator().manual_seed(B + n + hop)
+    T = 1 + n // hop
+    spec = torch.complex(torch.randn(B, 257, T, generator=g), torch.randn(B, 257, T, generator=g))
+    spec[-1] *= 1e-3
+    w = torch.ones(512)
+    for length in (n, None, n - 37):
+        want = torch.istft(spec, 512, hop_length=hop, win_length=512, window=w, length=length)
+        got = ops.istft(spec.cuda(), 512, hop, 512, length=length)                     # [B,F,T] contiguous: strided rows
+        worst = max(relerr(got[b], want[b]) for b in range(B))
+        assert got.shape == want.shape and worst < TOL, (length, worst)
+    fm = spec.transpose(1, 2).contiguous().transpose(1, 2).cuda()                       # torch.stft's frame-major layout
+    got2, stats = ops.istft(fm, 512, hop, 512, length=n, return_stats=True)
+    want = torch.istft(spec, 512, hop_length=hop, win_length=512, window=w, length=n)
+    assert relerr(got2, want) < TOL
+    s = stats.sum(dim=1).cpu()
+    np.testing.assert_allclose(s[:, 0], want.double().sum(dim=1), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(s[:, 1], (want.double() ** 2).sum(dim=1), rtol=1e-4)
+
+
+def test_streaming_istft_round_trip_and_determinism(ops):
+    B, n, hop = 16, 64000, 160
+    g = torch.Generator().manual_seed(3)
+    wav = 0.1 * torch.randn(B, n, generator=g).cuda()
+    X, _, _ = ops.stft(wav, 512, hop, 512, want_mag=False, want_phase=False)
+    first = None
+    for _ in range(20):
+        y, st = ops.istft(X, 512, hop, 512, length=n, return_stats=True)
+        if first is None:
+            first = (y.clone(), st.clone())
+            assert relerr(y, wav) < 1e-5
+        else:
+            assert torch.equal(y, first[0]) and torch.equal(st, first[1])
+

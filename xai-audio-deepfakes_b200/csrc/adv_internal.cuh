@@ -57,6 +57,10 @@ int launch_explain3(const adv_plan* p, const float* wav, int64_t wav_stride, con
 int launch_explain4(const adv_plan* p, const float* wav, int64_t wav_stride, const float* mask, int Fm, int Tm,
                     int mode_flags, int batch, float* rel, float* irr, double* stats, cudaStream_t s);
 int explain4_slots(const adv_plan* p, int batch);
+// streaming iSTFT of the same generation (same domain, any spectrum strides); istft4_slots(): statistics slots per clip
+int launch_istft4(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
+                  double* stats, cudaStream_t s);
+int istft4_slots(const adv_plan* p, int batch);
 int istft3_frames_cap(const adv_plan* p);    // 32 when launch_istft3 takes the plan, else 0 (plan default)
 bool istft_balanced();  // tiling policy of the stand-alone iSTFT kernels (ADV_ISTFT_BALANCED=1 selects the round-balanced tile length; default: longest tile)
 int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,

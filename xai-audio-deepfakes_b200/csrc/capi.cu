@@ -68,11 +68,16 @@ Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm, bool balanc
     // tile: for 64 clips of 400 hops the longest tile (29 hops, 32 frames) gives 896 tiles = 6.05 rounds on 148
     // one-CTA SMs but costs 7 full rounds, while 25 hops (28 frames) gives 1024 tiles = 6.92 rounds of shorter
     // passes - the same number of frames transformed, 12 % less time.
-    static int n_sm = 0;
-    if (n_sm == 0) {
+    int n_sm = 0;
+    {
         int dev = 0;
         cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+        static int cache[64] = {0};
+        if (dev >= 0 && dev < 64 && cache[dev] > 0) n_sm = cache[dev];
+        else {
+            if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+            if (dev >= 0 && dev < 64) cache[dev] = n_sm;
+        }
     }
     const PlanDev& d = p->d;
     const int total_hops = (d.n_out + d.hop - 1) / d.hop;
@@ -248,7 +253,8 @@ int adv_plan_tiles(const adv_plan* plan, int batch) {
 }
 int adv_plan_tiles_istft(const adv_plan* plan, int batch) {
     if (!plan || batch <= 0 || plan->d.n_out <= 0) return ADV_ERR_INVALID;
-    return choose_tiling(plan, batch, 2, istft_balanced(), istft3_frames_cap(plan)).tiles;
+    const int s4 = istft4_slots(plan, batch);   // statistics slots per clip of the streaming iSTFT
+    return s4 > 0 ? s4 : choose_tiling(plan, batch, 2, istft_balanced(), istft3_frames_cap(plan)).tiles;
 }
 
 int adv_stft(const adv_plan* plan, const float* wav, int64_t wav_stride, int batch, adv_c64* X, float* mag,

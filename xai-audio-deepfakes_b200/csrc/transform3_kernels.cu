@@ -62,7 +62,10 @@ __device__ __forceinline__ void store_bin(float2* __restrict__ X, float* __restr
 }
 
 template <int NF, bool MAG, bool PHASE, bool RECT, bool VEC, bool ZP>
-__global__ void __launch_bounds__(kThreads, VEC ? 3 : 4)
+#ifndef ADV_STFT3_VEC_CTAS
+#define ADV_STFT3_VEC_CTAS 3
+#endif
+__global__ void __launch_bounds__(kThreads, VEC ? ADV_STFT3_VEC_CTAS : 4)
 stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int total_items, int items_per_clip,
              float2* __restrict__ X, float* __restrict__ mag, float* __restrict__ phase) {
     using C = S3Cfg<NF, VEC>;
@@ -819,29 +822,9 @@ explain3_kernel(PlanDev P, Tiling TL, int total_tiles, const float* __restrict__
 // ------------------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------------------
-static int sm_count_dev() {  // SM count of the CURRENT device (plans of several devices may share this process)
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    static int cache[64] = {0};
-    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    if (dev >= 0 && dev < 64) cache[dev] = n;
-    return n;
-}
-
-// resident CTAs per SM, cached per (kernel, shared-memory size)
+static int sm_count_dev() { return sm_count(); }
 template <class K>
-static int resident3(K kernel, int threads, size_t smem, int cap) {
-    static std::mutex mu;
-    static std::unordered_map<size_t, int> memo;
-    std::lock_guard<std::mutex> lock(mu);
-    const size_t key = (reinterpret_cast<size_t>(reinterpret_cast<const void*>(kernel)) * 1000003u) ^ smem;
-    auto it = memo.find(key);
-    if (it != memo.end()) return it->second;
-    const int r = adv_resident_ctas(kernel, threads, smem, 0, cap);
-    memo[key] = r;
-    return r;
-}
+static int resident3(K kernel, int threads, size_t smem, int cap) { return resident_memo(kernel, threads, smem, cap); }
 
 static bool stft3_vec() {
     static const char* e = getenv("ADV_STFT3_VEC");  // A/B: 64-bit (default) or planar ("0") exchanges in the STFT
@@ -864,7 +847,7 @@ static int launch_stft3_t(const adv_plan* p, const float* wav, int64_t wav_strid
     do {                                                                                                         \
         auto kernel = stft3_kernel<NF, M, PH, RECT, VEC, ZP>;                                                    \
         if ((rc = set_smem(kernel, smem)) != ADV_OK) return rc;                                                  \
-        const long slots = (long)resident3(kernel, kThreads, smem, VEC ? 3 : 4) * sm_count_dev();                \
+        const long slots = (long)resident3(kernel, kThreads, smem, VEC ? ADV_STFT3_VEC_CTAS : 4) * sm_count_dev();                \
         const int grid = (int)(ctas < slots ? ctas : slots);                                                     \
         ADV_CUDA_CHECK(launch_pdl(kernel, grid, kThreads, smem, s, p->d, wav, wav_stride, (int)total,            \
                                   items_per_clip, X, mag, phase));                                               \

@@ -444,6 +444,196 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Streaming iSTFT (torch.istft, audioprocessor.py:123-129) - the same pipeline of warps without the forward transform
+// and the mask: a unit's two spectrum rows come straight from global memory into the lanes that own their bins
+// (32 consecutive bins per load instruction), ONE inverse transform carries frames a and b as real / imaginary part,
+// overlap-add in registers, tails through shared memory, heads stored from registers.  64 registers per thread and
+// the next unit's rows are requested (into registers) as soon as the current ones are merged, a whole pass ahead of use.
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef ADV_ISTFT4_UNITS
+#define ADV_ISTFT4_UNITS 8   // warps (= units per pass) of a CTA
+#endif
+#ifndef ADV_ISTFT4_CTAS
+#define ADV_ISTFT4_CTAS 2    // resident CTAs per SM the kernel is compiled for: 2 x 256 threads -> up to 128 registers per thread
+#endif                       // (the next unit's 18 spectrum values per lane are held in registers across the transform).
+                             // Measured (64 x 4 s clips, rows loaded at the start of a pass): 2 x 512 threads at 64 registers
+                             // spills, 29.9 us; 1 x 512 at 128: 21.1 us; 3 x 256 at 80: 20.7 us; 2 x 256 at 120: 20.3 us
+constexpr int kI4Units = ADV_ISTFT4_UNITS, kI4Threads = 32 * kI4Units;
+
+template <int HS>
+struct I4Cfg {
+    using E = E4Cfg<HS>;
+    static constexpr int UNITS = kI4Units, NBARS = 2 * UNITS;
+    static size_t bytes() {
+        return al16(sizeof(float2) * E::TW3N) + al16(sizeof(float) * UNITS * f3::Scr<true>::FLOATS) +
+               al16(sizeof(float) * UNITS * E::TAIL * 32) + al16(sizeof(uint64_t) * NBARS);
+    }
+};
+
+template <int HS, bool CONTIG>
+__global__ void __launch_bounds__(kI4Threads, ADV_ISTFT4_CTAS)
+istft4_kernel(PlanDev P, int upc, int total_units, const float2* __restrict__ X, int64_t sb, int64_t st, int64_t sf,
+              float* __restrict__ out, double* __restrict__ stats, int slots) {
+    using C = E4Cfg<HS>;
+    constexpr int UNITS = kI4Units, NT = kI4Threads, HOP = C::HOP, USTEP = C::USTEP;
+    constexpr int ROWS = C::ROWS, HEAD = C::HEAD, TAIL = C::TAIL, NB = C::NB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(C::TW3N);
+    float* scratch = cv.take<float>(UNITS * f3::Scr<true>::FLOATS);
+    float* tails = cv.take<float>(UNITS * TAIL * 32);
+    uint64_t* bars = cv.take<uint64_t>(I4Cfg<HS>::NBARS);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + UNITS;
+
+    const int tid = threadIdx.x, l = tid & 31;
+    const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const long G = gridDim.x;
+    const int g_begin = (int)(((long)blockIdx.x * total_units) / G);
+    const int g_end = (int)(((long)(blockIdx.x + 1) * total_units) / G);
+    const int b0 = g_begin / upc, u0 = g_begin - b0 * upc;
+    const int halo = u0 < NB ? u0 : NB;
+    const int start = g_begin - halo;
+    const int n_pass = (g_end - start + UNITS - 1) / UNITS;
+
+    if (tid == 0)
+        for (int i = 0; i < UNITS; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, NB);
+        }
+    for (int i = tid; i < C::TW3N / 2; i += NT) cp_async16(tw_s + 2 * i, P.tw3 + 2 * i);
+    cp_async_commit();
+    pdl_launch_dependents();
+    cp_async_wait_all();
+    __syncthreads();
+    pdl_wait();
+
+    if (stats != nullptr && g_end > g_begin) {
+        const int b_last = (g_end - 1) / upc;
+        for (int b = b0; b <= b_last; ++b) {
+            const long gb = (long)b * upc;
+            const int c_first = (int)(((gb + 1) * G - 1) / total_units);
+            const int c_last = (int)(((gb + upc) * G - 1) / total_units);
+            double* row = stats + (size_t)b * slots * 2;
+            if (l < 2) row[(((int)blockIdx.x - c_first) * UNITS + w) * 2 + l] = 0.0;
+            if ((int)blockIdx.x == c_first)
+                for (int i = (c_last - c_first + 1) * UNITS * 2 + tid; i < slots * 2; i += NT) row[i] = 0.0;
+        }
+    }
+
+    float* my = scratch + w * f3::Scr<true>::FLOATS;
+    float* tail_w = tails + w * (TAIL * 32);
+    const int q1 = l == 0 ? 32 : 64 - l;
+    const int64_t sfe = CONTIG ? 1 : sf;
+
+    UnitPos pos;
+    {
+        const int g = start + w;
+        pos.b = g / upc;
+        pos.u = g - pos.b * upc;
+    }
+    float acc[2] = {0.f, 0.f};
+    int acc_b = -1;
+    auto flush = [&]() {
+        const double q0 = warp_sum((double)acc[0]), q1s = warp_sum((double)acc[1]);
+        if (stats != nullptr && acc_b >= 0 && l == 0) {
+            const int c_first = (int)((((long)acc_b * upc + 1) * G - 1) / total_units);
+            double* row = stats + ((size_t)acc_b * slots + ((int)blockIdx.x - c_first) * UNITS + w) * 2;
+            row[0] = q0;
+            row[1] = q1s;
+        }
+        acc[0] = acc[1] = 0.f;
+    };
+    const float2 zero2 = make_float2(0.f, 0.f);
+    // spectrum rows of a unit -> the lanes that own their bins (frames past the last one, units past the run: zeros)
+    float2 xa[9], xb[9];
+    auto load_rows = [&](const UnitPos& q, bool live) {
+        const int fa = 2 * q.u;
+        const bool va = live && fa < P.T, vb = live && fa + 1 < P.T;
+        const float2* pa = X + (size_t)q.b * sb + (size_t)fa * st;
+        const float2* pb = pa + st;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xa[i] = va ? __ldg(pa + (l + 64 * i) * sfe) : zero2;
+            xa[4 + i] = va ? __ldg(pa + (q1 + 64 * i) * sfe) : zero2;
+            xb[i] = vb ? __ldg(pb + (l + 64 * i) * sfe) : zero2;
+            xb[4 + i] = vb ? __ldg(pb + (q1 + 64 * i) * sfe) : zero2;
+        }
+        xa[8] = (l == 0 && va) ? __ldg(pa + 256 * sfe) : zero2;
+        xb[8] = (l == 0 && vb) ? __ldg(pb + 256 * sfe) : zero2;
+    };
+    load_rows(pos, start + w < g_end);
+
+    for (int p = 0; p < n_pass; ++p) {
+        const int g = start + p * UNITS + w;
+        const bool active = g < g_end;
+        const bool is_out = active && g >= g_begin;
+        const UnitPos cur = pos;
+        pos.advance(UNITS, upc);
+
+        // -- 1. the unit's two spectrum rows were requested a pass ago (registers xa / xb); build the transform input and
+        //       request the next pass's rows, which then travel while this pass computes
+        float2 v[16];
+        f3::merge(v, l, xa, xb);
+        load_rows(pos, p + 1 < n_pass && g + UNITS < g_end);
+        // -- 2. inverse transform, overlap-add of the two frames in registers, tail rows to shared memory
+        f3::fft_inverse<true>(v, l, tw_s, my);
+        float head[HEAD];
+        if (p >= 1) mbar_wait(empty + w, (p - 1) & 1);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            float o = r < 16 ? v[r < 16 ? r : 0].x : 0.0f;
+            if (r >= HS) o += v[r >= HS ? r - HS : 0].y;
+            if (r < HEAD) head[r < HEAD ? r : 0] = o;
+            else tail_w[(r - HEAD) * 32 + l] = o;
+        }
+        __syncwarp();
+        if (l == 0) mbar_arrive(full + w);
+
+        const int s_base = USTEP * cur.u - 256 + l;
+        float env[HEAD];
+        if (is_out) {
+#pragma unroll
+            for (int r = 0; r < HEAD; ++r) {
+                const int sidx = s_base + 32 * r;
+                env[r] = (sidx >= 0 && sidx < P.n_out) ? __ldg(P.inv_env + sidx) : 0.0f;
+            }
+        }
+        // -- 3. tails of the previous NB units (see explain4_kernel for the protocol)
+#pragma unroll
+        for (int k = NB; k >= 1; --k) {
+            const int slot = (w - k) & (UNITS - 1);
+            const int pp = w >= k ? p : p - 1;
+            if (pp >= 0) mbar_wait(full + slot, pp & 1);
+            if (is_out && cur.u >= k) {
+                const float* tn = tails + slot * (TAIL * 32) + l;
+#pragma unroll
+                for (int r = (k - 1) * HEAD; r < k * HEAD && r < TAIL; ++r) head[r - (k - 1) * HEAD] += tn[r * 32];
+            }
+            __syncwarp();
+            if (l == 0 && pp >= 0) mbar_arrive(empty + slot);
+        }
+        // -- 4. scale, statistics, store
+        if (is_out) {
+            if (cur.b != acc_b) {
+                if (acc_b >= 0) flush();
+                acc_b = cur.b;
+            }
+            float* orow = out + (size_t)cur.b * P.n_out;
+#pragma unroll
+            for (int r = 0; r < HEAD; ++r) {
+                const int sidx = s_base + 32 * r;
+                const float a = head[r] * env[r];
+                acc[0] += a;
+                acc[1] = fmaf(a, a, acc[1]);
+                if (sidx >= 0 && sidx < P.n_out) orow[sidx] = a;
+            }
+        }
+    }
+    if (acc_b >= 0) flush();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 static bool gen4_enabled() {
@@ -512,6 +702,55 @@ int launch_explain4(const adv_plan* p, const float* wav, int64_t wav_stride, con
     if (r.hs == 5) ADV_E4(5);
     ADV_E4(8);
 #undef ADV_E4
+}
+
+// ---- streaming iSTFT
+struct RunI4 { int hs, upc, grid, slots; long total; };
+static RunI4 plan_run_i4(const adv_plan* p, int batch) {
+    RunI4 r = {0, 0, 0, 0, 0};
+    const PlanDev& d = p->d;
+    if (!gen4_enabled() || d.n_fft != 512 || !d.rect_full || d.n_out <= 0 || batch <= 0) return r;
+    if (d.hop != 128 && d.hop != 160 && d.hop != 256) return r;
+    r.upc = (d.n_out + 256 + 2 * d.hop - 1) / (2 * d.hop);
+    r.total = (long)r.upc * batch;
+    if (r.total > 0x3fffffffL) return r;
+    const long by_work = r.total / 8 > 0 ? r.total / 8 : 1;
+    const long slots_hw = (long)ADV_ISTFT4_CTAS * sm_count4();
+    r.grid = (int)(by_work < slots_hw ? by_work : slots_hw);
+    const long span = ((long)(r.upc - 1) * r.grid + r.total - 1) / r.total;
+    r.slots = kI4Units * (int)(span + 1);
+    r.hs = d.hop / 32;
+    return r;
+}
+
+int istft4_slots(const adv_plan* p, int batch) {
+    const RunI4 r = plan_run_i4(p, batch);
+    return r.hs ? r.slots : 0;
+}
+
+template <int HS, bool CONTIG>
+static int launch_istft4_t(const adv_plan* p, const RunI4& r, const float2* X, int64_t sb, int64_t st, int64_t sf,
+                           float* out, double* stats, cudaStream_t s) {
+    const size_t smem = I4Cfg<HS>::bytes();
+    auto kernel = istft4_kernel<HS, CONTIG>;
+    int rc = set_smem(kernel, smem);
+    if (rc != ADV_OK) return rc;
+    ADV_CUDA_CHECK(launch_pdl(kernel, r.grid, kI4Threads, smem, s, p->d, r.upc, (int)r.total, X, sb, st, sf, out, stats, r.slots));
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int launch_istft4(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
+                  double* stats, cudaStream_t s) {
+    const RunI4 r = plan_run_i4(p, batch);
+    if (!r.hs) return ADV_ERR_UNSUPPORTED;
+#define ADV_I4(HS)                                                                        \
+    return sf == 1 ? launch_istft4_t<HS, true>(p, r, X, sb, st, sf, out, stats, s)        \
+                   : launch_istft4_t<HS, false>(p, r, X, sb, st, sf, out, stats, s)
+    if (r.hs == 4) ADV_I4(4);
+    if (r.hs == 5) ADV_I4(5);
+    ADV_I4(8);
+#undef ADV_I4
 }
 
 }  // namespace adv

@@ -365,13 +365,28 @@ static int set_smem(K kernel, size_t bytes) {
     return ADV_OK;
 }
 
-static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
+// resident CTAs per SM of a persistent kernel, cached per (kernel, dynamic shared-memory size): the footprint depends
+// on the plan (hop, window support), so a per-instantiation static would go stale with the second plan
+template <class K>
+static int resident_memo(K kernel, int threads, size_t smem, int cap) {
+    static std::mutex mu;
+    static std::unordered_map<size_t, int> memo;
+    std::lock_guard<std::mutex> lock(mu);
+    const size_t key = (reinterpret_cast<size_t>(reinterpret_cast<const void*>(kernel)) * 1000003u) ^ smem;
+    auto it = memo.find(key);
+    if (it != memo.end()) return it->second;
+    const int r = adv_resident_ctas(kernel, threads, smem, 0, cap);
+    memo[key] = r;
+    return r;
+}
+
+static int sm_count() {   // of the CURRENT device (plans of several devices may share this process)
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    static int cache[64] = {0};
+    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev] = n;
     return n;
 }
 

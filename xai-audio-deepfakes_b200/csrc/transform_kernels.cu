@@ -1855,7 +1855,7 @@ static int launch_stft_ww(const adv_plan* p, const float* wav, int64_t wav_strid
     do {                                                                                                         \
         auto kernel = stft_ww_kernel<M, PH, RECT>;                                                               \
         if ((rc = set_smem(kernel, smem)) != ADV_OK) return rc;                                                  \
-        static const int resident = adv_resident_ctas(kernel, kThreads, smem, 0, 4);                             \
+        const int resident = resident_memo(kernel, kThreads, smem, 4);                                           \
         const long slots = (long)resident * sm_count();                                                          \
         const int grid = (int)(ctas < slots ? ctas : slots);                                                     \
         ADV_CUDA_CHECK(launch_pdl(kernel, grid, kThreads, smem, s, p->d, wav, wav_stride, (int)total,            \
@@ -1962,7 +1962,7 @@ static int launch_istft_w512(const adv_plan* p, const float2* X, int64_t sb, int
     auto kernel = istft_w512_kernel<RECT, HS>;
     int rc = set_smem(kernel, smem);
     if (rc != ADV_OK) return rc;
-    static const int resident = adv_resident_ctas(kernel, kWideThreads, smem, 0, 2);
+    const int resident = resident_memo(kernel, kWideThreads, smem, 2);
     const long slots = (long)resident * sm_count();
     const int grid = (int)(total < slots ? total : slots);
     ADV_CUDA_CHECK(launch_pdl(kernel, grid, kWideThreads, smem, s, p->d, tl, (int)total, X, sb, st, out, stats));
@@ -1972,6 +1972,7 @@ static int launch_istft_w512(const adv_plan* p, const float2* X, int64_t sb, int
 
 int launch_istft(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
                  double* stats, cudaStream_t s) {
+    if (istft4_slots(p, batch) > 0) return launch_istft4(p, X, sb, st, sf, batch, out, stats, s);
     {
         const int rc3 = launch_istft3(p, X, sb, st, sf, batch, out, stats, s);
         if (rc3 != ADV_ERR_UNSUPPORTED) return rc3;

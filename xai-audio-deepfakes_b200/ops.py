@@ -29,6 +29,23 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _on_input_device(fn):
+    """Run ``fn`` with the device of its first CUDA tensor argument current: plans, launches, the stream and the outputs
+    then live where the data is (host inputs keep going to the current device, like the reference's ``.to(device)``)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if torch.is_tensor(a) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def _f32_rows(x, name):
     """float32 CUDA tensor [B, n] with unit stride on the last dim."""
     if x.dtype != torch.float32:
@@ -50,6 +67,7 @@ def _mask3(mask):
 
 
 # ----------------------------------------------------------------------------------------------
+@_on_input_device
 def stft(wave, n_fft, hop, win_length, window=None, want_mag=True, want_phase=True):
     """wave [B,n] -> (X [B,F,T] complex64 with torch.stft's frame-major strides, mag, phase)."""
     wave = _f32_rows(wave, "waveform")
@@ -69,10 +87,11 @@ def _spec_strides(spec):
     """(tensor, sb, st, sf) element strides of a complex [B,F,T] tensor, no copy when possible."""
     if spec.dtype != torch.complex64:
         spec = spec.to(torch.complex64)
-    spec = spec.to(_dev(), non_blocking=True)
+    spec = spec.to(_dev(), non_blocking=True).resolve_conj()   # (X.conj() is lazy: data_ptr() would be the unconjugated data)
     return spec, spec.stride(0), spec.stride(2), spec.stride(1)
 
 
+@_on_input_device
 def istft(spec, n_fft, hop, win_length, length=None, window=None, return_stats=False):
     """spec complex [B,F,T] (any strides) -> wave [B, length]; length=None => hop*(T-1)."""
     spec, sb, st, sf = _spec_strides(spec)
@@ -89,6 +108,7 @@ def istft(spec, n_fft, hop, win_length, length=None, window=None, return_stats=F
     return (out, stats) if return_stats else out
 
 
+@_on_input_device
 def normalize_(x, stats=None, width=2, col=0, out=None):
     """(x - mean) / (std_unbiased + 1e-7) per row (classifier_embedder.py:59-63); ``stats`` are the
     per-tile partial sums an upstream kernel already produced, else one extra pass computes them."""
@@ -107,6 +127,7 @@ def normalize_(x, stats=None, width=2, col=0, out=None):
     return out
 
 
+@_on_input_device
 def explain(wave, mask, n_fft, hop, win_length, length=None, mode="log1p", window=None, normalize=False,
             out=None, outside="drop"):
     """Fused wave + mask -> (masked-in wave, masked-out wave) [B, length] (LMAC_metrics.py:136-157).
@@ -136,6 +157,7 @@ def explain(wave, mask, n_fft, hop, win_length, length=None, mode="log1p", windo
     return rel, irr
 
 
+@_on_input_device
 def normalize_pair_(rel, irr, stats):
     """In-place zero_mean_unit_var_norm of both explain outputs from the per-tile sums the explain kernel wrote
     (stats float64 [B, tiles, 4]); one launch."""
@@ -152,6 +174,7 @@ def explain_tiles(n_fft, hop, win_length, n, batch, length=None, window=None):
     return get_plan(n_fft, hop, win_length, window, T, n, n_out).tiles(batch)
 
 
+@_on_input_device
 def explain_spec(spec, mask, n_fft, hop, win_length, length=None, mode="log1p", window=None, normalize=False,
                  outside="drop"):
     """Same as :func:`explain` starting from an STFT (complex [B,F,T])."""
@@ -215,6 +238,7 @@ class _ExplainLinearFn(torch.autograd.Function):
         return gm.reshape(mshape), None, None, None, None, None, None, None
 
 
+@_on_input_device
 def explain_linear(spec, mask, n_fft, hop, win_length, length=None, window=None, outside="drop"):
     """Linear-mode explain from an STFT, differentiable w.r.t. ``mask`` (training callers: loss_function.py).
     Out-of-mask bins (``outside``, see :func:`explain`) are constants of the mask either way, so the gradient formula
@@ -224,6 +248,7 @@ def explain_linear(spec, mask, n_fft, hop, win_length, length=None, window=None,
     return explain_spec(spec, mask, n_fft, hop, win_length, length=length, mode="linear", window=window, outside=outside)
 
 
+@_on_input_device
 def mask_apply(mag, phase, mask, mode="log1p"):
     """(|X|, angle X, mask) [B,F,T] -> (rel, irr) complex [B,F,T] exactly as the reference spells it
     (expm1(m*log1p(mag)) * exp(1j*phase)); outputs are frame-major like torch.stft's."""
@@ -250,6 +275,7 @@ class LmacWorkspace:
         self.sums = torch.zeros(6, dtype=torch.float64, device=device)
 
 
+@_on_input_device
 def lmac(p, theta, q, is_logit=False, want_scores=True, workspace=None, accumulate=False):
     """Three [N] or [N,1] tensors -> (scores [N,7] or None, sums float64 [6]) on the device.
     Score columns: faithfulness, fidelity, AD, AI, AG, pc, oc; sums = the first five summed, then N."""
@@ -267,6 +293,7 @@ def lmac(p, theta, q, is_logit=False, want_scores=True, workspace=None, accumula
     return scores, ws.sums
 
 
+@_on_input_device
 def td_mask(wave, attribution, want_mask=True):
     """captum_saliency.py:136-143 per clip: returns (mask, wave*mask, wave*(1-mask))."""
     wave = _f32_rows(wave if wave.dim() == 2 else wave.unsqueeze(0), "wave")
@@ -281,6 +308,7 @@ def td_mask(wave, attribution, want_mask=True):
     return m, rel, irr
 
 
+@_on_input_device
 def mask_head(y1, weight, bias):
     """sigmoid(conv1x1(C->1)) on [B,C,H,W] -> [B,1,H,W] (addvisor.py:57-60,82)."""
     dev = _dev()
@@ -295,6 +323,7 @@ def mask_head(y1, weight, bias):
     return out
 
 
+@_on_input_device
 def band_swap(spec_real, spec_voc, f_lo, f_hi):
     """Rows [f_lo, f_hi) of ``spec_voc`` replace those of ``spec_real`` (complex [B,F,T])."""
     dev = _dev()
@@ -314,6 +343,7 @@ def band_rows(n_bins, start_hz, end_hz, f_top=8000.0):
     return (int(idx[0]), int(idx[-1]) + 1) if idx.numel() else (0, 0)
 
 
+@_on_input_device
 def band_swap_all(spec_real, spec_voc, band_width=1000, f_max=8000, f_top=8000.0):
     """The whole fabrication loop of hifigan.py:206-214 / train_logReg_swapping.py:64-75 in one launch: for every
     ``band_width`` band below ``f_max`` the rows of ``spec_voc`` replace those of ``spec_real``.
