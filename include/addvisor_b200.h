@@ -167,6 +167,20 @@ int adv_band_swap_multi(const adv_c64* real, const adv_c64* voc, int batch, int 
 int adv_mel_project(const adv_c64* X, int64_t rows, int T, int F, const float* fb_hi, const float* fb_lo, int Kpad,
                     int n_mels, float power, int log_compress, float clip, float* out, void* stream);
 
+/* The same front-end in ONE launch (n_fft 1024): framed STFT of the plan -> |X|^power -> filterbank contraction on
+ * tcgen05 (bf16 hi/lo split, three passes: 16 mantissa bits) -> log(max(., clip)); the spectrum never leaves the SM.
+ * wav: dev float [B][wav_stride] (plan n_in samples used, reflect-padded like torch.stft centre=True); out: dev float
+ * [B][n_mels][T].  The filterbank is BAND-COMPRESSED by the host (mel.MelSpectrogram): for each of the eight 64-bin K
+ * chunks of bins 0..511 only the mel columns [n0, n0 + n) that are non-zero there are stored, as a [n][64] bf16
+ * K-major SWIZZLE_128B tile (element (r, k) at byte r*128 + (((k>>3) ^ (r&7)) << 4) + (k&7)*2); fb_tiles = all hi
+ * tiles, then (from byte lo_base) all lo tiles at the same offsets; chunk_table: HOST int [8][3] = {n0, n, byte offset}
+ * (n a multiple of 8, offsets multiples of 1024); fb_nyq: dev float [ceil16(n_mels)] = the bank's row of bin 512 (added
+ * by the epilogue).  Returns ADV_ERR_UNSUPPORTED when the tiles do not fit in shared memory next to the 128 KB operand
+ * tile (a dense bank): the caller then uses adv_stft + adv_mel_project. */
+int adv_mel_fused(const adv_plan* plan, const float* wav, int64_t wav_stride, int batch, const void* fb_tiles, int fb_bytes,
+                  int lo_base, const int* chunk_table, const float* fb_nyq, int n_mels, float power, int log_compress,
+                  float clip, float* out, void* stream);
+
 /* ---- HiFi-GAN generator layers (SpeechBrain HifiganGenerator behind hifi_gan.decode_batch, hifigan.py:180) -----
  * adv_conv1d_bf16: channels-last bf16 conv1d as an implicit GEMM, "same" length, odd tap count:
  *   out[b,l,n] = out_scale * ( bias[n] + sum_{tap,ci} w[n][tap*Cin+ci] * lrelu(in[b, l+(tap-center)*dil, ci], pre_slope)

@@ -214,6 +214,64 @@ def test_mel_against_reference_golden(pkg):
     assert np.abs(got - g["mel"]).max() / np.abs(g["mel"]).max() < 1e-4
 
 
+@pytest.mark.parametrize("variant", ["torchaudio_default", "speechbrain_vocoder"])
+@pytest.mark.parametrize("B,n", [(1, 16000), (3, 64000), (5, 23456), (64, 8000)])
+def test_mel_fused_single_launch(pkg, variant, B, n):
+    """adv_mel_fused (STFT -> |X|^p -> band-compressed bf16x3 tcgen05 filterbank -> log in one launch) against torch's
+    own stft + matmul in float64 and against the two-launch path; ragged tile fills (odd frame counts, clips that end
+    inside a 64-slot tile, reflect-padded edge frames)."""
+    g = torch.Generator().manual_seed(B * 1000 + n)
+    wav = 0.1 * torch.randn(B, n, generator=g)
+    if variant == "torchaudio_default":
+        mt = pkg.mel.MelSpectrogram(16000, 1024, 322, 644, 80)
+    else:
+        mt = pkg.mel.MelSpectrogram(16000, 1024, 256, 1024, 80, 0.0, 8000.0, 1.0, "slaney", "slaney", log_compress=True)
+    got = mt(wav.cuda())
+    assert mt.last_path == "fused"
+    mt.fused = False
+    two = mt(wav.cuda())
+    assert mt.last_path == "two-launch"
+    win = torch.hann_window(mt.win_length, dtype=torch.float64)
+    X = torch.stft(wav.double(), 1024, hop_length=mt.hop_length, win_length=mt.win_length, window=win, return_complex=True)
+    ref = (X.abs() ** mt.power).transpose(1, 2) @ mt.fb.double()
+    ref = ref.transpose(1, 2)
+    if mt.log_compress:
+        ref = torch.log(ref.clamp_min(mt.clip))
+        assert float((got.cpu().double() - ref).abs().max()) < 2e-4      # log domain: absolute == relative of x
+        assert float((got - two).abs().max()) < 2e-4
+    else:
+        assert float((got.cpu().double() - ref).abs().max() / ref.abs().max()) < 1e-4
+        assert float((got - two).abs().max() / two.abs().max()) < 1e-4
+    assert got.shape == ref.shape
+
+
+def test_mel_fused_refuses_dense_bank(pkg):
+    """A dense [513 x 80] bank does not fit next to the 128 KB operand tile: ADV_ERR_UNSUPPORTED, the caller falls back
+    to adv_stft + adv_mel_project and the result still matches."""
+    g = torch.Generator().manual_seed(11)
+    wav = 0.1 * torch.randn(2, 16000, generator=g)
+    mt = pkg.mel.MelSpectrogram(16000, 1024, 256, 1024, 80)
+    mt.fb = torch.rand(513, 80, generator=g)
+    got = mt(wav.cuda())
+    assert mt.last_path == "two-launch"
+    X = torch.stft(wav.double(), 1024, hop_length=256, window=torch.hann_window(1024, dtype=torch.float64), return_complex=True)
+    ref = ((X.abs() ** 2).transpose(1, 2) @ mt.fb.double()).transpose(1, 2)
+    assert float((got.cpu().double() - ref).abs().max() / ref.abs().max()) < 1e-4
+
+
+def test_mel_fused_generic_power_and_partial_bank(pkg):
+    """power 1.5 (out-of-line pow), 40 mels up to 4 kHz: the upper K chunks are empty and skipped."""
+    g = torch.Generator().manual_seed(12)
+    wav = 0.1 * torch.randn(4, 12000, generator=g)
+    mt = pkg.mel.MelSpectrogram(16000, 1024, 200, 800, 40, 50.0, 4000.0, 1.5)
+    got = mt(wav.cuda())
+    assert mt.last_path == "fused"
+    X = torch.stft(wav.double(), 1024, hop_length=200, win_length=800, window=torch.hann_window(800, dtype=torch.float64),
+                   return_complex=True)
+    ref = ((X.abs() ** 1.5).transpose(1, 2) @ mt.fb.double()).transpose(1, 2)
+    assert float((got.cpu().double() - ref).abs().max() / ref.abs().max()) < 1e-4
+
+
 @pytest.mark.parametrize("reflect,pipeline,fuse", [(False, "tma", "always"), (False, "tma", "auto"), (False, "tma", "never"),
                                                    (False, "gather", "never"), (True, "gather", "never"),
                                                    (True, "tma", "auto")])

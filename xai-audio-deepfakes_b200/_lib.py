@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libaddvisor_sm100.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "transform_kernels.cu", "transform3_kernels.cu", "transform4_kernels.cu", "pointwise_kernels.cu", "gemm_kernels.cu", "conv_tma_kernels.cu",
+SOURCES = ["capi.cu", "transform_kernels.cu", "transform3_kernels.cu", "transform4_kernels.cu", "pointwise_kernels.cu", "gemm_kernels.cu", "mel_fused_kernels.cu", "conv_tma_kernels.cu",
            "resunit_kernels.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC"]
@@ -109,6 +109,8 @@ _SIGS = {
 _SIGS.update({
     "adv_mel_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "adv_mel_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "adv_conv1d_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                   C.c_void_p]),

@@ -4,6 +4,16 @@
 #include <stdint.h>
 #include "../../include/addvisor_b200.h"
 
+#include <stdlib.h>
+// A/B switches (environment variables selecting an older kernel generation or an alternative policy) exist only in
+// -DADV_AB builds (ADV_NVCC_EXTRA=-DADV_AB); the product build reads no environment variable on a launch path and does
+// not instantiate the superseded kernels.
+#ifdef ADV_AB
+#define ADV_AB_ENV(name) getenv(name)
+#else
+#define ADV_AB_ENV(name) ((const char*)nullptr)
+#endif
+
 namespace adv {
 
 constexpr int kThreads = 256;  // CTA size of the transform kernels

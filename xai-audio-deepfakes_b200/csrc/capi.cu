@@ -44,19 +44,19 @@ bool pdl_enabled() {
     // istft 29.1 -> 28.7, explain 87.0 -> 85.8 us), but the pooled multi-stream step LOSES 20 % (774 k -> 613 k clips/s):
     // early-scheduled CTAs of the next explain kernel sit in griddepcontrol.wait on the shared memory the normaliser
     // CTAs of the high-priority stream were meant to use.  Opt-in therefore: ADV_PDL=1.
-    static const char* e = getenv("ADV_PDL");
+    static const char* e = ADV_AB_ENV("ADV_PDL");
     static const bool on = e && e[0] == '1';
     return on;
 }
 
 bool istft_balanced() {
-    static const char* e = getenv("ADV_ISTFT_BALANCED");
+    static const char* e = ADV_AB_ENV("ADV_ISTFT_BALANCED");
     static const bool on = e && e[0] == '1';  // measured: no gain for the wide-unit kernel (30.7 vs 29.7 us), off
     return on;
 }
 
 bool gen3_enabled() {
-    static const char* e = getenv("ADV_GEN3");   // A/B switch: ADV_GEN3=0 routes every call to the generation-2 kernels
+    static const char* e = ADV_AB_ENV("ADV_GEN3");   // A/B switch: ADV_GEN3=0 routes every call to the generation-2 kernels
     static const bool on = !(e && e[0] == '0');
     return on;
 }
@@ -86,7 +86,7 @@ Tiling choose_tiling(const adv_plan* p, int batch, int slots_per_sm, bool balanc
     // pipelined step 9 % slower (101.7 vs 94.8 us): with the longest tiles the 7th round is almost empty and the next
     // kernels / the next batch's launch fill it, while 6.92 full rounds leave nothing to overlap.  The longest tile is
     // therefore the default; ADV_TILING_BALANCED=1 selects the balanced policy (stand-alone kernel latency).
-    static const bool env_longest = getenv("ADV_TILING_BALANCED") == nullptr;
+    static const bool env_longest = ADV_AB_ENV("ADV_TILING_BALANCED") == nullptr;
     // (the stand-alone iSTFT can ask for the balanced policy, see istft_balanced)
     const bool longest = env_longest && !balanced;
     int best_k = 0;

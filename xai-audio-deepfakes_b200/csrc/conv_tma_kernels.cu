@@ -625,7 +625,7 @@ extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* b
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return ADV_ERR_INVALID;
     }
-    static const bool no_slab = getenv("ADV_NO_SLAB") != nullptr;
+    static const bool no_slab = ADV_AB_ENV("ADV_NO_SLAB") != nullptr;
     if (!no_slab && Cin == N && (Cin == 32 || Cin == 64)) {
         const int halo = ((taps - 1) / 2) * dil, rows = 128 + 2 * halo;
         if (rows <= 256) {
@@ -656,7 +656,7 @@ extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* b
                              : launch_conv_slab<32>(ms, mws, sa, (cudaStream_t)stream);
         }
     }
-    static const bool no_slab2 = getenv("ADV_NO_SLAB2") != nullptr;
+    static const bool no_slab2 = ADV_AB_ENV("ADV_NO_SLAB2") != nullptr;
     if (!no_slab && !no_slab2 && Cin % 128 == 0 && N % 128 == 0) {
         const int halo = ((taps - 1) / 2) * dil, rows = 256 + 2 * halo, rb = (rows + 1) / 2;
         if (rb <= 256) {

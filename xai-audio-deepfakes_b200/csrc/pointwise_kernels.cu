@@ -694,7 +694,7 @@ int adv_normalize_pair(float* rel, float* irr, int batch, int n, const double* s
     const int chunks = (n + kRowChunk - 1) / kRowChunk;
     // 256-thread CTAs by default; ADV_NORM_THREADS=128 selects 128-thread CTAs (one fits next to an explain kernel
     // capped at 120 registers - measured: the cap costs the explain kernel more than the overlap returns)
-    static const char* nt_env = getenv("ADV_NORM_THREADS");
+    static const char* nt_env = ADV_AB_ENV("ADV_NORM_THREADS");
     if (nt_env && nt_env[0] == '1')
         ADV_CUDA_CHECK(launch_pdl(normalize_kernel<128>, dim3(chunks, batch, 2), dim3(128), 0, (cudaStream_t)stream, rel, rel,
                                   irr, irr, n, stats, parts, 4, 0));
@@ -739,7 +739,7 @@ int adv_td_mask(const float* wave, const float* attr, int batch, int n, float* m
     const int chunks = (n + kRowChunk - 1) / kRowChunk;
     const uintptr_t al = reinterpret_cast<uintptr_t>(wave) | reinterpret_cast<uintptr_t>(attr) | reinterpret_cast<uintptr_t>(rel) |
                          reinterpret_cast<uintptr_t>(irr) | reinterpret_cast<uintptr_t>(mask_out);
-    static const bool scalar = getenv("ADV_TD_MASK_SCALAR") != nullptr;
+    static const bool scalar = ADV_AB_ENV("ADV_TD_MASK_SCALAR") != nullptr;
     if (!scalar && n % 4 == 0 && al % 16 == 0) {
         rowmax_abs4_kernel<<<dim3(chunks, batch), kPwThreads, 0, s>>>(attr, n, rowmax);
         td_mask4_kernel<<<dim3(chunks, batch), kPwThreads, 0, s>>>(wave, attr, n, rowmax, mask_out, rel, irr);

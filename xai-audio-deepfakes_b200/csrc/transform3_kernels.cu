@@ -826,11 +826,13 @@ static int sm_count_dev() { return sm_count(); }
 template <class K>
 static int resident3(K kernel, int threads, size_t smem, int cap) { return resident_memo(kernel, threads, smem, cap); }
 
+#ifdef ADV_AB
 static bool stft3_vec() {
-    static const char* e = getenv("ADV_STFT3_VEC");  // A/B: 64-bit (default) or planar ("0") exchanges in the STFT
+    static const char* e = ADV_AB_ENV("ADV_STFT3_VEC");  // A/B: 64-bit (default) or planar ("0") exchanges in the STFT
     static const bool on = !(e && e[0] == '0');
     return on;
 }
+#endif
 
 template <int NF, bool RECT, bool VEC>
 static int launch_stft3_t(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
@@ -867,12 +869,13 @@ static int launch_stft3_t(const adv_plan* p, const float* wav, int64_t wav_strid
 int launch_stft3(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,
                  float* phase, int flags, cudaStream_t s) {
     if (!p->gen3 || !gen3_enabled()) return ADV_ERR_UNSUPPORTED;
+#ifdef ADV_AB
     // n_fft 1024: the generation-2 warp-autonomous kernel (a warp per frame, 32 values per lane) measures faster than the
     // half-size complex transform with its twiddle pass here - 64 x 5 s clips, hop 322: X only 22.4 vs 27.4 us,
     // X + |X| + angle 39.5 vs 43.4 us (profiles/r02c_kbench_gen3_vs_gen2.jsonl).  ADV_STFT3_1024=1 keeps this kernel.
-    static const char* e1024 = getenv("ADV_STFT3_1024");
+    static const char* e1024 = ADV_AB_ENV("ADV_STFT3_1024");
     if (p->d.n_fft == 1024 && !(e1024 && e1024[0] == '1')) return ADV_ERR_UNSUPPORTED;
-    const bool vec = stft3_vec();
+    const bool vec = stft3_vec();   // ADV_STFT3_VEC=0: planar exchanges (measured slower: 18.9 vs 17.2 us X only)
     if (p->d.n_fft == 512) {
         if (p->d.rect_full)
             return vec ? launch_stft3_t<512, true, true>(p, wav, wav_stride, batch, X, mag, phase, flags, s)
@@ -883,6 +886,13 @@ int launch_stft3(const adv_plan* p, const float* wav, int64_t wav_stride, int ba
     // n_fft 1024: the window is always applied (a rectangular full-frame window multiplies by ones)
     return vec ? launch_stft3_t<1024, false, true>(p, wav, wav_stride, batch, X, mag, phase, flags, s)
                : launch_stft3_t<1024, false, false>(p, wav, wav_stride, batch, X, mag, phase, flags, s);
+#else
+    // product build: n_fft 512 with 64-bit exchanges; n_fft 1024 stays on the generation-2 warp-autonomous kernel, which
+    // measures faster than the half-size complex transform here (22.4 vs 27.4 us X only, 64 x 5 s clips, hop 322)
+    if (p->d.n_fft != 512) return ADV_ERR_UNSUPPORTED;
+    return p->d.rect_full ? launch_stft3_t<512, true, true>(p, wav, wav_stride, batch, X, mag, phase, flags, s)
+                          : launch_stft3_t<512, false, true>(p, wav, wav_stride, batch, X, mag, phase, flags, s);
+#endif
 }
 
 int istft3_frames_cap(const adv_plan* p) {

@@ -637,7 +637,7 @@ istft4_kernel(PlanDev P, int upc, int total_units, const float2* __restrict__ X,
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 static bool gen4_enabled() {
-    static const char* e = getenv("ADV_GEN4");   // A/B switch: ADV_GEN4=0 routes the call to the generation-3 kernel
+    static const char* e = ADV_AB_ENV("ADV_GEN4");   // A/B switch: ADV_GEN4=0 routes the call to the generation-3 kernel
     static const bool on = !(e && e[0] == '0');
     return on;
 }

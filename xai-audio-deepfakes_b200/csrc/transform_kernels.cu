@@ -1876,7 +1876,7 @@ int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int bat
         if (rc3 != ADV_ERR_UNSUPPORTED) return rc3;
     }
 #ifdef ADV_AB
-    static const char* var = getenv("ADV_STFT");  // A/B switch: "v2" one tile per CTA, "p" persistent CTA tiles
+    static const char* var = ADV_AB_ENV("ADV_STFT");  // A/B switch: "v2" one tile per CTA, "p" persistent CTA tiles
     const int which = var == nullptr ? 0 : (var[0] == 'v' ? 2 : (var[0] == 'p' ? 1 : 0));
     if (which != 0 && (flags & ADV_STFT_ZERO_PAD)) return ADV_ERR_UNSUPPORTED;  // older kernels: reflect padding only
     if (which == 2)
@@ -1890,11 +1890,11 @@ int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int bat
                               : launch_stft_p<1024, false>(p, wav, wav_stride, batch, X, mag, phase, s);
     }
 #endif  // ADV_AB
-    // n_fft 512, reflect padding, magnitude and / or phase requested (compute_stft's full return): the wide-unit kernel.
-    // Measured per 64 x 4 s clips: X + |X| + angle 31.5 us (wide) vs 36.3 us (narrow); X only 18.5 vs 17.1 us - the
-    // two-frame items of the wide kernel pay their per-item staging twice as often, which only the heavier sqrt / atan2
-    // tail amortises.  ADV_STFT_WW=0 / =all force the narrow / the wide kernel.
-    static const char* ww_env = getenv("ADV_STFT_WW");
+#ifdef ADV_AB
+    // generation 2, n_fft 512 (reachable with ADV_GEN3=0): the wide-unit kernel when magnitude and / or phase are requested
+    // (X + |X| + angle 31.5 us vs 36.3 us on the narrow units per 64 x 4 s clips; X only 18.5 vs 17.1 us).
+    // ADV_STFT_WW=0 / =all force the narrow / the wide kernel.
+    static const char* ww_env = ADV_AB_ENV("ADV_STFT_WW");
     static const bool ww_on = !(ww_env && ww_env[0] == '0'), ww_all = ww_env && ww_env[0] == 'a';
     if (ww_on && (mag || phase || ww_all) && p->d.n_fft == 512 && !(flags & ADV_STFT_ZERO_PAD))
         return p->d.rect_full ? launch_stft_ww<true>(p, wav, wav_stride, batch, X, mag, phase, s)
@@ -1902,6 +1902,11 @@ int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int bat
     if (p->d.n_fft == 512)
         return p->d.rect_full ? launch_stft_w<512, true>(p, wav, wav_stride, batch, X, mag, phase, flags, s)
                               : launch_stft_w<512, false>(p, wav, wav_stride, batch, X, mag, phase, flags, s);
+#else
+    if (p->d.n_fft == 512) return ADV_ERR_UNSUPPORTED;  // generation 3 owns n_fft 512 (plans without it cannot exist)
+#endif
+    // n_fft 1024: the warp-autonomous kernel (a warp per frame, 32 values per lane) - faster than the generation-3
+    // half-size transform (transform3_kernels.cu, launch_stft3)
     return p->d.rect_full ? launch_stft_w<1024, true>(p, wav, wav_stride, batch, X, mag, phase, flags, s)
                           : launch_stft_w<1024, false>(p, wav, wav_stride, batch, X, mag, phase, flags, s);
 }
@@ -1977,14 +1982,13 @@ int launch_istft(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int
         const int rc3 = launch_istft3(p, X, sb, st, sf, batch, out, stats, s);
         if (rc3 != ADV_ERR_UNSUPPORTED) return rc3;
     }
-    static const bool v2 = getenv("ADV_ISTFT_V2") != nullptr;  // A/B switch: the one-tile-per-CTA kernel
 #ifdef ADV_AB
+    static const bool v2 = ADV_AB_ENV("ADV_ISTFT_V2") != nullptr;  // A/B switch: the one-tile-per-CTA kernel
     if (v2 && p->d.n_fft == 512) return launch_istft_nf<512>(p, X, sb, st, sf, batch, out, stats, s);
-#endif
     if (v2 && p->d.n_fft == 1024) return launch_istft_nf<1024>(p, X, sb, st, sf, batch, out, stats, s);
-    // n_fft 512, contiguous rows, 4-sample groups aligned: the wide-unit kernel (ADV_ISTFT_W512=0 selects the
-    // narrow-unit istft_p_kernel)
-    static const char* w512_env = getenv("ADV_ISTFT_W512");
+    // generation 2, n_fft 512, contiguous rows, 4-sample groups aligned (reachable with ADV_GEN3=0 ADV_GEN4=0): the
+    // wide-unit kernel (ADV_ISTFT_W512=0 selects the narrow-unit istft_p_kernel)
+    static const char* w512_env = ADV_AB_ENV("ADV_ISTFT_W512");
     static const bool w512_on = !(w512_env && w512_env[0] == '0');
     if (w512_on && p->d.n_fft == 512 && sf == 1 && p->d.hop % 4 == 0 && p->d.n_out % 4 == 0 &&
         reinterpret_cast<uintptr_t>(out) % 16 == 0 && IWCfg::bytes(p->d.hop, p->d.whi - p->d.wlo) <= 110 * 1024) {
@@ -1995,12 +1999,17 @@ int launch_istft(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int
         return p->d.rect_full ? launch_istft_w512<true, 0>(p, X, sb, st, batch, out, stats, s)
                               : launch_istft_w512<false, 0>(p, X, sb, st, batch, out, stats, s);
     }
+#endif
+    // What is left for generation 2 in the product build: n_fft 512 with strided rows / odd hops / unaligned outputs
+    // (istft_p_kernel) and n_fft 1024 geometries outside generation 3's domain (odd hop, oversized strips).
     // n_fft 1024 (one unit per warp, 8 units per CTA): the persistent kernel measured slower than the
     // one-tile-per-CTA kernel (51 vs 47 us on 64 x 5 s clips) - it spills around the row prefetch
-    static const bool p1024 = getenv("ADV_ISTFT_P1024") != nullptr;
     if (p->d.n_fft == 512) return launch_istft_pv<512>(p, X, sb, st, sf, batch, out, stats, s);
-    return p1024 ? launch_istft_pv<1024>(p, X, sb, st, sf, batch, out, stats, s)
-                 : launch_istft_nf<1024>(p, X, sb, st, sf, batch, out, stats, s);
+#ifdef ADV_AB
+    static const bool p1024 = ADV_AB_ENV("ADV_ISTFT_P1024") != nullptr;
+    if (p1024) return launch_istft_pv<1024>(p, X, sb, st, sf, batch, out, stats, s);
+#endif
+    return launch_istft_nf<1024>(p, X, sb, st, sf, batch, out, stats, s);
 }
 
 template <int NF, int MODE, bool FROM_SPEC>
@@ -2052,8 +2061,9 @@ int launch_explain(const adv_plan* p, const float* wav, int64_t wav_stride, cons
     mode &= 0xff;
     const Tiling tl = choose_tiling(p, batch, 1);
     const bool spec = (X != nullptr);
-    static const bool narrow = getenv("ADV_EXPLAIN_NARROW") != nullptr;  // keep the 16-lane-unit kernel reachable
-    static const bool oldwide = getenv("ADV_EXPLAIN_W512") != nullptr;   // A/B: the one-tile-per-CTA wide kernel
+#ifdef ADV_AB
+    static const bool narrow = ADV_AB_ENV("ADV_EXPLAIN_NARROW") != nullptr;  // keep the 16-lane-unit kernel reachable
+    static const bool oldwide = ADV_AB_ENV("ADV_EXPLAIN_W512") != nullptr;   // A/B: the one-tile-per-CTA wide kernel
     if (p->d.n_fft == 512 && !narrow && !oldwide && !spec && !drop && p->d.hop % 4 == 0 && p->d.n_out % 4 == 0 &&
         (reinterpret_cast<uintptr_t>(rel) & 15) == 0 && (reinterpret_cast<uintptr_t>(irr) & 15) == 0 &&
         (tl.hops_per_tile * p->d.hop) % 4 == 0) {
@@ -2075,8 +2085,8 @@ int launch_explain(const adv_plan* p, const float* wav, int64_t wav_stride, cons
             return ADV_OK;
         }
     }
+#endif
 #ifndef ADV_AB
-    (void)narrow;
     if (p->d.n_fft == 512) {
 #else
     if (p->d.n_fft == 512 && !narrow) {

@@ -5,19 +5,79 @@
 SpeechBrain's ``mel_spectogram`` configures it for the vocoder (hifigan.py:163-178: slaney scale and
 norm, power 1, f_max 8000, followed by ``log(clamp(x, 1e-5))``).
 
-Pipeline: ``adv_stft`` (hann window, spectrum only) -> ``adv_mel_project``: |X|^power and the
-[F x n_mels] filterbank contraction as a 3xTF32 split GEMM on tcgen05 with fp32 TMEM accumulation
-(fp32-level accuracy; plain bf16/tf32 would miss the 1e-4 parity gate), log-compress in the epilogue.
-The filterbank itself is a constant built once on the host with the same formulas torchaudio uses.
+n_fft 1024 (every mel front-end of the reference): ONE launch, ``adv_mel_fused`` - framed STFT, |X|^power, the
+filterbank contraction on tcgen05 (bf16 hi/lo split in three passes = 16 mantissa bits, fp32 TMEM accumulation) and
+the log-compress epilogue; the spectrum never leaves the SM.  The bank is band-compressed here on the host: per
+64-bin K chunk only the mel columns that are non-zero in it are stored and multiplied.
+Other sizes, or a dense bank that does not fit in shared memory: ``adv_stft`` (hann window, spectrum only) ->
+``adv_mel_project``: |X|^power and the [F x n_mels] contraction as a 3xTF32 split GEMM on tcgen05.
+Plain bf16 / tf32 would miss the 1e-4 parity gate.  The filterbank itself is a constant built once on the host with
+the same formulas torchaudio uses.
 """
 from __future__ import annotations
 
 import math
 
+import ctypes
+
+import numpy as np
 import torch
 
 from . import ops
-from ._lib import check, lib, ptr, stream_ptr
+from ._lib import ADV_ERR_UNSUPPORTED, check, lib, ptr, stream_ptr
+
+
+def _bf16_bits(x):
+    """fp32 ndarray -> (bf16 bit patterns as uint16, the rounded values as fp32); round-to-nearest-even."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint32)
+    return r.astype(np.uint16), (r << 16).astype(np.uint32).view(np.float32)
+
+
+def pack_band_tiles(fb, n_mels):
+    """Band-compressed bf16 hi/lo operand tiles of a [F >= 513, n_mels] filterbank for ``adv_mel_fused``
+    (layout: include/addvisor_b200.h).  Returns (bytes uint8 [2 * lo_base], lo_base, chunk_table int32 [8][3], nyq fp32)."""
+    fbn = np.asarray(fb, dtype=np.float32)
+    nm = (n_mels + 15) // 16 * 16
+    table = np.zeros((8, 3), dtype=np.int32)
+    tiles_hi, tiles_lo, off = [], [], 0
+    for c in range(8):
+        blk = fbn[64 * c:64 * c + 64, :n_mels]               # [64 bins][n_mels]
+        cols = np.nonzero(np.any(blk != 0, axis=0))[0]
+        if cols.size == 0:
+            continue
+        n0 = int(cols[0]) // 8 * 8
+        n1 = min(nm, (int(cols[-1]) + 8) // 8 * 8)
+        n = n1 - n0
+        dense = np.zeros((n, 64), dtype=np.float32)           # row = mel n0 + r, column = bin inside the chunk
+        hi_col = min(n1, n_mels)
+        dense[:hi_col - n0, :] = blk[:, n0:hi_col].T
+        hb, hv = _bf16_bits(dense)
+        lb, _ = _bf16_bits(dense - hv)
+        r = np.arange(n)[:, None]
+        k = np.arange(64)[None, :]
+        pos = r * 64 + (((k >> 3) ^ (r & 7)) << 3) + (k & 7)  # uint16 index inside the swizzled tile
+        th, tl = np.zeros(n * 64, dtype=np.uint16), np.zeros(n * 64, dtype=np.uint16)
+        th[pos.ravel()] = hb.ravel()
+        tl[pos.ravel()] = lb.ravel()
+        tiles_hi.append(th)
+        tiles_lo.append(tl)
+        table[c] = (n0, n, off)
+        off += n * 128
+    lo_base = max(off, 1024)
+    buf = np.zeros(lo_base, dtype=np.uint16)                  # 2 * lo_base bytes
+    cur = 0
+    for th in tiles_hi:
+        buf[cur:cur + th.size] = th
+        cur += th.size
+    cur = lo_base // 2
+    for tl in tiles_lo:
+        buf[cur:cur + tl.size] = tl
+        cur += tl.size
+    nyq = np.zeros(nm, dtype=np.float32)
+    if fbn.shape[0] > 512:
+        nyq[:n_mels] = fbn[512, :n_mels]
+    return buf.view(np.uint8), lo_base, table, nyq
 
 
 def _hz_to_mel(f, scale):
@@ -66,6 +126,36 @@ class MelSpectrogram:
         self.fb = melscale_fbanks(n_fft // 2 + 1, float(f_min), f_max, n_mels, sample_rate, norm, mel_scale)
         self.window = torch.hann_window(self.win_length)
         self._dev = None
+        self._fused_dev, self._fused_ok = None, n_fft == 1024 and n_mels <= 128
+        self.fused = True          # set False to force the two-launch path (tests, A/B)
+        self.last_path = None      # "fused" / "two-launch": what the last call ran
+
+    def _fused_tables(self, dev):
+        if self._fused_dev != dev:
+            raw, lo_base, table, nyq = pack_band_tiles(self.fb.numpy(), self.n_mels)
+            self._ftiles = torch.from_numpy(raw.copy()).to(dev)
+            self._fnyq = torch.from_numpy(nyq).to(dev)
+            self._ftable = np.ascontiguousarray(table)
+            self._flo, self._fused_dev = int(lo_base), dev
+        return self._ftiles, self._fnyq, self._ftable, self._flo
+
+    def _call_fused(self, wav):
+        """One launch; returns None when the bank does not fit (dense) and the caller must take the two-launch path."""
+        wav = ops._f32_rows(wav, "waveform")
+        B, n = wav.shape
+        T = 1 + n // self.hop_length
+        with torch.cuda.device_of(wav):
+            plan = ops.get_plan(self.n_fft, self.hop_length, self.win_length, self.window, T, n, 0)  # forward-only plan
+            tiles, nyq, table, lo_base = self._fused_tables(wav.device)
+            out = torch.empty((B, self.n_mels, T), dtype=torch.float32, device=wav.device)
+            rc = lib().adv_mel_fused(plan.handle, ptr(wav), wav.stride(0), B, ptr(tiles), tiles.numel(), lo_base,
+                                     table.ctypes.data_as(ctypes.c_void_p), ptr(nyq), self.n_mels, self.power,
+                                     int(self.log_compress), self.clip, ptr(out), stream_ptr())
+        if rc == ADV_ERR_UNSUPPORTED:
+            self._fused_ok = False
+            return None
+        check(rc, "adv_mel_fused")
+        return out
 
     def _tables(self, dev):
         if self._dev != dev:
@@ -84,6 +174,12 @@ class MelSpectrogram:
     def __call__(self, waveform):
         shape = waveform.shape
         wav = waveform.reshape(-1, shape[-1])
+        if self.fused and self._fused_ok and wav.shape[-1] > self.n_fft // 2:
+            out = self._call_fused(wav)
+            if out is not None:
+                self.last_path = "fused"
+                return out.reshape(*shape[:-1], self.n_mels, out.shape[-1])
+        self.last_path = "two-launch"
         X, _, _ = ops.stft(wav, self.n_fft, self.hop_length, self.win_length, window=self.window, want_mag=False,
                            want_phase=False)
         B, F, T = X.shape
