@@ -226,6 +226,16 @@ int adv_avg_relayout_bf16(const void* a, const void* b, const void* c, int batch
 int adv_post_conv_tanh(const void* in, const float* w, const float* bias, int batch, int L, int C, int taps, float slope,
                        int pad_reflect, float* out, void* stream);
 
+/* ---- AudioProcessor.load_audio for a BATCH of clips (audioprocessor.py:49-63): decode + resample + pad / crop in one
+ * launch.  in: dev int16 PCM (in_is_pcm16 != 0; scaled by 1/32768 like torchaudio.load) or dev float, clip b = the
+ * lens[b] samples from element offs[b] (dev int64 / dev int arrays); orig / newf: source / target rate divided by their
+ * gcd; h: dev float [newf][2*width + orig] polyphase sinc filter of torchaudio.transforms.Resample (defaults), range:
+ * dev int [newf][2] first / past-last non-zero tap of every phase; out: dev float [B][n_out],
+ * out[b][j] = sum_k h[j % newf][k] * x_b[(j / newf) * orig + k - width] for j < ceil(newf * len_b / orig), zero beyond
+ * (F.pad to audio_length * target_sr) and cropped at n_out.  orig == newf: conversion and pad / crop only (h may be NULL). */
+int adv_resample_rows(const void* in, int in_is_pcm16, const long long* offs, const int* lens, int batch, int orig, int newf,
+                      int width, const float* h, const int* range, int n_out, float* out, void* stream);
+
 /* Cross-correlation alignment shift of align_waveforms (hifigan.py:113-136):
  *   cc[j] = sum_i ref[j + i - n_deg] * deg[i], j = 0 .. n_ref + n_deg;  *shift = argmax_j cc[j] - n_deg (first maximum).
  * Direct fp32 accumulation like the reference's conv1d.  ws_val / ws_idx: dev scratch of adv_xcorr_blocks(n_ref, n_deg)

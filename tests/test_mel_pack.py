@@ -46,3 +46,18 @@ def test_bf16_bits_round_to_nearest_even():
     want = torch.from_numpy(x).to(torch.bfloat16)
     assert np.array_equal(vals, want.float().numpy())
     assert np.array_equal(bits, want.view(torch.int16).numpy().view(np.uint16))
+
+
+def test_resample_filter_is_torchaudio_default():
+    """audioprocessor.resample_filter restates T.Resample's kernel construction; where torchaudio's own (private) builder
+    is importable the taps must be bit-identical, and every tap outside the per-phase range must be zero."""
+    FF = pytest.importorskip("torchaudio.functional.functional")
+    import math
+    ap = pkg.audioprocessor
+    for o, n in [(44100, 16000), (8000, 16000), (22050, 16000), (48000, 16000)]:
+        h, rng, orig, new, width = ap.resample_filter(o, n)
+        k, w = FF._get_sinc_resample_kernel(o, n, math.gcd(o, n))
+        assert w == width and torch.equal(h, k[:, 0, :])
+        for p in range(new):
+            lo, hi = int(rng[p, 0]), int(rng[p, 1])
+            assert not h[p, :lo].any() and not h[p, hi:].any()

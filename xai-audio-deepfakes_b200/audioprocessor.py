@@ -15,6 +15,7 @@ kernel and then calls whatever ``wav2vec2`` module ``classifier_embedder`` holds
 """
 from __future__ import annotations
 
+import math
 import wave as _wave
 
 import numpy as np
@@ -27,6 +28,65 @@ from . import ops
 def _device():
     ops._lib.require_cuda()
     return torch.device("cuda", torch.cuda.current_device())
+
+
+def resample_filter(orig_freq, new_freq, lowpass_filter_width=6, rolloff=0.99):
+    """Polyphase sinc filter of ``torchaudio.transforms.Resample(orig_freq, new_freq)`` with its defaults
+    (sinc_interp_hann) - the transform ``load_audio`` applies (audioprocessor.py:53-55) - built with the same torch
+    expressions, dtypes included (float32 phase offsets, float64 tap positions), so the taps are bit-identical.
+    Returns (h float32 [new][2*width + orig], range int32 [new][2] = non-zero tap span per phase, orig, new, width)
+    with orig / new divided by their gcd.  A host-side constant like the mel filterbank."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base_freq = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base_freq)
+    idx = torch.arange(-width, width + orig, dtype=torch.float64)[None, None] / orig
+    t = torch.arange(0, -new, -1)[:, None, None] / new + idx
+    t *= base_freq
+    t = t.clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t *= math.pi
+    scale = base_freq / orig
+    kernels = torch.where(t == 0, torch.tensor(1.0).to(t), t.sin() / t)
+    kernels *= window * scale
+    h = kernels.to(torch.float32)[:, 0, :].contiguous()
+    nz = h != 0
+    lo = torch.where(nz.any(1), nz.float().argmax(1), torch.zeros(new, dtype=torch.long))
+    hi = torch.where(nz.any(1), h.shape[1] - nz.flip(1).float().argmax(1), torch.zeros(new, dtype=torch.long))
+    rng = torch.stack([lo, hi], 1).to(torch.int32).contiguous()
+    return h, rng, orig, new, width
+
+
+def resample_rows(src, offsets, lengths, orig_freq, new_freq, n_out):
+    """Clips ``src[offsets[b] : offsets[b] + lengths[b]]`` (CUDA int16 PCM or float32, mono) -> float32 [B, n_out]:
+    decoded (int16 / 32768), resampled orig_freq -> new_freq like ``T.Resample``, zero-padded / cropped to n_out
+    (audioprocessor.py:49-63 for a whole batch in one launch, ``adv_resample_rows``)."""
+    lib_, L = ops._lib.lib(), ops._lib
+    dev = src.device
+    offs = torch.as_tensor(offsets, dtype=torch.int64).to(dev)
+    lens = torch.as_tensor(lengths, dtype=torch.int32).to(dev)
+    B = int(lens.numel())
+    out = torch.empty((B, int(n_out)), dtype=torch.float32, device=dev)
+    if int(orig_freq) == int(new_freq):
+        h = rng = None
+        orig = new = 1
+        width = 0
+    else:
+        key = (int(orig_freq), int(new_freq), str(dev))
+        if key not in _RESAMPLE_TABLES:
+            h, rng, orig, new, width = resample_filter(orig_freq, new_freq)
+            _RESAMPLE_TABLES[key] = (h.to(dev), rng.to(dev), orig, new, width)
+        h, rng, orig, new, width = _RESAMPLE_TABLES[key]
+    if src.dtype not in (torch.int16, torch.float32):
+        raise TypeError("resample_rows expects int16 PCM or float32 samples")
+    with torch.cuda.device(dev):
+        L.check(lib_.adv_resample_rows(L.ptr(src), int(src.dtype == torch.int16), L.ptr(offs), L.ptr(lens), B, orig, new,
+                                       width, L.ptr(h), L.ptr(rng), int(n_out), L.ptr(out), L.stream_ptr()),
+                "adv_resample_rows")
+    return out
+
+
+_RESAMPLE_TABLES = {}
 
 
 class AudioProcessor:
@@ -70,6 +130,38 @@ class AudioProcessor:
             import torchaudio.transforms as T
             audio = T.Resample(orig_freq=sr, new_freq=target_sr)(audio)
         return self._fit(audio, int(self.audio_length * target_sr)), target_sr
+
+    def load_audio_batch(self, audio_paths, target_sr=16000):
+        """``load_audio`` for a list of files -> (float32 CUDA tensor [B, audio_length * target_sr], target_sr).
+        Host side: the PCM16 payloads are read with the stdlib ``wave`` module into ONE pinned buffer and copied once;
+        device side: decode, per-source-rate sinc resampling (T.Resample's filter) and pad / crop for all clips of a
+        rate in one launch - instead of B x (torchaudio.load, Resample, F.pad) on the host and B copies.
+        (batched wav I/O.)"""
+        n_out = int(self.audio_length * target_sr)
+        meta, chunks, pos = [], [], 0
+        for path in audio_paths:
+            with _wave.open(path, "rb") as f:
+                sr, ch, width = f.getframerate(), f.getnchannels(), f.getsampwidth()
+                if width != 2 or ch != 1:   # the reference's squeeze(0) only handles mono; 16-bit PCM is what it ships
+                    raise ValueError(f"{path}: expected mono 16-bit PCM (got {ch} channels, {8 * width} bits)")
+                pcm = np.frombuffer(f.readframes(f.getnframes()), dtype="<i2")
+            meta.append((sr, pos, pcm.size))
+            chunks.append(pcm)
+            pos += pcm.size
+        dev = _device()
+        host = torch.empty(max(pos, 1), dtype=torch.int16).pin_memory()
+        if pos:
+            host[:pos] = torch.from_numpy(np.concatenate(chunks))
+        src = host.to(dev, non_blocking=True)
+        out = torch.empty((len(meta), n_out), dtype=torch.float32, device=dev)
+        for sr in sorted({m[0] for m in meta}):
+            rows = [i for i, m in enumerate(meta) if m[0] == sr]
+            part = resample_rows(src, [meta[i][1] for i in rows], [meta[i][2] for i in rows], sr, target_sr, n_out)
+            if len(rows) == len(meta):
+                out = part
+            else:
+                out[torch.as_tensor(rows, device=dev)] = part
+        return out, target_sr
 
     @staticmethod
     def _fit(x, length):

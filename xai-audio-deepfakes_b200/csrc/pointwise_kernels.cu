@@ -835,3 +835,65 @@ extern "C" int adv_band_swap_multi(const adv_c64* real, const adv_c64* voc, int 
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// AudioProcessor.load_audio, batched (audioprocessor.py:49-63): PCM16 -> float (/ 32768, torchaudio.load's normalisation)
+// -> optional sinc resampling (torchaudio.transforms.Resample defaults: sinc_interp_hann, lowpass_filter_width 6, rolloff
+// 0.99) -> zero-pad / crop to n_out samples, for B ragged clips in one launch.  The polyphase filter h[new][K]
+// (K = 2 width + orig) is built on the host with torchaudio's own formula (audioprocessor.resample_filter);
+// out[b][j] = sum_k h[j % new][k] * x_b[(j / new) * orig + k - width]   for j < ceil(new * len_b / orig), zero beyond;
+// only the taps inside [range[p].x, range[p].y) are non-zero for phase p (the formula clamps t to the window's support:
+// ~34 of 475 taps for 44.1 kHz -> 16 kHz) and only those are summed.
+// ---------------------------------------------------------------------------------------------------------------------
+template <class TIn>
+__device__ __forceinline__ float sample_as_float(const TIn* p, long i);
+template <>
+__device__ __forceinline__ float sample_as_float<short>(const short* p, long i) { return (float)p[i] * (1.0f / 32768.0f); }
+template <>
+__device__ __forceinline__ float sample_as_float<float>(const float* p, long i) { return p[i]; }
+
+template <class TIn>
+__global__ void resample_rows_kernel(const TIn* __restrict__ in, const long long* __restrict__ offs, const int* __restrict__ lens,
+                                     int orig, int newf, int width, int K, const float* __restrict__ h,
+                                     const int2* __restrict__ range, int n_out, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int len = lens[b];
+    const TIn* x = in + offs[b];
+    const long long target = orig == newf ? (long long)len : ((long long)newf * len + orig - 1) / orig;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += gridDim.x * blockDim.x) {
+        float acc = 0.0f;
+        if (j < target) {
+            if (orig == newf) {
+                acc = sample_as_float<TIn>(x, j);
+            } else {
+                const int n = j / newf, p = j - n * newf;
+                const int2 r = range[p];
+                const long base = (long)n * orig - width;
+                const float* hp = h + (size_t)p * K;
+                for (int k = r.x; k < r.y; ++k) {
+                    const long i = base + k;
+                    if (i >= 0 && i < len) acc = fmaf(hp[k], sample_as_float<TIn>(x, i), acc);
+                }
+            }
+        }
+        out[(size_t)b * n_out + j] = acc;
+    }
+}
+
+extern "C" int adv_resample_rows(const void* in, int in_is_pcm16, const long long* offs, const int* lens, int batch, int orig,
+                                 int newf, int width, const float* h, const int* range, int n_out, float* out, void* stream) {
+    if (!in || !offs || !lens || !out || batch <= 0 || n_out <= 0 || orig <= 0 || newf <= 0) return ADV_ERR_INVALID;
+    if (orig != newf && (!h || !range || width <= 0)) return ADV_ERR_INVALID;
+    const int K = 2 * width + orig;
+    int gx = (n_out + kPwThreads - 1) / kPwThreads;
+    if (gx > 148 * 8) gx = 148 * 8;
+    dim3 grid(gx, batch);
+    if (in_is_pcm16)
+        resample_rows_kernel<short><<<grid, kPwThreads, 0, (cudaStream_t)stream>>>((const short*)in, offs, lens, orig, newf, width,
+                                                                                   K, h, (const int2*)range, n_out, out);
+    else
+        resample_rows_kernel<float><<<grid, kPwThreads, 0, (cudaStream_t)stream>>>((const float*)in, offs, lens, orig, newf, width,
+                                                                                   K, h, (const int2*)range, n_out, out);
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
