@@ -48,6 +48,11 @@ typedef struct adv_plan adv_plan;
 typedef struct adv_c64 { float re, im; } adv_c64;
 
 int adv_version(void);
+/* Programmatic dependent launch for the transform / normalise / metric kernels (a kernel's set-up overlaps the tail of
+ * the previous kernel of the same stream; every kernel waits for its predecessor before touching data).  Process-wide,
+ * on by default; returns the previous setting.  Multi-stream pipelines that co-schedule kernels on one SM may prefer it
+ * off (pipeline.PipelinedPool does). */
+int adv_set_pdl(int on);
 const char* adv_strerror(int status);
 const char* adv_last_cuda_error(void);
 

@@ -24,11 +24,14 @@ ap.add_argument("--pool", type=int, default=16)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--tag", default="")
 ap.add_argument("--winlen", type=int, default=0)
+ap.add_argument("--pdl", type=int, default=-1, help="0 / 1: programmatic dependent launch off / on (default: the library's)")
 args = ap.parse_args()
 
 pkg = importlib.import_module("xai-audio-deepfakes_b200")
 pkg._lib.build()
 ops = pkg.ops
+if args.pdl >= 0:
+    pkg._lib.lib().adv_set_pdl(args.pdl)
 B, n, n_fft, hop = args.batch, args.n, args.nfft, args.hop
 win_len = args.winlen or (n_fft if n_fft == 512 else 644)
 window = None if args.win == "rect" else torch.hann_window(win_len)

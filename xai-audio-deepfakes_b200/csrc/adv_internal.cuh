@@ -46,8 +46,21 @@ struct adv_plan {
     int max_hops_cap[2];  // the same for tiles of 16 / 32 frames (generation-3 kernels: 16 warps x 1 or 2 frames)
     int gen3;             // generation-3 kernels usable for this geometry (n_fft 512, or n_fft 1024 with an even hop)
     int device;
-    void* dev_block;      // single allocation holding window / inv_env / tw
+    void* dev_block;      // single allocation holding window / inv_env / tw / work counters
+    int* work_ctr;        // dev [kWorkSlots][kWorkInts] zeroed ints: draw counters + finished warps of a dynamically scheduled launch
+    unsigned work_next;   // host: slot of the next such launch (rotates, so launches in flight never share a slot)
 };
+
+namespace adv {
+constexpr int kWorkSlots = 64, kWorkGroups = 16, kWorkPad = 64, kWorkInts = (kWorkGroups + 1) * kWorkPad;   // per launch: kWorkGroups draw counters + the finished-warp count, 256 bytes apart (separate L2 lines)
+// Counter pair for one launch of a dynamically scheduled kernel (stft3_kernel).  The kernel leaves both at zero when its
+// last warp retires, so a slot can be baked into a CUDA graph and replayed; slots rotate per launch, so up to kWorkSlots
+// launches of one plan may be in flight (or captured in graphs that run concurrently) at once.
+static inline int* next_work_slot(const adv_plan* p) {
+    const unsigned k = __atomic_fetch_add(&const_cast<adv_plan*>(p)->work_next, 1u, __ATOMIC_RELAXED);
+    return p->work_ctr + kWorkInts * (k % kWorkSlots);
+}
+}  // namespace adv
 
 namespace adv {
 void set_cuda_error(cudaError_t e);

@@ -39,15 +39,13 @@ static int tile_frame_span(const PlanDev& d, int k) {
     return worst;
 }
 
-bool pdl_enabled() {
-    // Measured (B200, 64 x 4 s clips): back-to-back launches of one kernel gain 0.4 - 1.2 us (stft 17.1 -> 16.7,
-    // istft 29.1 -> 28.7, explain 87.0 -> 85.8 us), but the pooled multi-stream step LOSES 20 % (774 k -> 613 k clips/s):
-    // early-scheduled CTAs of the next explain kernel sit in griddepcontrol.wait on the shared memory the normaliser
-    // CTAs of the high-priority stream were meant to use.  Opt-in therefore: ADV_PDL=1.
-    static const char* e = ADV_AB_ENV("ADV_PDL");
-    static const bool on = e && e[0] == '1';
-    return on;
-}
+// Programmatic dependent launch: on by default (adv_set_pdl).  Measured (B200, 64 x 4 s clips): back-to-back launches on
+// ONE stream gain 0.4 - 1.2 us each (the next kernel's table staging and barrier set-up run under the previous kernel's
+// tail), but the pooled multi-stream step of pipeline.PipelinedPool LOSES 20 % (774 k -> 613 k clips/s): early-scheduled
+// CTAs of the next explain kernel sit in griddepcontrol.wait on the shared memory the normaliser CTAs of the
+// high-priority stream were meant to use - that pipeline switches it off for its own capture.
+static int g_pdl = 1;
+bool pdl_enabled() { return __atomic_load_n(&g_pdl, __ATOMIC_RELAXED) != 0; }
 
 bool istft_balanced() {
     static const char* e = ADV_AB_ENV("ADV_ISTFT_BALANCED");
@@ -113,7 +111,9 @@ using namespace adv;
 
 extern "C" {
 
-int adv_version(void) { return 100; }
+int adv_version(void) { return 101; }
+
+int adv_set_pdl(int on) { return __atomic_exchange_n(&adv::g_pdl, on ? 1 : 0, __ATOMIC_RELAXED); }
 
 const char* adv_strerror(int status) {
     switch (status) {
@@ -185,7 +185,9 @@ int adv_plan_create(adv_plan** out, int n_fft, int hop, int win_length, const fl
     const size_t b_tw3 = sizeof(float2) * tw3.size();
     const size_t o_env = (b_win + 255) / 256 * 256, o_tw = o_env + (b_env + 255) / 256 * 256;
     const size_t o_tw3 = o_tw + (b_tw + 255) / 256 * 256;
-    cudaError_t e = cudaMalloc(&p->dev_block, o_tw3 + b_tw3);
+    const size_t o_work = o_tw3 + (b_tw3 + 255) / 256 * 256, b_work = sizeof(int) * kWorkInts * kWorkSlots;
+    cudaError_t e = cudaMalloc(&p->dev_block, o_work + b_work);
+    if (e == cudaSuccess) e = cudaMemset((char*)p->dev_block + o_work, 0, b_work);
     if (e == cudaSuccess) e = cudaMemcpy((char*)p->dev_block + o_tw3, tw3.data(), b_tw3, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy((char*)p->dev_block, win.data(), b_win, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy((char*)p->dev_block + o_env, inv_env.data(), b_env, cudaMemcpyHostToDevice);
@@ -212,6 +214,8 @@ int adv_plan_create(adv_plan** out, int n_fft, int hop, int win_length, const fl
     p->d.inv_env = (const float*)((char*)p->dev_block + o_env);
     p->d.tw = (const float2*)((char*)p->dev_block + o_tw);
     p->d.tw3 = (const float2*)((char*)p->dev_block + o_tw3);
+    p->work_ctr = (int*)((char*)p->dev_block + o_work);
+    p->work_next = 0;
     p->gen3 = (n_fft == 512 || (n_fft == 1024 && hop % 2 == 0)) ? 1 : 0;
     p->win_length = win_length;
     p->frames_per_tile = 2 * (kThreads / lanes);

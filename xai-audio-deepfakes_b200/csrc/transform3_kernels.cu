@@ -65,9 +65,12 @@ template <int NF, bool MAG, bool PHASE, bool RECT, bool VEC, bool ZP>
 #ifndef ADV_STFT3_VEC_CTAS
 #define ADV_STFT3_VEC_CTAS 3
 #endif
+#ifndef ADV_STFT3_DYN
+#define ADV_STFT3_DYN 0   // 1: items drawn from per-group counters instead of the static round-robin (A/B, see the kernel)
+#endif
 __global__ void __launch_bounds__(kThreads, VEC ? ADV_STFT3_VEC_CTAS : 4)
 stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int total_items, int items_per_clip,
-             float2* __restrict__ X, float* __restrict__ mag, float* __restrict__ phase) {
+             float2* __restrict__ X, float* __restrict__ mag, float* __restrict__ phase, int* __restrict__ work, int groups) {
     using C = S3Cfg<NF, VEC>;
     constexpr int F = NF / 2 + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -82,6 +85,62 @@ stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int t
     float* seg = seg_all + (size_t)w * C::seg_floats(P.hop);
     uint64_t* bar = bars + w;
     const int seglen = P.hop + NF;
+#if ADV_STFT3_DYN
+    // A/B variant (-DADV_STFT3_DYN=1): every warp starts on item blockIdx * WARPS + w and then DRAWS its next items from
+    // a counter instead of walking the static round-robin.  Why it exists: at 1 024 clips with all three outputs the static
+    // schedule leaves SMs idle for 16 % of the launch (ncu, profiles/r02s_*: per-SM active cycles 639 k ... 894 k of 907 k -
+    // SMs differ in their write path to HBM).  The CTAs form `groups` equal groups (blockIdx mod groups, groups = the largest
+    // divisor of the grid up to 16, members spread over the chip); group g draws from its own counter - 256 bytes apart: 12
+    // counters in ONE L2 line serialise like one (17.2 -> 23.7 us per 64 clips, 218 -> 460 us per 1 024) - and owns the items
+    // n_warps + g + groups * j.  Draws are issued two items ahead (lane 0, broadcast when needed).
+    // Measured (profiles/r02v_stft_dyn_ab.jsonl): X + |X| + angle at 1 024 clips 455 -> 426 us (66 -> 70 % of HBM peak), no
+    // change at 256 clips (111.9 / 111.5 us), SLOWER at 64 clips (28.0 -> 30.4 us; X only 17.6 -> 20.5 us: the opening draws
+    // and a non-uniform trip count cost more than 3.6 items per warp can win back).  The static schedule stays the default.
+    const int n_warps = gridDim.x * C::WARPS;
+    const int grp = blockIdx.x % groups;
+    auto draw = [&]() -> int { return l == 0 ? n_warps + grp + groups * atomicAdd(work + grp * kWorkPad, 1) : 0; };
+
+    if (l == 0) mbar_init(bar, 1);
+    stage_tw3<NF, kThreads>(tw_s, win_s, P, !RECT);
+    pdl_launch_dependents();
+    cp_async_wait_all();
+    __syncthreads();  // tables staged, barriers initialised
+    pdl_wait();
+
+    float* my = scratch + w * f3::Scr<VEC>::FLOATS;
+    const int q1 = q1_lane(l);
+    int item = blockIdx.x * C::WARPS + w;
+    int d1 = 0, d2 = 0;
+    bool have = item < total_items;
+    int b = 0, t0 = 0, shift = 0;
+    if (have) {
+        d1 = draw();
+        d2 = draw();
+        b = item / items_per_clip;
+        t0 = (item - b * items_per_clip) * 2;
+        shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar, l, ZP);
+    }
+    constexpr bool active = true;
+
+    for (uint32_t it = 0; have; ++it) {
+        __syncwarp();  // plain-load part of the slice visible to the warp
+        mbar_wait(bar, it & 1);
+        const int cur_b = b, fa = t0, cur_shift = shift;
+        const int next = __shfl_sync(0xffffffffu, d1, 0);
+        const bool more = next < total_items;   // (warp-uniform)
+        have = more;
+        d1 = d2;
+        d2 = more ? draw() : 0;
+        auto request_next = [&]() {   // (called from inside the forward transform: every lane has consumed its samples)
+            if (more) {
+                item = next;
+                b = item / items_per_clip;
+                t0 = (item - b * items_per_clip) * 2;
+                shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar,
+                                                l, ZP);
+            }
+        };
+#else
     const int stride = gridDim.x * C::WARPS;
     // CTA-uniform trip count (the grid never exceeds ceil(items / WARPS) CTAs): every warp runs the same loop, so the
     // transforms - and their __syncwarp()s - sit in provably convergent code.  A warp whose item index runs past the
@@ -117,6 +176,7 @@ stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int t
                                                 l, ZP);
             }
         };
+#endif
         if constexpr (NF == 512) {
             float2 v[16];
             {
@@ -181,6 +241,19 @@ stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int t
             }
         }
     }
+#if ADV_STFT3_DYN
+    // Retire: the warp's outstanding draws must have returned before it reports (a draw still in flight would land on
+    // the counter AFTER the reset below); the last warp of the launch leaves both counters at zero for the next one.
+    if (l == 0) {
+        asm volatile("" ::"r"(d1), "r"(d2) : "memory");
+        __threadfence();
+        if (atomicAdd(work + kWorkGroups * kWorkPad, 1) == n_warps - 1) {
+#pragma unroll
+            for (int i = 0; i <= kWorkGroups; ++i) work[i * kWorkPad] = 0;
+            __threadfence();
+        }
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -851,8 +924,10 @@ static int launch_stft3_t(const adv_plan* p, const float* wav, int64_t wav_strid
         if ((rc = set_smem(kernel, smem)) != ADV_OK) return rc;                                                  \
         const long slots = (long)resident3(kernel, kThreads, smem, VEC ? ADV_STFT3_VEC_CTAS : 4) * sm_count_dev();                \
         const int grid = (int)(ctas < slots ? ctas : slots);                                                     \
+        int groups = kWorkGroups;                                                                                \
+        while (grid % groups != 0) --groups;                                                                     \
         ADV_CUDA_CHECK(launch_pdl(kernel, grid, kThreads, smem, s, p->d, wav, wav_stride, (int)total,            \
-                                  items_per_clip, X, mag, phase));                                               \
+                                  items_per_clip, X, mag, phase, next_work_slot(p), groups));                    \
     } while (0)
     if (zero_pad) {  // the adjoint-of-istft use (training backward): spectrum only
         if (mag || phase) return ADV_ERR_UNSUPPORTED;

@@ -96,7 +96,11 @@ class PipelinedPool:
     that two 256-thread CTAs of the memory-bound normaliser fit next to a resident explain CTA: the normaliser of
     batch j streams through L2 / HBM while explain(j+1) owns the issue slots.  One replay = ``len(pool)`` steps."""
 
-    def __init__(self, audio_processor, batch, sets, mode="log1p", explain_streams=2, accumulate=True):
+    def __init__(self, audio_processor, batch, sets, mode="log1p", explain_streams=2, accumulate=True, pdl=False):
+        # programmatic dependent launch stays OFF for this schedule: early-scheduled CTAs of the next explain kernel would
+        # sit in griddepcontrol.wait on the shared memory the normaliser CTAs of the high-priority stream are meant to
+        # use (measured: 774 k -> 613 k clips/s); single-stream chains keep the library default (on)
+        self.pdl = bool(pdl)
         self.pipes = [ExplainPipeline(audio_processor, batch, mode, use_graph=False, accumulate=accumulate)
                       for _ in range(sets)]
         dev = self.pipes[0].dev
@@ -110,6 +114,14 @@ class PipelinedPool:
     def _enqueue_all(self, root, count=None):
         """``count`` steps (default: one per buffer set); step i runs on buffer set i % len(pipes) - a set that is used
         again waits for the normaliser / metric reduction of its previous step."""
+        from ._lib import lib
+        prev = lib().adv_set_pdl(int(self.pdl))
+        try:
+            self._enqueue_all_inner(root, count)
+        finally:
+            lib().adv_set_pdl(prev)
+
+    def _enqueue_all_inner(self, root, count=None):
         n = len(self.pipes)
         count = n if count is None else count
         start = torch.cuda.Event()
