@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libaddvisor_sm100.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "transform_kernels.cu", "transform3_kernels.cu", "transform4_kernels.cu", "pointwise_kernels.cu", "gemm_kernels.cu", "mel_fused_kernels.cu", "conv_tma_kernels.cu",
+SOURCES = ["capi.cu", "transform_kernels.cu", "transform3_kernels.cu", "transform4_kernels.cu", "transform5_kernels.cu", "pointwise_kernels.cu", "gemm_kernels.cu", "mel_fused_kernels.cu", "conv_tma_kernels.cu",
            "resunit_kernels.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC"]

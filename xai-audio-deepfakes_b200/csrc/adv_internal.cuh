@@ -44,6 +44,7 @@ struct adv_plan {
     int frames_per_tile;  // capacity of one CTA pass: 2 * units
     int max_hops;         // largest hops_per_tile whose frame span fits frames_per_tile
     int max_hops_cap[2];  // the same for tiles of 16 / 32 frames (generation-3 kernels: 16 warps x 1 or 2 frames)
+    int rect_sup;         // window == 1 on its whole support [wlo, whi) (a rectangular win_length < n_fft window)
     int gen3;             // generation-3 kernels usable for this geometry (n_fft 512, or n_fft 1024 with an even hop)
     int device;
     void* dev_block;      // single allocation holding window / inv_env / tw / work counters
@@ -84,6 +85,13 @@ int explain4_slots(const adv_plan* p, int batch);
 int launch_istft4(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
                   double* stats, cudaStream_t s);
 int istft4_slots(const adv_plan* p, int batch);
+// streaming kernels for n_fft 1024 (transform5_kernels.cu): even hop / window support / n_out, 64 <= hop <= 512, support <= 4 hops
+int launch_istft5(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
+                  double* stats, cudaStream_t s);
+int istft5_slots(const adv_plan* p, int batch);
+int launch_explain5(const adv_plan* p, const float* wav, int64_t wav_stride, const float* mask, int Fm, int Tm,
+                    int mode_flags, int batch, float* rel, float* irr, double* stats, cudaStream_t s);
+int explain5_slots(const adv_plan* p, int batch);   // 0: outside the kernel's domain (or its strips / slices do not fit)
 int istft3_frames_cap(const adv_plan* p);    // 32 when launch_istft3 takes the plan, else 0 (plan default)
 bool istft_balanced();  // tiling policy of the stand-alone iSTFT kernels (ADV_ISTFT_BALANCED=1 selects the round-balanced tile length; default: longest tile)
 int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag,

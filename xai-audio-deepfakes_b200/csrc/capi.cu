@@ -210,6 +210,9 @@ int adv_plan_create(adv_plan** out, int n_fft, int hop, int win_length, const fl
     p->d.rect_full = 1;
     for (int i = 0; i < n_fft; ++i)
         if (win[i] != 1.0f) p->d.rect_full = 0;
+    p->rect_sup = 1;
+    for (int i = wlo; i < whi; ++i)
+        if (win[i] != 1.0f) p->rect_sup = 0;
     p->d.window = (const float*)p->dev_block;
     p->d.inv_env = (const float*)((char*)p->dev_block + o_env);
     p->d.tw = (const float2*)((char*)p->dev_block + o_tw);
@@ -252,12 +255,16 @@ int adv_plan_bins(const adv_plan* plan) { return plan ? plan->d.n_fft / 2 + 1 : 
 int adv_plan_frames(const adv_plan* plan) { return plan ? plan->d.T : ADV_ERR_INVALID; }
 int adv_plan_tiles(const adv_plan* plan, int batch) {
     if (!plan || batch <= 0 || plan->d.n_out <= 0) return ADV_ERR_INVALID;
-    const int s4 = explain4_slots(plan, batch);   // statistics slots per clip of the generation-4 explain kernel
-    return s4 > 0 ? s4 : choose_tiling(plan, batch, 1).tiles;
+    const int s4 = explain4_slots(plan, batch);   // statistics slots per clip of the streaming explain kernels
+    if (s4 > 0) return s4;
+    const int s5 = explain5_slots(plan, batch);
+    return s5 > 0 ? s5 : choose_tiling(plan, batch, 1).tiles;
 }
 int adv_plan_tiles_istft(const adv_plan* plan, int batch) {
     if (!plan || batch <= 0 || plan->d.n_out <= 0) return ADV_ERR_INVALID;
     const int s4 = istft4_slots(plan, batch);   // statistics slots per clip of the streaming iSTFT
+    const int s5 = s4 > 0 ? 0 : istft5_slots(plan, batch);
+    if (s5 > 0) return s5;
     return s4 > 0 ? s4 : choose_tiling(plan, batch, 2, istft_balanced(), istft3_frames_cap(plan)).tiles;
 }
 

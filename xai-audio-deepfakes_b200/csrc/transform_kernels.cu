@@ -1978,6 +1978,11 @@ static int launch_istft_w512(const adv_plan* p, const float2* X, int64_t sb, int
 int launch_istft(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
                  double* stats, cudaStream_t s) {
     if (istft4_slots(p, batch) > 0) return launch_istft4(p, X, sb, st, sf, batch, out, stats, s);
+    if (istft5_slots(p, batch) > 0) {   // n_fft 1024 streaming kernel; the plan's statistics layout is its own
+        const int rc5 = launch_istft5(p, X, sb, st, sf, batch, out, stats, s);
+        if (rc5 != ADV_ERR_UNSUPPORTED) return rc5;
+        if (stats != nullptr) return ADV_ERR_INVALID;   // (an output row that is not 8-byte aligned)
+    }
     {
         const int rc3 = launch_istft3(p, X, sb, st, sf, batch, out, stats, s);
         if (rc3 != ADV_ERR_UNSUPPORTED) return rc3;
@@ -2052,6 +2057,13 @@ int launch_explain(const adv_plan* p, const float* wav, int64_t wav_stride, cons
     if (explain4_slots(p, batch) > 0) {   // the plan's statistics layout is the generation-4 kernel's (adv_plan_tiles)
         if (X == nullptr) return launch_explain4(p, wav, wav_stride, mask, Fm, Tm, mode, batch, rel, irr, stats, s);
         if (stats != nullptr) return ADV_ERR_INVALID;   // spectrum input wants a plan created with n_in = 0
+    }
+    if (explain5_slots(p, batch) > 0) {   // n_fft 1024 streaming kernel (the plan's statistics layout is its own)
+        if (X == nullptr) {
+            const int rc5 = launch_explain5(p, wav, wav_stride, mask, Fm, Tm, mode, batch, rel, irr, stats, s);
+            if (rc5 != ADV_ERR_UNSUPPORTED) return rc5;
+        }
+        if (stats != nullptr) return ADV_ERR_INVALID;   // spectrum input / unaligned rows want a plan created with n_in = 0
     }
     {
         const int rc3 = launch_explain3(p, wav, wav_stride, X, sb, st, sf, mask, Fm, Tm, mode, batch, rel, irr, stats, s);
