@@ -89,6 +89,8 @@ int istft4_slots(const adv_plan* p, int batch);
 int launch_istft5(const adv_plan* p, const float2* X, int64_t sb, int64_t st, int64_t sf, int batch, float* out,
                   double* stats, cudaStream_t s);
 int istft5_slots(const adv_plan* p, int batch);
+int launch_stft5(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag, float* phase,
+                 int flags, cudaStream_t s);
 int launch_explain5(const adv_plan* p, const float* wav, int64_t wav_stride, const float* mask, int Fm, int Tm,
                     int mode_flags, int batch, float* rel, float* irr, double* stats, cudaStream_t s);
 int explain5_slots(const adv_plan* p, int batch);   // 0: outside the kernel's domain (or its strips / slices do not fit)

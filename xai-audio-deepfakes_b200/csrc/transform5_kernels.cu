@@ -528,6 +528,127 @@ explain5_kernel(PlanDev P, Geo5 G, int upc, int total_units, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// STFT, n_fft 1024 (torch.stft + abs + angle, audioprocessor.py:102-110): warp-autonomous like stft3_kernel, but an item
+// is ONE frame and its slice is the window support only (644 of 1024 samples for the reference's default window - the
+// rest of the frame multiplies zeros), so the per-warp staging shrinks from hop + 1024 to ~650 floats and three 256-thread
+// CTAs share an SM (the generation-3 form of this size held two, the generation-2 form 16 warps of 128 registers).
+// A rectangular-on-its-support window costs no multiplies.  Reflect padding only (the zero-padded adjoint form stays
+// on stft_w_kernel).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kF5Warps = 8, kF5Threads = 32 * kF5Warps;
+
+struct F5Cfg {
+    static __host__ __device__ int seg_floats(int sup) { return (sup + 8 + 3) & ~3; }
+    static size_t bytes(int sup, bool rect) {
+        return al16(sizeof(float2) * f3::TW_TOTAL) + al16(sizeof(float) * kF5Warps * f3::Scr<true>::FLOATS) +
+               al16(sizeof(float) * kF5Warps * seg_floats(sup)) + (rect ? 0 : al16(sizeof(float) * 1024)) +
+               al16(sizeof(uint64_t) * kF5Warps);
+    }
+};
+
+template <bool MAG, bool PHASE>
+__device__ __forceinline__ void store_bin5(float2* __restrict__ X, float* __restrict__ mag, float* __restrict__ phase,
+                                           size_t idx, float2 x) {
+    X[idx] = x;
+    if (MAG) {  // r2 * rsqrt(r2): <= 2 ulp
+        const float r2 = fmaf(x.x, x.x, x.y * x.y);
+        mag[idx] = r2 * rsqrtf(fmaxf(r2, 1e-37f));
+    }
+    if (PHASE) phase[idx] = fast_atan2f(x.y, x.x);
+}
+
+template <bool MAG, bool PHASE, bool RECT>
+__global__ void __launch_bounds__(kF5Threads, 3)
+stft5_kernel(PlanDev P, Geo5 G, const float* __restrict__ wav, int64_t wav_stride, int total_items,
+             float2* __restrict__ X, float* __restrict__ mag, float* __restrict__ phase) {
+    constexpr int F = 513, WARPS = kF5Warps;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Carver cv{smem_raw};
+    float2* tw_s = cv.take<float2>(f3::TW_TOTAL);
+    float* scratch = cv.take<float>(WARPS * f3::Scr<true>::FLOATS);
+    const int SEG = F5Cfg::seg_floats(G.sup);
+    float* seg_all = cv.take<float>(WARPS * SEG);
+    float* win_s = RECT ? nullptr : cv.take<float>(1024);
+    uint64_t* bars = cv.take<uint64_t>(WARPS);
+
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    float* seg = seg_all + (size_t)w * SEG;
+    uint64_t* bar = bars + w;
+    const int stride = gridDim.x * WARPS;
+    // CTA-uniform trip count: the transforms and their __syncwarp()s sit in provably convergent code; a warp whose item
+    // index runs past the list repeats the last item with its stores switched off (see stft3_kernel)
+    const int first = blockIdx.x * WARPS;
+    const int n_iter = (total_items - first + stride - 1) / stride;
+
+    if (l == 0) mbar_init(bar, 1);
+    for (int i = tid; i < f3::TW_TOTAL / 2; i += kF5Threads) cp_async16(tw_s + 2 * i, P.tw3 + 2 * i);
+    if (!RECT)
+        for (int i = tid; i < 1024 / 4; i += kF5Threads) cp_async16(win_s + 4 * i, P.window + 4 * i);
+    cp_async_commit();
+    pdl_launch_dependents();
+    cp_async_wait_all();
+    __syncthreads();
+    pdl_wait();
+
+    float* my = scratch + w * f3::Scr<true>::FLOATS;
+    const int q1 = l == 0 ? 32 : 64 - l;
+    int item = min(first + w, total_items - 1);
+    int b = item / P.T, t = item - b * P.T;
+    int shift = stage_segment_async<32>(seg, G.sup, wav + (size_t)b * wav_stride, t * G.hop - 512 + G.wlo, P.n_in, bar, l);
+
+    for (int it = 0; it < n_iter; ++it) {
+        __syncwarp();
+        mbar_wait(bar, it & 1);
+        const int cur_b = b, cur_t = t, cur_shift = shift;
+        const bool active = first + it * stride + w < total_items;
+        const bool more = it + 1 < n_iter;
+        float2 v[16];
+        {
+            const float* sp = seg + cur_shift + 2 * l - G.wlo;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = 64 * j + 2 * l - G.wlo;
+                float2 x = make_float2(0.f, 0.f);
+                if ((unsigned)k < (unsigned)G.sup) {
+                    x = *reinterpret_cast<const float2*>(sp + 64 * j);
+                    if (!RECT) {
+                        const float2 ww = *reinterpret_cast<const float2*>(win_s + 64 * j + 2 * l);
+                        x.x *= ww.x;
+                        x.y *= ww.y;
+                    }
+                }
+                v[j] = x;
+            }
+        }
+        f3::fft_forward<true>(v, l, tw_s, my, [&] {   // every lane has consumed its samples: request the next slice
+            if (more) {
+                item = min(first + (it + 1) * stride + w, total_items - 1);
+                b = item / P.T;
+                t = item - b * P.T;
+                shift = stage_segment_async<32>(seg, G.sup, wav + (size_t)b * wav_stride, t * G.hop - 512 + G.wlo, P.n_in,
+                                                bar, l);
+            }
+        });
+        float2 xk[9], xm[9];
+        f3::r1024_post(v, l, tw_s, xk, xm);
+        if (active) {
+            const size_t row = ((size_t)cur_b * P.T + cur_t) * F;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                store_bin5<MAG, PHASE>(X, mag, phase, row + l + 64 * i, xk[i]);
+                store_bin5<MAG, PHASE>(X, mag, phase, row + 512 - l - 64 * i, xm[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                store_bin5<MAG, PHASE>(X, mag, phase, row + q1 + 64 * i, xk[4 + i]);
+                store_bin5<MAG, PHASE>(X, mag, phase, row + 512 - q1 - 64 * i, xm[4 + i]);
+            }
+            if (l == 0) store_bin5<MAG, PHASE>(X, mag, phase, row + 256, xk[8]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 struct Run5 { int ok, upc, grid, slots, rect; long total; Geo5 g; };
@@ -587,6 +708,50 @@ int launch_istft5(const adv_plan* p, const float2* X, int64_t sb, int64_t st, in
                 : launch_istft5_t<false, false>(p, r, X, sb, st, sf, out, stats, s);
 }
 
+
+// ---- STFT
+template <bool RECT>
+static int launch_stft5_t(const adv_plan* p, const Geo5& g, const float* wav, int64_t wav_stride, int batch, float2* X,
+                          float* mag, float* phase, cudaStream_t s) {
+    const size_t smem = F5Cfg::bytes(g.sup, RECT);
+    const long total = (long)p->d.T * batch;
+    if (total > 0x7fffffffL) return ADV_ERR_UNSUPPORTED;
+    const long ctas = (total + kF5Warps - 1) / kF5Warps;
+    int rc;
+#define ADV_LAUNCH_STFT5(M, PH)                                                                                  \
+    do {                                                                                                         \
+        auto kernel = stft5_kernel<M, PH, RECT>;                                                                 \
+        if ((rc = set_smem(kernel, smem)) != ADV_OK) return rc;                                                  \
+        const long slots = (long)resident_memo(kernel, kF5Threads, smem, 3) * sm_count();                        \
+        const int grid = (int)(ctas < slots ? ctas : slots);                                                     \
+        ADV_CUDA_CHECK(launch_pdl(kernel, grid, kF5Threads, smem, s, p->d, g, wav, wav_stride, (int)total, X, mag, phase)); \
+    } while (0)
+    if (mag && phase) ADV_LAUNCH_STFT5(true, true);
+    else if (mag) ADV_LAUNCH_STFT5(true, false);
+    else if (phase) ADV_LAUNCH_STFT5(false, true);
+    else ADV_LAUNCH_STFT5(false, false);
+#undef ADV_LAUNCH_STFT5
+    ADV_CUDA_CHECK(cudaGetLastError());
+    return ADV_OK;
+}
+
+int launch_stft5(const adv_plan* p, const float* wav, int64_t wav_stride, int batch, float2* X, float* mag, float* phase,
+                 int flags, cudaStream_t s) {
+    const PlanDev& d = p->d;
+    if (d.n_fft != 1024 || d.n_in <= 0 || (flags & ADV_STFT_ZERO_PAD) || (d.hop & 1)) return ADV_ERR_UNSUPPORTED;
+    Geo5 g = {};
+    const int wlo = d.wlo & ~1, whi = (d.whi + 1) & ~1;
+    g.hop = d.hop; g.wlo = wlo; g.sup = whi - wlo; g.nb = 0; g.strip = 0;
+    const bool rect = p->rect_sup && wlo == d.wlo && whi == d.whi;
+    // Measured (profiles/r02z_kbench_stft5.jsonl, 64 x 5 s clips, hop 322, 644-tap rectangular window): X only 22.4 -> 20.8 us
+    // (58 -> 63 % of HBM peak; 70 % at 256 clips); hann 1024 / hop 256 X only 25.7 -> 23.9 us, X + |X| + angle 44.1 -> 38.4 us.
+    // With |X| and angle on the rectangular default window the two-frames-per-transform generation-2 kernel needs fewer
+    // instructions per frame (this kernel: 1 484, 63 % of the issue slots, ncu) and stays ahead - 40.4 vs 41.3 us, and 52.9 vs
+    // 62.4 us on 16 x 30 s clips - so that call keeps it.
+    if (rect && (mag || phase)) return ADV_ERR_UNSUPPORTED;
+    return rect ? launch_stft5_t<true>(p, g, wav, wav_stride, batch, X, mag, phase, s)
+                : launch_stft5_t<false>(p, g, wav, wav_stride, batch, X, mag, phase, s);
+}
 
 // ---- fused explain
 static Run5 plan_run_e5(const adv_plan* p, int batch) {

@@ -1875,6 +1875,10 @@ int launch_stft(const adv_plan* p, const float* wav, int64_t wav_stride, int bat
         const int rc3 = launch_stft3(p, wav, wav_stride, batch, X, mag, phase, flags, s);
         if (rc3 != ADV_ERR_UNSUPPORTED) return rc3;
     }
+    {   // n_fft 1024, even hop, reflect padding: one frame per warp, support-only slices (transform5_kernels.cu)
+        const int rc5 = launch_stft5(p, wav, wav_stride, batch, X, mag, phase, flags, s);
+        if (rc5 != ADV_ERR_UNSUPPORTED) return rc5;
+    }
 #ifdef ADV_AB
     static const char* var = ADV_AB_ENV("ADV_STFT");  // A/B switch: "v2" one tile per CTA, "p" persistent CTA tiles
     const int which = var == nullptr ? 0 : (var[0] == 'v' ? 2 : (var[0] == 'p' ? 1 : 0));
