@@ -159,6 +159,117 @@ __device__ __forceinline__ void conv_epilogue(const EpiArgs& a, int b, int l0, i
     }
 }
 
+// ---- epilogue with the residual row held in registers --------------------------------------------------------------
+// The layers that add a residual and write two outputs are HBM-bound (4.3 GB per launch at 256 clips), and the epilogue
+// above moves 3/4 of those bytes with 64 bytes per thread in flight and one exposed memory latency per 32 columns: 39 %
+// of the DRAM throughput, 14 % tensor activity on the 128-channel convs (profiles/r02zb_vocoder_launches_b256.csv).  Here a
+// thread's WHOLE residual row (BN / 8 int4) is requested one tile ahead - while the previous tile is converted and stored -
+// so 128 threads keep 16 - 64 KB in flight per CTA and no load is waited for.  One CTA per SM: the registers are there.
+// NH = 1: the warp owns all BN columns of its 32 rows; NH = 2: two warps share a TMEM lane quarter, `half` selects the
+// BN / 2 columns of this one.
+template <int BN, int NH = 1>
+__device__ __forceinline__ void epi_load_resid(const EpiArgs& a, int b, int l0, int tn, int quad, int lane, bool live,
+                                               int4 (&r)[BN / 8 / NH], int half = 0) {
+    const int l = l0 + quad * 32 + lane;
+    const bool ok = live && a.resid != nullptr && l < a.L;
+    const int4* p = reinterpret_cast<const int4*>(a.resid + ((size_t)b * a.L + (ok ? l : 0)) * a.N + (size_t)tn * BN +
+                                                  half * (BN / NH));
+#pragma unroll
+    for (int j = 0; j < BN / 8 / NH; ++j) r[j] = ok ? __ldg(p + j) : make_int4(0, 0, 0, 0);
+}
+// Coalesced form: ncu on the residual convs (gpurun_out/r02zd) shows what bounds them - every 16-byte store of the
+// thread-per-row epilogue lands in a different 128-byte line (31.6 sectors per request), the LSU data pipe is 61 % busy and
+// L1 is the busiest unit of the kernel (66 - 72 %) while DRAM sits at 39 %.  Here a warp stages 32 output columns of its 32
+// rows in a private 2 KB shared-memory tile (16-byte chunks XOR-swizzled with the row) and writes it out with 4 lanes per
+// row: a store instruction covers 8 rows x 64 contiguous bytes = 16 full sectors instead of 32 half-used ones in 32 lines.
+// `stg` = this warp's tile.
+constexpr int kEpiStageBytes = 2048;
+template <int BN, int NH = 1>
+__device__ __forceinline__ void conv_epilogue_pre(const EpiArgs& a, int b, int l0, int tn, uint32_t tmem_acc, int quad,
+                                                  int lane, uint64_t* tfull_bar, uint32_t parity,
+                                                  const int4 (&res)[BN / 8 / NH], unsigned char* stg, int half = 0) {
+    constexpr int W = 32;                         // columns staged per pass (one tcgen05.ld.x32)
+    constexpr int CH = W / 8;                     // 16-byte chunks per staged row
+    constexpr int RPI = 32 / CH;                  // rows written per store instruction
+    const int lrow = l0 + quad * 32;              // first row of this warp
+    const bool has_res = a.resid != nullptr;
+    bar_wait(tfull_bar, parity);
+    fence_after_sync();
+    const uint32_t trow = tmem_acc + ((uint32_t)(quad * 32) << 16);
+    const int srow = lane / CH, sch = lane % CH;  // this lane's (row offset, chunk) in the write-out
+    const int cbase = half * (BN / NH);           // first column of this warp
+#pragma unroll
+    for (int pp = 0; pp < BN / NH; pp += W) {
+        const int p0 = cbase + pp;
+        int4 act[CH];
+#pragma unroll
+        for (int h = 0; h < W / 32; ++h) {
+            const int c0 = p0 + 32 * h;
+            float v[32];
+            tmem_ld32(trow + c0, v);
+            const int n = tn * BN + c0;
+            if (a.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n) + j);
+                    v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+                }
+            }
+            if (has_res) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&res[(pp + 32 * h) / 8 + q]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __bfloat1622float2(rp[j]);
+                        v[8 * q + 2 * j] += f.x;
+                        v[8 * q + 2 * j + 1] += f.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= a.out_scale;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int4 o, oa;
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+                __nv_bfloat162* oq = reinterpret_cast<__nv_bfloat162*>(&oa);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float x0 = v[8 * q + 2 * j], x1 = v[8 * q + 2 * j + 1];
+                    op[j] = __floats2bfloat162_rn(x0, x1);
+                    oq[j] = __floats2bfloat162_rn(x0 > 0.f ? x0 : x0 * a.act_slope, x1 > 0.f ? x1 : x1 * a.act_slope);
+                }
+                const int ch = 4 * h + q;
+                act[ch] = oa;
+                if (a.out_raw != nullptr) *reinterpret_cast<int4*>(stg + lane * (CH * 16) + ((ch ^ (lane & (CH - 1))) << 4)) = o;
+            }
+        }
+        // write-out: raw tile, then (through the same buffer) the activated tile
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            __nv_bfloat16* dst = pass == 0 ? a.out_raw : a.out_act;
+            if (dst == nullptr) continue;   // (uniform)
+            if (pass == 1) {
+                __syncwarp();   // the raw tile has been read out
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch)
+                    *reinterpret_cast<int4*>(stg + lane * (CH * 16) + ((ch ^ (lane & (CH - 1))) << 4)) = act[ch];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 32 / RPI; ++i) {
+                const int r = i * RPI + srow;
+                const int l = lrow + r;
+                const int4 o = *reinterpret_cast<const int4*>(stg + r * (CH * 16) + ((sch ^ (r & (CH - 1))) << 4));
+                if (l < a.L)
+                    *reinterpret_cast<int4*>(dst + ((size_t)b * a.L + l) * a.N + (size_t)tn * BN + p0 + sch * 8) = o;
+            }
+        }
+        __syncwarp();   // the tile is free for the next pass
+    }
+}
+
 template <int BN, int BK, int STAGES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv1d_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, ConvTmaArgs a) {
@@ -276,7 +387,7 @@ struct SlabArgs {
 // breaks the result), for both the 128-byte and the 64-byte modes and for odd row shifts.
 
 template <int C, int STAGES>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)   // two CTAs per SM where shared memory allows: <= 168 registers
 conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, SlabArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -291,6 +402,9 @@ conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     uint64_t* wbar = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
     constexpr uint32_t kCols = 2 * C;
+    // per-warp output staging tiles of the epilogue warps (conv_epilogue_pre)
+    unsigned char* stg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~uintptr_t(127)) +
+                         ((threadIdx.x >> 5) & 3) * kEpiStageBytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -351,13 +465,35 @@ conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     } else {
         const int quad = warp & 3;
         uint32_t it = 0;
-        for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int b = (int)(tile / a.tiles_l), l0 = (int)(tile % a.tiles_l) * 128;
-            const uint32_t ab = it & 1, aph = (it >> 1) & 1;
-            conv_epilogue<C>(a.e, b, l0, 0, tmem_base + ab * C, quad, lane, &tfull[ab], aph);
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) bar_arrive(&tempty[ab]);
+        // Measured per layer at 256 clips (profiles/r02z*_vocoder_launches_b256.csv): the prefetching + staged epilogue wins
+        // where the layer adds a residual and writes two outputs at 64 channels (1 123 -> 900 us, 47 -> 59 % of the DRAM
+        // throughput) and loses everywhere else (more instructions in an epilogue that was not waiting on L1).
+        if (C == 64 && a.e.resid != nullptr) {
+            int4 res[C / 8];   // this thread's residual row of the tile about to be finished (requested a tile ahead)
+            if ((long)blockIdx.x < total_tiles)
+                epi_load_resid<C>(a.e, (int)(blockIdx.x / a.tiles_l), (int)(blockIdx.x % a.tiles_l) * 128, 0, quad, lane, true, res);
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int b = (int)(tile / a.tiles_l), l0 = (int)(tile % a.tiles_l) * 128;
+                const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+                int4 cur[C / 8];
+#pragma unroll
+                for (int j = 0; j < C / 8; ++j) cur[j] = res[j];
+                const long nt = tile + gridDim.x;
+                epi_load_resid<C>(a.e, (int)(nt / a.tiles_l), (int)(nt % a.tiles_l) * 128, 0, quad, lane, nt < total_tiles, res);
+                conv_epilogue_pre<C>(a.e, b, l0, 0, tmem_base + ab * C, quad, lane, &tfull[ab], aph, cur, stg);
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) bar_arrive(&tempty[ab]);
+            }
+        } else {
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int b = (int)(tile / a.tiles_l), l0 = (int)(tile % a.tiles_l) * 128;
+                const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+                conv_epilogue<C>(a.e, b, l0, 0, tmem_base + ab * C, quad, lane, &tfull[ab], aph);
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) bar_arrive(&tempty[ab]);
+            }
         }
     }
     fence_before_sync();
@@ -482,6 +618,10 @@ conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     } else {
         const int quad = warp & 3;
         uint32_t tcount = 0;
+        // (Measured and dropped for this kernel, profiles/r02z*_vocoder_launches_b256.csv: residual rows held in registers a
+        // tile ahead - no change; the staged, coalesced write-out - 676 -> 820 us on the layers without a residual; eight
+        // epilogue warps splitting the columns - 676 -> 931 us.  ncu shows L1 as the busiest unit (66 - 72 %) with 31.6 sectors
+        // per store request, but every variant that traded those for more epilogue instructions lost.)
         for (long item = blockIdx.x; item < items; item += gridDim.x, ++tcount) {
             const int tn = (int)(item % a.tiles_n);
             const long pr = item / a.tiles_n;
@@ -577,7 +717,7 @@ template <int C>
 static int launch_conv_slab(const CUtensorMap& ma, const CUtensorMap& mw, const SlabArgs& a, cudaStream_t s) {
     constexpr int STAGES = 3;
     const size_t slab_stride = ((size_t)a.rows * C * 2 + 1023) & ~size_t(1023);
-    const size_t smem = (size_t)a.taps * C * C * 2 + STAGES * slab_stride + 256 + 1024;
+    const size_t smem = (size_t)a.taps * C * C * 2 + STAGES * slab_stride + 256 + 1024 + 4 * kEpiStageBytes + 256;
     int rc = set_smem_attr2(conv1d_slab_kernel<C, STAGES>, smem);
     if (rc != ADV_OK) return rc;
     const int per_sm = resident_ctas(conv1d_slab_kernel<C, STAGES>, smem, 2 * C);
