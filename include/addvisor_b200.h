@@ -197,6 +197,11 @@ int adv_mel_fused(const adv_plan* plan, const float* wav, int64_t wav_stride, in
 int adv_conv1d_bf16(const void* in, const void* w, const float* bias, const void* resid, void* out, void* out_act,
                     int batch, int L, int Cin, int taps, int dil, int N, int Kpad, int pad_reflect, float pre_slope,
                     float act_slope, float out_scale, void* stream);
+/* Epilogue of the wide conv kernel (C_in, N multiples of 128): 1 (default) = output blocks staged in shared memory and
+ * written by the TMA engine (cp.async.bulk.tensor), 0 = per-thread 16-byte stores.  Process-wide; returns the previous
+ * setting (A/B measurements: scripts/bench_vocoder.py --epilogue). */
+int adv_set_conv_epilogue(int tma);
+
 /* Same contraction on the production pipeline: operands fetched by TMA (3-D tensor map over [B][L][Cin], the tap
  * is a row coordinate, zero padding = TMA out-of-bounds fill), warp-specialised producer / MMA / epilogue roles,
  * persistent CTAs, double-buffered TMEM accumulators.  Zero padding only; Cin = 32 or a multiple of 64;

@@ -11,11 +11,12 @@ ap.add_argument("--frames", type=int, default=251)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--pipeline", default="tma")
 ap.add_argument("--fuse", default="auto")
+ap.add_argument("--epilogue", default="tma", help="auto / tma / direct: epilogue of the slab conv kernels (HifiganGenerator)")
 args = ap.parse_args()
 pkg = importlib.import_module("xai-audio-deepfakes_b200")
 pkg._lib.build()
 H = pkg.hifigan
-gen = H.HifiganGenerator(H.init_weights(seed=0, std=0.01), pipeline=args.pipeline, fuse=args.fuse)
+gen = H.HifiganGenerator(H.init_weights(seed=0, std=0.01), pipeline=args.pipeline, fuse=args.fuse, epilogue=args.epilogue)
 g = torch.Generator(device="cuda").manual_seed(1234)
 mel = -4 + 2 * torch.randn(args.batch, 80, args.frames, generator=g, device="cuda")
 gen.decode_batch(mel)
@@ -32,6 +33,6 @@ peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_P
     os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"bf16_tflops_sustained": 1384.0}
 peak = peaks["bf16_tflops_sustained"]
 print(json.dumps({"metric": "vocoded clips/s", "value": args.batch / t, "unit": "clips/s", "batch": args.batch,
-                  "frames": args.frames, "pipeline": args.pipeline, "fuse": args.fuse, "launches": gen.launches // (args.iters + 1), "s_per_batch": t, "tflops": flops / t / 1e12,
+                  "frames": args.frames, "pipeline": args.pipeline, "fuse": args.fuse, "epilogue": args.epilogue, "epilogue_choices": {"tma": sum(gen._epi.values()), "direct": len(gen._epi) - sum(gen._epi.values())}, "launches": gen.launches // (args.iters + 1), "s_per_batch": t, "tflops": flops / t / 1e12,
                   "roofline": {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s",
                                "frac": flops / t / 1e12 / peak}, "out_shape": list(wav.shape)}))

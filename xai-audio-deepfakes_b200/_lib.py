@@ -73,6 +73,7 @@ _SIGS = {
     # name: (restype, argtypes)
     "adv_version": (C.c_int, []),
     "adv_set_pdl": (C.c_int, [C.c_int]),
+    "adv_set_conv_epilogue": (C.c_int, [C.c_int]),
     "adv_strerror": (C.c_char_p, [C.c_int]),
     "adv_last_cuda_error": (C.c_char_p, []),
     "adv_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,

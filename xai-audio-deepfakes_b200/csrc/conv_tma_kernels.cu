@@ -159,6 +159,104 @@ __device__ __forceinline__ void conv_epilogue(const EpiArgs& a, int b, int l0, i
     }
 }
 
+// ---- epilogue with TMA stores -------------------------------------------------------------------------------------
+// What ncu says bounds the thread-per-row epilogue (gpurun_out/r02zd, profiles/r02zd_*): L1 is the busiest unit of the
+// kernel (66 - 72 %), every 16-byte store lands in a different 128-byte line (31.6 sectors per request), DRAM sits at
+// 39 %.  Variants that re-read a staged tile with the LSU lost on instruction count.  Here the warp writes its 32 x 32
+// output block (raw and / or activated) into a 2 KB SWIZZLE_64B tile and ONE lane hands it to the TMA engine
+// (cp.async.bulk.tensor shared -> global, 3-D map [C][L][B], box 32 x 32 x 1): four STS.128 per thread replace four
+// uncoalesced STG.128, rows past the end of the clip are clipped by the tensor map, and the store runs asynchronously under
+// the next 32 columns' TMEM load and arithmetic.  `stg`: 4 KB per warp (raw tile, activated tile).
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_tma(const EpiArgs& a, const CUtensorMap* map_raw, const CUtensorMap* map_act,
+                                                  int b, int l0, int tn, uint32_t tmem_acc, int quad, int lane,
+                                                  uint64_t* tfull_bar, uint32_t parity, unsigned char* stg) {
+    const int lrow = l0 + quad * 32;
+    const int l = lrow + lane;
+    const bool row_ok = l < a.L;
+    const size_t rowoff = ((size_t)b * a.L + l) * a.N + (size_t)tn * BN;
+    const bool has_res = a.resid != nullptr && row_ok;
+    int4 rnext[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        rnext[j] = has_res ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff) + j) : make_int4(0, 0, 0, 0);
+    bar_wait(tfull_bar, parity);
+    fence_after_sync();
+    const uint32_t trow = tmem_acc + ((uint32_t)(quad * 32) << 16);
+    unsigned char* tile_raw = stg + lane * 64;
+    unsigned char* tile_act = stg + 2048 + lane * 64;
+    const int sw = (lane >> 1) & 3;   // SWIZZLE_64B: chunk ^= bits [7, 9) of the byte address = (row >> 1) & 3
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        int4 rcur[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+        if (c0 + 32 < BN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                rnext[j] = has_res ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff + c0 + 32) + j)
+                                   : make_int4(0, 0, 0, 0);
+        }
+        float v[32];
+        tmem_ld32(trow + c0, v);
+        const int n = tn * BN + c0;
+        if (a.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n) + j);
+                v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+            }
+        }
+        if (has_res) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rcur[q]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(rp[j]);
+                    v[8 * q + 2 * j] += f.x;
+                    v[8 * q + 2 * j + 1] += f.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= a.out_scale;
+        // the previous block's stores have read the tiles
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int4 o, oa;
+            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+            __nv_bfloat162* oq = reinterpret_cast<__nv_bfloat162*>(&oa);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float x0 = v[8 * q + 2 * j], x1 = v[8 * q + 2 * j + 1];
+                op[j] = __floats2bfloat162_rn(x0, x1);
+                oq[j] = __floats2bfloat162_rn(x0 > 0.f ? x0 : x0 * a.act_slope, x1 > 0.f ? x1 : x1 * a.act_slope);
+            }
+            if (a.out_raw != nullptr) *reinterpret_cast<int4*>(tile_raw + ((q ^ sw) << 4)) = o;
+            if (a.out_act != nullptr) *reinterpret_cast<int4*>(tile_act + ((q ^ sw) << 4)) = oa;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            if (a.out_raw != nullptr) tma_store_3d(map_raw, stg, n, lrow, b);
+            if (a.out_act != nullptr) tma_store_3d(map_act, stg + 2048, n, lrow, b);
+            bulk_commit();
+        }
+    }
+}
+
 // ---- epilogue with the residual row held in registers --------------------------------------------------------------
 // The layers that add a residual and write two outputs are HBM-bound (4.3 GB per launch at 256 clips), and the epilogue
 // above moves 3/4 of those bytes with 64 bytes per thread in flight and one exposed memory latency per 32 columns: 39 %
@@ -380,6 +478,7 @@ struct SlabArgs {
     EpiArgs e;
     int B, taps, dil, halo, rows;  // rows = 128 + 2*halo (TMA box height)
     int tiles_l;
+    int epi_tma;   // outputs through TMA stores (conv_epilogue_tma)
 };
 
 // Row-shifted start addresses need nothing special in the descriptor: measured on B200, the swizzle XOR is
@@ -388,7 +487,8 @@ struct SlabArgs {
 
 template <int C, int STAGES>
 __global__ void __launch_bounds__(kConvThreads, 2)   // two CTAs per SM where shared memory allows: <= 168 registers
-conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, SlabArgs a) {
+conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                   const __grid_constant__ CUtensorMap map_or, const __grid_constant__ CUtensorMap map_oa, SlabArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kRow = C * 2, kWTile = C * kRow;
@@ -402,9 +502,9 @@ conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     uint64_t* wbar = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
     constexpr uint32_t kCols = 2 * C;
-    // per-warp output staging tiles of the epilogue warps (conv_epilogue_pre)
-    unsigned char* stg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~uintptr_t(127)) +
-                         ((threadIdx.x >> 5) & 3) * kEpiStageBytes;
+    // per-warp 4 KB output tiles of the epilogue warps (conv_epilogue_tma: raw + activated tile; conv_epilogue_pre: the first 2 KB)
+    unsigned char* stg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023)) +
+                         ((threadIdx.x >> 5) & 3) * 4096;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -468,7 +568,17 @@ conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // Measured per layer at 256 clips (profiles/r02z*_vocoder_launches_b256.csv): the prefetching + staged epilogue wins
         // where the layer adds a residual and writes two outputs at 64 channels (1 123 -> 900 us, 47 -> 59 % of the DRAM
         // throughput) and loses everywhere else (more instructions in an epilogue that was not waiting on L1).
-        if (C == 64 && a.e.resid != nullptr) {
+        if (a.epi_tma) {
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int b = (int)(tile / a.tiles_l), l0 = (int)(tile % a.tiles_l) * 128;
+                const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+                conv_epilogue_tma<C>(a.e, &map_or, &map_oa, b, l0, 0, tmem_base + ab * C, quad, lane, &tfull[ab], aph, stg);
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) bar_arrive(&tempty[ab]);
+            }
+            if (lane == 0) bulk_wait0();
+        } else if (C == 64 && a.e.resid != nullptr) {
             int4 res[C / 8];   // this thread's residual row of the tile about to be finished (requested a tile ahead)
             if ((long)blockIdx.x < total_tiles)
                 epi_load_resid<C>(a.e, (int)(blockIdx.x / a.tiles_l), (int)(blockIdx.x % a.tiles_l) * 128, 0, quad, lane, true, res);
@@ -515,11 +625,13 @@ struct Slab2Args {
     int B, Cin, taps, dil, halo;
     int rb;                       // TMA box height: the slab (256 + 2*halo rows) arrives as two boxes
     int pairs_l, tiles_n, groups; // tile pairs per clip, 128-wide N tiles, channel groups of 128
+    int epi_tma;                  // outputs through TMA stores (conv_epilogue_tma) instead of per-thread stores
 };
 
 template <int WSTAGES>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, Slab2Args a) {
+conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_or, const __grid_constant__ CUtensorMap map_oa, Slab2Args a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kRow = 128, kWTile = 128 * kRow;           // 64 channels bf16 per row; 128 x 64 weight block
@@ -533,6 +645,9 @@ conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t* tfull = wempty + WSTAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    // per-warp output tiles of the TMA-store epilogue (1 KB aligned: the 64-byte swizzle follows the address bits)
+    unsigned char* stg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023)) +
+                         ((threadIdx.x >> 5) & 3) * 4096;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -627,12 +742,19 @@ conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const long pr = item / a.tiles_n;
             const int b = (int)(pr / a.pairs_l), l0 = (int)(pr % a.pairs_l) * 256;
             const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
-            conv_epilogue<128>(a.e, b, l0, tn, tmem_base + ab * 256, quad, lane, &tfull[ab], aph);
-            conv_epilogue<128>(a.e, b, l0 + 128, tn, tmem_base + ab * 256 + 128, quad, lane, &tfull[ab], aph);
+            if (a.epi_tma) {
+                conv_epilogue_tma<128>(a.e, &map_or, &map_oa, b, l0, tn, tmem_base + ab * 256, quad, lane, &tfull[ab], aph, stg);
+                conv_epilogue_tma<128>(a.e, &map_or, &map_oa, b, l0 + 128, tn, tmem_base + ab * 256 + 128, quad, lane, &tfull[ab],
+                                       aph, stg);
+            } else {
+                conv_epilogue<128>(a.e, b, l0, tn, tmem_base + ab * 256, quad, lane, &tfull[ab], aph);
+                conv_epilogue<128>(a.e, b, l0 + 128, tn, tmem_base + ab * 256 + 128, quad, lane, &tfull[ab], aph);
+            }
             fence_before_sync();
             __syncwarp();
             if (lane == 0) bar_arrive(&tempty[ab]);
         }
+        if (a.epi_tma && lane == 0) bulk_wait0();   // the tiles must outlive the last stores' reads; the data is then in flight to L2
     }
     fence_before_sync();
     __syncthreads();
@@ -645,6 +767,8 @@ conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int g_conv_epi_tma = 1;   // adv_set_conv_epilogue(): 1 = TMA-store epilogue where it exists (default), 0 = per-thread stores
 
 static EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = nullptr;
@@ -714,17 +838,18 @@ static int launch_conv_tma(const CUtensorMap& ma, const CUtensorMap& mw, ConvTma
 }
 
 template <int C>
-static int launch_conv_slab(const CUtensorMap& ma, const CUtensorMap& mw, const SlabArgs& a, cudaStream_t s) {
+static int launch_conv_slab(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& m_or, const CUtensorMap& m_oa,
+                            const SlabArgs& a, cudaStream_t s) {
     constexpr int STAGES = 3;
     const size_t slab_stride = ((size_t)a.rows * C * 2 + 1023) & ~size_t(1023);
-    const size_t smem = (size_t)a.taps * C * C * 2 + STAGES * slab_stride + 256 + 1024 + 4 * kEpiStageBytes + 256;
+    const size_t smem = (size_t)a.taps * C * C * 2 + STAGES * slab_stride + 256 + 1024 + 4 * 4096 + 1024;
     int rc = set_smem_attr2(conv1d_slab_kernel<C, STAGES>, smem);
     if (rc != ADV_OK) return rc;
     const int per_sm = resident_ctas(conv1d_slab_kernel<C, STAGES>, smem, 2 * C);
     const long tiles = (long)a.B * a.tiles_l;
     long grid = (long)num_sms() * per_sm;
     if (grid > tiles) grid = tiles;
-    conv1d_slab_kernel<C, STAGES><<<(unsigned)grid, kConvThreads, smem, s>>>(ma, mw, a);
+    conv1d_slab_kernel<C, STAGES><<<(unsigned)grid, kConvThreads, smem, s>>>(ma, mw, m_or, m_oa, a);
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }
@@ -732,6 +857,12 @@ static int launch_conv_slab(const CUtensorMap& ma, const CUtensorMap& mw, const 
 }  // namespace adv
 
 using namespace adv;
+
+extern "C" int adv_set_conv_epilogue(int tma) {
+    const int prev = adv::g_conv_epi_tma;
+    adv::g_conv_epi_tma = tma ? 1 : 0;
+    return prev;
+}
 
 extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* bias, const void* resid, void* out_raw,
                                    void* out_act, int batch, int L, int Cin, int taps, int dil, int N, float act_slope,
@@ -792,8 +923,21 @@ extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* b
                            act_slope, out_scale};
             sa.B = batch; sa.taps = taps; sa.dil = dil; sa.halo = halo; sa.rows = rows;
             sa.tiles_l = (L + 127) / 128;
-            return Cin == 64 ? launch_conv_slab<64>(ms, mws, sa, (cudaStream_t)stream)
-                             : launch_conv_slab<32>(ms, mws, sa, (cudaStream_t)stream);
+            CUtensorMap m_or = ms, m_oa = ms;   // output maps of the TMA-store epilogue: [N][L][B], box 32 x 32, 64-byte swizzle
+            sa.epi_tma = g_conv_epi_tma != 0;
+            for (int k = 0; k < 2 && sa.epi_tma; ++k) {
+                void* dst = k == 0 ? out_raw : out_act;
+                if (!dst) continue;
+                cuuint64_t od[3] = {(cuuint64_t)N, (cuuint64_t)L, (cuuint64_t)batch};
+                cuuint64_t ost[2] = {(cuuint64_t)N * 2, (cuuint64_t)L * N * 2};
+                cuuint32_t ob[3] = {32, 32, 1};
+                cuuint32_t oe[3] = {1, 1, 1};
+                if (enc(k == 0 ? &m_or : &m_oa, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dst, od, ost, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    sa.epi_tma = 0;
+            }
+            return Cin == 64 ? launch_conv_slab<64>(ms, mws, m_or, m_oa, sa, (cudaStream_t)stream)
+                             : launch_conv_slab<32>(ms, mws, m_or, m_oa, sa, (cudaStream_t)stream);
         }
     }
     static const bool no_slab2 = ADV_AB_ENV("ADV_NO_SLAB2") != nullptr;
@@ -824,13 +968,28 @@ extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* b
             sa.pairs_l = (L + 255) / 256; sa.tiles_n = N / 128; sa.groups = Cin / 128;
             constexpr int WS = 3;
             const size_t part = ((size_t)2 * rb * 128 + 1023) & ~size_t(1023);
-            const size_t smem = 4 * part + (size_t)WS * 128 * 128 + 256 + 1024;
+            size_t smem = 4 * part + (size_t)WS * 128 * 128 + 256 + 1024;
+            // output maps of the TMA-store epilogue: [N][L][B], box 32 channels x 32 rows, 64-byte swizzle
+            CUtensorMap m_or = ms, m_oa = ms;
+            sa.epi_tma = g_conv_epi_tma != 0 && smem + 4 * 4096 + 1024 <= 227 * 1024;
+            for (int k = 0; k < 2 && sa.epi_tma; ++k) {
+                void* dst = k == 0 ? out_raw : out_act;
+                if (!dst) continue;
+                cuuint64_t od[3] = {(cuuint64_t)N, (cuuint64_t)L, (cuuint64_t)batch};
+                cuuint64_t ost[2] = {(cuuint64_t)N * 2, (cuuint64_t)L * N * 2};
+                cuuint32_t ob[3] = {32, 32, 1};
+                cuuint32_t oe[3] = {1, 1, 1};
+                if (enc(k == 0 ? &m_or : &m_oa, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dst, od, ost, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    sa.epi_tma = 0;
+            }
+            if (sa.epi_tma) smem += 4 * 4096 + 1024;
             int rc = set_smem_attr2(conv1d_slab2_kernel<WS>, smem);
             if (rc == ADV_OK) {
                 const long items = (long)batch * sa.pairs_l * sa.tiles_n;
                 long grid = num_sms();
                 if (grid > items) grid = items;
-                conv1d_slab2_kernel<WS><<<(unsigned)grid, kConvThreads, smem, (cudaStream_t)stream>>>(ms, mws, sa);
+                conv1d_slab2_kernel<WS><<<(unsigned)grid, kConvThreads, smem, (cudaStream_t)stream>>>(ms, mws, m_or, m_oa, sa);
                 ADV_CUDA_CHECK(cudaGetLastError());
                 return ADV_OK;
             }

@@ -154,8 +154,17 @@ class HifiganGenerator:
     (``adv_avg_relayout_bf16``) switches to the zero halo the next transposed conv needs.  ``pipeline="gather"``:
     first-generation kernel (operands gathered with ordinary loads, activation and reflection on load)."""
 
-    def __init__(self, weights=None, cfg=HifiganConfig, device=None, seed=0, pipeline=None, fuse="auto"):
+    def __init__(self, weights=None, cfg=HifiganConfig, device=None, seed=0, pipeline=None, fuse="auto", epilogue="tma"):
         self.cfg = cfg
+        # epilogue of the slab conv kernels: "tma" = output blocks staged in shared memory and written by the TMA engine,
+        # "direct" = per-thread 16-byte stores, "auto" = each distinct layer shape is timed both ways on first use (outside
+        # graph capture) and keeps the faster one.  Measured at 256 clips: the TMA form wins 17 - 37 % on the layers that
+        # wait on L1 / HBM (128 channels and below, residual + two outputs) and loses 3 - 9 % on the tensor-bound 256-channel
+        # and 11-tap layers, whose four epilogue warps have no slack (profiles/r02zh_vocoder_launches_b256.csv); whole
+        # generator: "direct" 3 726, "auto" 3 957 (a layer timed alone, L2-warm, is not the layer in sequence), "tma" 4 046
+        # clips/s - the default.
+        self.epilogue = epilogue
+        self._epi = {}
         # fused residual units on the narrow stages: "auto" = where measured faster, "always" = wherever the
         # kernel supports the shape, "never" = every conv is its own launch
         self.fuse = {True: "auto", False: "never"}.get(fuse, fuse)
@@ -201,10 +210,35 @@ class HifiganGenerator:
     def _conv_tma(self, x, layer, B, L, resid=None, want_raw=True, act_slope=None):
         out = self._buf(B, L, layer.cout) if want_raw else None
         act = self._buf(B, L, layer.cout) if act_slope is not None else None
-        check(lib().adv_conv1d_bf16_tma(ptr(x), ptr(layer.w_tma), ptr(layer.bias), ptr(resid), ptr(out), ptr(act), B, L,
-                                        layer.cin, layer.taps, layer.dil, layer.cout,
-                                        float(act_slope if act_slope is not None else 1.0), 1.0, stream_ptr()),
-              "adv_conv1d_bf16_tma")
+
+        def launch():
+            check(lib().adv_conv1d_bf16_tma(ptr(x), ptr(layer.w_tma), ptr(layer.bias), ptr(resid), ptr(out), ptr(act), B, L,
+                                            layer.cin, layer.taps, layer.dil, layer.cout,
+                                            float(act_slope if act_slope is not None else 1.0), 1.0, stream_ptr()),
+                  "adv_conv1d_bf16_tma")
+
+        if self.epilogue == "auto":
+            key = (layer.cin, layer.cout, layer.taps, layer.dil, resid is not None, want_raw, act_slope is not None, B, L)
+            mode = self._epi.get(key)
+            if mode is None and not torch.cuda.is_current_stream_capturing():
+                best = None
+                for m in (0, 1):            # time the layer both ways (same inputs, same outputs)
+                    lib().adv_set_conv_epilogue(m)
+                    launch()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(3):
+                        launch()
+                    b.record()
+                    b.synchronize()
+                    t = a.elapsed_time(b)
+                    if best is None or t < best[0]:
+                        best = (t, m)
+                mode = self._epi[key] = best[1]
+            lib().adv_set_conv_epilogue(1 if mode is None else mode)
+        elif self.epilogue in ("tma", "direct"):
+            lib().adv_set_conv_epilogue(int(self.epilogue == "tma"))
+        launch()
         self.launches += 1
         return out, act
 
