@@ -176,19 +176,39 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int BN>
-__device__ __forceinline__ void conv_epilogue_tma(const EpiArgs& a, const CUtensorMap* map_raw, const CUtensorMap* map_act,
-                                                  int b, int l0, int tn, uint32_t tmem_acc, int quad, int lane,
-                                                  uint64_t* tfull_bar, uint32_t parity, unsigned char* stg) {
+// Residual block through the TMA engine too (res_tma): the warp's 32 x 32 block of the residual tensor is requested one
+// block ahead into one of two 2 KB tiles (mbarrier per tile, `rcount` = blocks requested so far by this warp: tile
+// rcount & 1, parity (rcount >> 1) & 1) and read back with one conflict-free LDS.128 per 8 columns - the per-thread
+// LDG.128 form touches 11 sectors per request.  `stg`: 8 KB per warp = raw tile, activated tile, 2 residual tiles;
+// `rbar`: this warp's two mbarriers.
+struct EpiTma {
+    const CUtensorMap* map_raw;
+    const CUtensorMap* map_act;
+    const CUtensorMap* map_res;
+    int res_tma;
+};
+template <int BN, bool RES_TMA>
+__device__ __forceinline__ void conv_epilogue_tma(const EpiArgs& a, const EpiTma& m, int b, int l0, int tn, uint32_t tmem_acc,
+                                                  int quad, int lane, uint64_t* tfull_bar, uint32_t parity, unsigned char* stg,
+                                                  uint64_t* rbar, uint32_t& rcount) {
     const int lrow = l0 + quad * 32;
     const int l = lrow + lane;
     const bool row_ok = l < a.L;
     const size_t rowoff = ((size_t)b * a.L + l) * a.N + (size_t)tn * BN;
-    const bool has_res = a.resid != nullptr && row_ok;
+    const bool has_res = a.resid != nullptr;
+    constexpr bool res_tma = RES_TMA;                    // (the caller instantiates it only for layers with a residual)
+    const bool res_ldg = has_res && !RES_TMA && row_ok;
+    auto request_res = [&](uint32_t k, int c0) {   // block k of this warp: columns tn * BN + c0 .. + 31
+        if (lane == 0) {
+            bar_expect_tx(&rbar[k & 1], 2048);
+            tma_load_3d(stg + 4096 + (k & 1) * 2048, m.map_res, &rbar[k & 1], tn * BN + c0, lrow, b);
+        }
+    };
     int4 rnext[4];
+    if (res_tma) request_res(rcount, 0);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        rnext[j] = has_res ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff) + j) : make_int4(0, 0, 0, 0);
+        rnext[j] = res_ldg ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff) + j) : make_int4(0, 0, 0, 0);
     bar_wait(tfull_bar, parity);
     fence_after_sync();
     const uint32_t trow = tmem_acc + ((uint32_t)(quad * 32) << 16);
@@ -198,13 +218,17 @@ __device__ __forceinline__ void conv_epilogue_tma(const EpiArgs& a, const CUtens
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         int4 rcur[4];
+        if (res_tma) {
+            if (c0 + 32 < BN) request_res(rcount + 1, c0 + 32);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-        if (c0 + 32 < BN) {
+            for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+            if (c0 + 32 < BN) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                rnext[j] = has_res ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff + c0 + 32) + j)
-                                   : make_int4(0, 0, 0, 0);
+                for (int j = 0; j < 4; ++j)
+                    rnext[j] = res_ldg ? __ldg(reinterpret_cast<const int4*>(a.resid + rowoff + c0 + 32) + j)
+                                       : make_int4(0, 0, 0, 0);
+            }
         }
         float v[32];
         tmem_ld32(trow + c0, v);
@@ -215,6 +239,13 @@ __device__ __forceinline__ void conv_epilogue_tma(const EpiArgs& a, const CUtens
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n) + j);
                 v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
             }
+        }
+        if (res_tma) {
+            bar_wait(&rbar[rcount & 1], (rcount >> 1) & 1);
+            const unsigned char* rt = stg + 4096 + (rcount & 1) * 2048 + lane * 64;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rcur[q] = *reinterpret_cast<const int4*>(rt + ((q ^ sw) << 4));
+            ++rcount;
         }
         if (has_res) {
 #pragma unroll
@@ -232,7 +263,7 @@ __device__ __forceinline__ void conv_epilogue_tma(const EpiArgs& a, const CUtens
         for (int j = 0; j < 32; ++j) v[j] *= a.out_scale;
         // the previous block's stores have read the tiles
         if (lane == 0) bulk_wait_read0();
-        __syncwarp();
+        __syncwarp();   // (also: every lane has read its residual row before that tile is requested again)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             int4 o, oa;
@@ -250,8 +281,8 @@ __device__ __forceinline__ void conv_epilogue_tma(const EpiArgs& a, const CUtens
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-            if (a.out_raw != nullptr) tma_store_3d(map_raw, stg, n, lrow, b);
-            if (a.out_act != nullptr) tma_store_3d(map_act, stg + 2048, n, lrow, b);
+            if (a.out_raw != nullptr) tma_store_3d(m.map_raw, stg, n, lrow, b);
+            if (a.out_act != nullptr) tma_store_3d(m.map_act, stg + 2048, n, lrow, b);
             bulk_commit();
         }
     }
@@ -479,6 +510,7 @@ struct SlabArgs {
     int B, taps, dil, halo, rows;  // rows = 128 + 2*halo (TMA box height)
     int tiles_l;
     int epi_tma;   // outputs through TMA stores (conv_epilogue_tma)
+    int res_tma;   // ... and the residual block through TMA loads
 };
 
 // Row-shifted start addresses need nothing special in the descriptor: measured on B200, the swizzle XOR is
@@ -488,7 +520,8 @@ struct SlabArgs {
 template <int C, int STAGES>
 __global__ void __launch_bounds__(kConvThreads, 2)   // two CTAs per SM where shared memory allows: <= 168 registers
 conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                   const __grid_constant__ CUtensorMap map_or, const __grid_constant__ CUtensorMap map_oa, SlabArgs a) {
+                   const __grid_constant__ CUtensorMap map_or, const __grid_constant__ CUtensorMap map_oa,
+                   const __grid_constant__ CUtensorMap map_rs, SlabArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kRow = C * 2, kWTile = C * kRow;
@@ -502,9 +535,12 @@ conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     uint64_t* wbar = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
     constexpr uint32_t kCols = 2 * C;
-    // per-warp 4 KB output tiles of the epilogue warps (conv_epilogue_tma: raw + activated tile; conv_epilogue_pre: the first 2 KB)
-    unsigned char* stg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023)) +
-                         ((threadIdx.x >> 5) & 3) * 4096;
+    // per-warp 8 KB of epilogue tiles (conv_epilogue_tma: raw, activated, 2 residual tiles; conv_epilogue_pre: the first 2 KB)
+    // and the residual tiles' mbarriers
+    uint64_t* rbars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+    unsigned char* stg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(rbars + 8) + 1023) & ~uintptr_t(1023)) +
+                         ((threadIdx.x >> 5) & 3) * 8192;
+    uint64_t* rbar = rbars + 2 * ((threadIdx.x >> 5) & 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -517,6 +553,7 @@ conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             bar_init(&tempty[i], 4);
         }
         bar_init(wbar, 1);
+        for (int i = 0; i < 8; ++i) bar_init(&rbars[i], 1);
         bar_init_fence();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kCols);
@@ -569,10 +606,15 @@ conv1d_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // where the layer adds a residual and writes two outputs at 64 channels (1 123 -> 900 us, 47 -> 59 % of the DRAM
         // throughput) and loses everywhere else (more instructions in an epilogue that was not waiting on L1).
         if (a.epi_tma) {
+            const EpiTma em{&map_or, &map_oa, &map_rs, a.res_tma};
+            uint32_t rcount = 0;
             for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int b = (int)(tile / a.tiles_l), l0 = (int)(tile % a.tiles_l) * 128;
                 const uint32_t ab = it & 1, aph = (it >> 1) & 1;
-                conv_epilogue_tma<C>(a.e, &map_or, &map_oa, b, l0, 0, tmem_base + ab * C, quad, lane, &tfull[ab], aph, stg);
+                if (a.res_tma)
+                    conv_epilogue_tma<C, true>(a.e, em, b, l0, 0, tmem_base + ab * C, quad, lane, &tfull[ab], aph, stg, rbar, rcount);
+                else
+                    conv_epilogue_tma<C, false>(a.e, em, b, l0, 0, tmem_base + ab * C, quad, lane, &tfull[ab], aph, stg, rbar, rcount);
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) bar_arrive(&tempty[ab]);
@@ -626,12 +668,14 @@ struct Slab2Args {
     int rb;                       // TMA box height: the slab (256 + 2*halo rows) arrives as two boxes
     int pairs_l, tiles_n, groups; // tile pairs per clip, 128-wide N tiles, channel groups of 128
     int epi_tma;                  // outputs through TMA stores (conv_epilogue_tma) instead of per-thread stores
+    int res_tma;                  // ... and the residual block through TMA loads (8 KB of tiles per epilogue warp)
 };
 
 template <int WSTAGES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                    const __grid_constant__ CUtensorMap map_or, const __grid_constant__ CUtensorMap map_oa, Slab2Args a) {
+                    const __grid_constant__ CUtensorMap map_or, const __grid_constant__ CUtensorMap map_oa,
+                    const __grid_constant__ CUtensorMap map_rs, Slab2Args a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kRow = 128, kWTile = 128 * kRow;           // 64 channels bf16 per row; 128 x 64 weight block
@@ -645,9 +689,12 @@ conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t* tfull = wempty + WSTAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    // per-warp output tiles of the TMA-store epilogue (1 KB aligned: the 64-byte swizzle follows the address bits)
-    unsigned char* stg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023)) +
-                         ((threadIdx.x >> 5) & 3) * 4096;
+    // per-warp tiles of the TMA epilogue (1 KB aligned: the 64-byte swizzle follows the address bits): raw, activated and -
+    // with res_tma - two residual tiles; the residual tiles' mbarriers
+    uint64_t* rbars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+    unsigned char* stg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(rbars + 8) + 1023) & ~uintptr_t(1023)) +
+                         ((threadIdx.x >> 5) & 3) * (a.res_tma ? 8192 : 4096);
+    uint64_t* rbar = rbars + 2 * ((threadIdx.x >> 5) & 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -661,6 +708,7 @@ conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             bar_init(&wfull[s], 1);
             bar_init(&wempty[s], 1);
         }
+        for (int i = 0; i < 8; ++i) bar_init(&rbars[i], 1);
         bar_init_fence();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -732,7 +780,7 @@ conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     } else {
         const int quad = warp & 3;
-        uint32_t tcount = 0;
+        uint32_t tcount = 0, rcount = 0;
         // (Measured and dropped for this kernel, profiles/r02z*_vocoder_launches_b256.csv: residual rows held in registers a
         // tile ahead - no change; the staged, coalesced write-out - 676 -> 820 us on the layers without a residual; eight
         // epilogue warps splitting the columns - 676 -> 931 us.  ncu shows L1 as the busiest unit (66 - 72 %) with 31.6 sectors
@@ -743,9 +791,16 @@ conv1d_slab2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int b = (int)(pr / a.pairs_l), l0 = (int)(pr % a.pairs_l) * 256;
             const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
             if (a.epi_tma) {
-                conv_epilogue_tma<128>(a.e, &map_or, &map_oa, b, l0, tn, tmem_base + ab * 256, quad, lane, &tfull[ab], aph, stg);
-                conv_epilogue_tma<128>(a.e, &map_or, &map_oa, b, l0 + 128, tn, tmem_base + ab * 256 + 128, quad, lane, &tfull[ab],
-                                       aph, stg);
+                const EpiTma em{&map_or, &map_oa, &map_rs, a.res_tma};
+                if (a.res_tma) {
+                    conv_epilogue_tma<128, true>(a.e, em, b, l0, tn, tmem_base + ab * 256, quad, lane, &tfull[ab], aph, stg, rbar, rcount);
+                    conv_epilogue_tma<128, true>(a.e, em, b, l0 + 128, tn, tmem_base + ab * 256 + 128, quad, lane, &tfull[ab], aph, stg,
+                                                 rbar, rcount);
+                } else {
+                    conv_epilogue_tma<128, false>(a.e, em, b, l0, tn, tmem_base + ab * 256, quad, lane, &tfull[ab], aph, stg, rbar, rcount);
+                    conv_epilogue_tma<128, false>(a.e, em, b, l0 + 128, tn, tmem_base + ab * 256 + 128, quad, lane, &tfull[ab], aph, stg,
+                                                  rbar, rcount);
+                }
             } else {
                 conv_epilogue<128>(a.e, b, l0, tn, tmem_base + ab * 256, quad, lane, &tfull[ab], aph);
                 conv_epilogue<128>(a.e, b, l0 + 128, tn, tmem_base + ab * 256 + 128, quad, lane, &tfull[ab], aph);
@@ -839,17 +894,17 @@ static int launch_conv_tma(const CUtensorMap& ma, const CUtensorMap& mw, ConvTma
 
 template <int C>
 static int launch_conv_slab(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& m_or, const CUtensorMap& m_oa,
-                            const SlabArgs& a, cudaStream_t s) {
+                            const CUtensorMap& m_rs, const SlabArgs& a, cudaStream_t s) {
     constexpr int STAGES = 3;
     const size_t slab_stride = ((size_t)a.rows * C * 2 + 1023) & ~size_t(1023);
-    const size_t smem = (size_t)a.taps * C * C * 2 + STAGES * slab_stride + 256 + 1024 + 4 * 4096 + 1024;
+    const size_t smem = (size_t)a.taps * C * C * 2 + STAGES * slab_stride + 256 + 1024 + 4 * 8192 + 1024 + 128;
     int rc = set_smem_attr2(conv1d_slab_kernel<C, STAGES>, smem);
     if (rc != ADV_OK) return rc;
     const int per_sm = resident_ctas(conv1d_slab_kernel<C, STAGES>, smem, 2 * C);
     const long tiles = (long)a.B * a.tiles_l;
     long grid = (long)num_sms() * per_sm;
     if (grid > tiles) grid = tiles;
-    conv1d_slab_kernel<C, STAGES><<<(unsigned)grid, kConvThreads, smem, s>>>(ma, mw, m_or, m_oa, a);
+    conv1d_slab_kernel<C, STAGES><<<(unsigned)grid, kConvThreads, smem, s>>>(ma, mw, m_or, m_oa, m_rs, a);
     ADV_CUDA_CHECK(cudaGetLastError());
     return ADV_OK;
 }
@@ -858,9 +913,9 @@ static int launch_conv_slab(const CUtensorMap& ma, const CUtensorMap& mw, const 
 
 using namespace adv;
 
-extern "C" int adv_set_conv_epilogue(int tma) {
+extern "C" int adv_set_conv_epilogue(int mode) {   // 0: per-thread stores; 1: TMA stores + TMA residual loads; 2: TMA stores only
     const int prev = adv::g_conv_epi_tma;
-    adv::g_conv_epi_tma = tma ? 1 : 0;
+    adv::g_conv_epi_tma = mode < 0 || mode > 2 ? 1 : mode;
     return prev;
 }
 
@@ -923,21 +978,23 @@ extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* b
                            act_slope, out_scale};
             sa.B = batch; sa.taps = taps; sa.dil = dil; sa.halo = halo; sa.rows = rows;
             sa.tiles_l = (L + 127) / 128;
-            CUtensorMap m_or = ms, m_oa = ms;   // output maps of the TMA-store epilogue: [N][L][B], box 32 x 32, 64-byte swizzle
+            CUtensorMap m_or = ms, m_oa = ms, m_rs = ms;   // output / residual maps of the TMA epilogue: [N][L][B], box 32 x 32, 64-byte swizzle
             sa.epi_tma = g_conv_epi_tma != 0;
-            for (int k = 0; k < 2 && sa.epi_tma; ++k) {
-                void* dst = k == 0 ? out_raw : out_act;
-                if (!dst) continue;
+            sa.res_tma = sa.epi_tma && resid != nullptr && g_conv_epi_tma != 2;
+            for (int k = 0; k < 3 && sa.epi_tma; ++k) {
+                void* dst = k == 0 ? out_raw : (k == 1 ? out_act : const_cast<void*>(resid));
+                if (!dst || (k == 2 && !sa.res_tma)) continue;
                 cuuint64_t od[3] = {(cuuint64_t)N, (cuuint64_t)L, (cuuint64_t)batch};
                 cuuint64_t ost[2] = {(cuuint64_t)N * 2, (cuuint64_t)L * N * 2};
                 cuuint32_t ob[3] = {32, 32, 1};
                 cuuint32_t oe[3] = {1, 1, 1};
-                if (enc(k == 0 ? &m_or : &m_oa, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dst, od, ost, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                    sa.epi_tma = 0;
+                if (enc(k == 0 ? &m_or : (k == 1 ? &m_oa : &m_rs), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dst, od, ost, ob, oe,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    sa.epi_tma = sa.res_tma = 0;
             }
-            return Cin == 64 ? launch_conv_slab<64>(ms, mws, m_or, m_oa, sa, (cudaStream_t)stream)
-                             : launch_conv_slab<32>(ms, mws, m_or, m_oa, sa, (cudaStream_t)stream);
+            return Cin == 64 ? launch_conv_slab<64>(ms, mws, m_or, m_oa, m_rs, sa, (cudaStream_t)stream)
+                             : launch_conv_slab<32>(ms, mws, m_or, m_oa, m_rs, sa, (cudaStream_t)stream);
         }
     }
     static const bool no_slab2 = ADV_AB_ENV("ADV_NO_SLAB2") != nullptr;
@@ -970,26 +1027,28 @@ extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* b
             const size_t part = ((size_t)2 * rb * 128 + 1023) & ~size_t(1023);
             size_t smem = 4 * part + (size_t)WS * 128 * 128 + 256 + 1024;
             // output maps of the TMA-store epilogue: [N][L][B], box 32 channels x 32 rows, 64-byte swizzle
-            CUtensorMap m_or = ms, m_oa = ms;
-            sa.epi_tma = g_conv_epi_tma != 0 && smem + 4 * 4096 + 1024 <= 227 * 1024;
-            for (int k = 0; k < 2 && sa.epi_tma; ++k) {
-                void* dst = k == 0 ? out_raw : out_act;
-                if (!dst) continue;
+            CUtensorMap m_or = ms, m_oa = ms, m_rs = ms;
+            sa.epi_tma = g_conv_epi_tma != 0 && smem + 4 * 4096 + 1024 + 128 <= 227 * 1024;
+            sa.res_tma = sa.epi_tma && resid != nullptr && g_conv_epi_tma != 2 && smem + 4 * 8192 + 1024 + 128 <= 227 * 1024;
+            for (int k = 0; k < 3 && sa.epi_tma; ++k) {
+                void* dst = k == 0 ? out_raw : (k == 1 ? out_act : const_cast<void*>(resid));
+                if (!dst || (k == 2 && !sa.res_tma)) continue;
                 cuuint64_t od[3] = {(cuuint64_t)N, (cuuint64_t)L, (cuuint64_t)batch};
                 cuuint64_t ost[2] = {(cuuint64_t)N * 2, (cuuint64_t)L * N * 2};
                 cuuint32_t ob[3] = {32, 32, 1};
                 cuuint32_t oe[3] = {1, 1, 1};
-                if (enc(k == 0 ? &m_or : &m_oa, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dst, od, ost, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                    sa.epi_tma = 0;
+                if (enc(k == 0 ? &m_or : (k == 1 ? &m_oa : &m_rs), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dst, od, ost, ob, oe,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    sa.epi_tma = sa.res_tma = 0;
             }
-            if (sa.epi_tma) smem += 4 * 4096 + 1024;
+            if (sa.epi_tma) smem += 4 * (sa.res_tma ? 8192 : 4096) + 1024 + 128;
             int rc = set_smem_attr2(conv1d_slab2_kernel<WS>, smem);
             if (rc == ADV_OK) {
                 const long items = (long)batch * sa.pairs_l * sa.tiles_n;
                 long grid = num_sms();
                 if (grid > items) grid = items;
-                conv1d_slab2_kernel<WS><<<(unsigned)grid, kConvThreads, smem, (cudaStream_t)stream>>>(ms, mws, m_or, m_oa, sa);
+                conv1d_slab2_kernel<WS><<<(unsigned)grid, kConvThreads, smem, (cudaStream_t)stream>>>(ms, mws, m_or, m_oa, m_rs, sa);
                 ADV_CUDA_CHECK(cudaGetLastError());
                 return ADV_OK;
             }

@@ -236,8 +236,8 @@ class HifiganGenerator:
                         best = (t, m)
                 mode = self._epi[key] = best[1]
             lib().adv_set_conv_epilogue(1 if mode is None else mode)
-        elif self.epilogue in ("tma", "direct"):
-            lib().adv_set_conv_epilogue(int(self.epilogue == "tma"))
+        elif self.epilogue in ("tma", "direct", "tma_st"):   # "tma_st": TMA stores, residual by per-thread loads (A/B)
+            lib().adv_set_conv_epilogue({"direct": 0, "tma": 1, "tma_st": 2}[self.epilogue])
         launch()
         self.launches += 1
         return out, act
