@@ -381,10 +381,16 @@ def main():
         wb = [0.1 * torch.randn(BB, N, generator=gen, device="cuda") for _ in range(4)]
         sb_ = [ops.stft(w_, want_mag=False, want_phase=False, **kw)[0] for w_ in wb]
 
-        def big_time(fn):
+        def big_time(fn):   # the 4 sets replayed from one CUDA graph (eager Python calls are not always faster than these kernels)
             fn(0)
             torch.cuda.synchronize()
-            return time_loop(lambda i: fn(i % 4), 40) / 40
+            g4 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g4):
+                for i in range(4):
+                    fn(i)
+            for _ in range(3):
+                g4.replay()
+            return time_loop(lambda i: g4.replay(), 10) / 40
 
         tb_s = big_time(lambda i: ops.stft(wb[i], want_mag=False, want_phase=False, **kw))
         tb_3 = big_time(lambda i: ops.stft(wb[i], **kw))
@@ -397,7 +403,7 @@ def main():
     except Exception as e:
         big = {"error": repr(e)[:200]}
     # the reference's DEFAULT geometry (AudioProcessor(): n_fft 1024, hop 322, win 644, 5 s clips) through the same
-    # entry points: these still run the first-generation n_fft 1024 kernels
+    # entry points: streaming n_fft 1024 kernels for explain / istft (transform5_kernels.cu), generation-2 STFT
     refdef = None
     try:
         kw1 = dict(n_fft=1024, hop=322, win_length=644)
@@ -406,10 +412,16 @@ def main():
         m1 = [torch.rand(BATCH, F1, T1, generator=gen, device="cuda") for _ in range(8)]
         s1 = [ops.stft(w_, want_mag=False, want_phase=False, **kw1)[0] for w_ in w1]
 
-        def t8(fn):
-            fn(0)
+        def t8(fn):   # 8 rotating sets (1.3 GB of spectra) replayed from one CUDA graph, like the kernels above: eager calls
+            fn(0)     # from Python cost 25 - 35 us each, more than the faster of these kernels
             torch.cuda.synchronize()
-            return time_loop(lambda i: fn(i % 8), 40) / 40
+            g8 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g8):
+                for i in range(8):
+                    fn(i)
+            for _ in range(3):
+                g8.replay()
+            return time_loop(lambda i: g8.replay(), 10) / 80
 
         t1e = t8(lambda i: ops.explain(w1[i], m1[i], length=n1, **kw1))
         t1s = t8(lambda i: ops.stft(w1[i], **kw1))

@@ -979,7 +979,10 @@ extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* b
             sa.B = batch; sa.taps = taps; sa.dil = dil; sa.halo = halo; sa.rows = rows;
             sa.tiles_l = (L + 127) / 128;
             CUtensorMap m_or = ms, m_oa = ms, m_rs = ms;   // output / residual maps of the TMA epilogue: [N][L][B], box 32 x 32, 64-byte swizzle
-            sa.epi_tma = g_conv_epi_tma != 0;
+            // tensor-bound layers keep the per-thread stores: an 11-tap conv without a residual and with one output loses 4 - 6 %
+            // to the staged form (its four epilogue warps have no slack), measured per layer in profiles/r02zh_* / r02zk_*
+            const bool mma_heavy = taps >= 11 && resid == nullptr && !(out_raw && out_act);
+            sa.epi_tma = g_conv_epi_tma != 0 && !mma_heavy;
             sa.res_tma = sa.epi_tma && resid != nullptr && g_conv_epi_tma != 2;
             for (int k = 0; k < 3 && sa.epi_tma; ++k) {
                 void* dst = k == 0 ? out_raw : (k == 1 ? out_act : const_cast<void*>(resid));
@@ -1028,7 +1031,9 @@ extern "C" int adv_conv1d_bf16_tma(const void* in, const void* w, const float* b
             size_t smem = 4 * part + (size_t)WS * 128 * 128 + 256 + 1024;
             // output maps of the TMA-store epilogue: [N][L][B], box 32 channels x 32 rows, 64-byte swizzle
             CUtensorMap m_or = ms, m_oa = ms, m_rs = ms;
-            sa.epi_tma = g_conv_epi_tma != 0 && smem + 4 * 4096 + 1024 + 128 <= 227 * 1024;
+            // (the 256-channel MRF convs - not the transposed convs - and the 11-tap convs without a residual are tensor-bound)
+            const bool mma_heavy = (Cin == 256 && N == 256) || (taps >= 11 && resid == nullptr && !(out_raw && out_act));
+            sa.epi_tma = g_conv_epi_tma != 0 && !mma_heavy && smem + 4 * 4096 + 1024 + 128 <= 227 * 1024;
             sa.res_tma = sa.epi_tma && resid != nullptr && g_conv_epi_tma != 2 && smem + 4 * 8192 + 1024 + 128 <= 227 * 1024;
             for (int k = 0; k < 3 && sa.epi_tma; ++k) {
                 void* dst = k == 0 ? out_raw : (k == 1 ? out_act : const_cast<void*>(resid));
