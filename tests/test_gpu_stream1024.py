@@ -171,3 +171,32 @@ def test_streaming_explain1024_strided_rows(ops):
     wide[:, 3:3 + n] = wav.cuda()
     rel, irr = ops.explain(wide[:, 3:3 + n], mask, 1024, hop, 644, length=n)
     assert relerr(rel, rel_r) < TOL and relerr(irr, irr_r) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# one-frame-per-warp STFT (stft5_kernel): spectrum only on any window, magnitude / phase on non-rectangular windows
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hop,win,kind", GEOMS + [(322, 1024, "rect"), (250, 644, "hann")])
+@pytest.mark.parametrize("B,n", [(1, 600), (2, 16000), (9, 8050), (64, 80000)])
+def test_stft1024_matches_torch(ops, hop, win, kind, B, n):
+    """clips barely longer than the reflect padding, frames that reach past both clip edges, ragged batches; the full
+    compute_stft return (X, |X|, angle) as well as the spectrum alone"""
+    if B == 64 and (hop, win) not in ((322, 644), (256, 1024)):
+        pytest.skip("full size on the two reference geometries")
+    g = torch.Generator().manual_seed(B * n + hop + win)
+    wav = 0.1 * torch.randn(B, n, generator=g)
+    w = window(win, kind)
+    wk = None if kind == "rect" else w
+    ref = torch.stft(wav, 1024, hop_length=hop, win_length=win, window=w, return_complex=True)
+    X, _, _ = ops.stft(wav, 1024, hop, win, window=wk, want_mag=False, want_phase=False)
+    assert X.shape == ref.shape
+    scale = float(ref.abs().max())
+    assert float((X.cpu() - ref).abs().max()) / scale < TOL
+    X2, mag, ph = ops.stft(wav, 1024, hop, win, window=wk)
+    assert float((X2.cpu() - ref).abs().max()) / scale < TOL
+    assert float((mag.cpu() - ref.abs()).abs().max()) / scale < TOL
+    d = (ph.cpu() - ref.angle()).abs()
+    d = torch.minimum(d, 2 * torch.pi - d)
+    strong = ref.abs() > 1e-3 * scale
+    bound = torch.clamp(3e-7 * scale / ref.abs()[strong], min=1e-5)
+    assert bool((d[strong] <= bound).all())
