@@ -203,6 +203,19 @@ lmac_kernel(const float* __restrict__ p_in, const float* __restrict__ th_in, con
         if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = acc[k];
     }
     __syncthreads();
+    if (gridDim.x == 1) {
+        // up to 1 024 clips (every per-batch call of the pipeline): the block's own fold IS the result - no partials, no
+        // fence / counter / re-read round trips (the kernel was 5.6 us of dependent global accesses for 64 clips, and a
+        // persistent explain CTA waiting for the SM it sits on starts that much later).  Same additions, same order.
+        if (threadIdx.x < 5) {
+            double s = 0.0;
+            for (int w = 0; w < kPwThreads / 32; ++w) s += red[threadIdx.x][w];
+            s = 0.0 + s;
+            sums[threadIdx.x] = (accumulate ? sums[threadIdx.x] : 0.0) + s;
+        }
+        if (threadIdx.x == 5) sums[5] = (accumulate ? sums[5] : 0.0) + (double)n;
+        return;
+    }
     if (threadIdx.x < 5) {
         double s = 0.0;
         for (int w = 0; w < kPwThreads / 32; ++w) s += red[threadIdx.x][w];
