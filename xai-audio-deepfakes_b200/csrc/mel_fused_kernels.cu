@@ -24,6 +24,11 @@
 //     accumulator is zeroed by the epilogue (tcgen05.st) because the chunks write different column ranges;
 //   * the MMAs of tile i run while the warps load and transform the first pair of tile i + 1; its epilogue is executed
 //     by all sixteen warps right before they overwrite the operand tile.
+// Measured and dropped (profiles/r02zr_mel_gen3_variant_slower.jsonl): the same kernel on the generation-3 transform
+// (one frame per warp as a 512-point complex transform + real-1024 post pass, 64-bit global loads with the next frame
+// prefetched in registers, frames of a tile round-robin over the warps, slot ranges balanced across CTAs) - 53.5 us per
+// 64 clips against 45.7 us here, 172 against 147 us per 256: per frame it pays the window multiply, the planar exchanges
+// and 17 address computations for the operand stores, which the two-frames-per-transform unit amortises.
 #include <cuda_bf16.h>
 #include <mutex>
 #include <unordered_map>
