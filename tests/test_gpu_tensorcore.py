@@ -369,3 +369,19 @@ def test_load_speechbrain_state_dict(pkg, H):
         assert torch.allclose(back[k], W[k], rtol=1e-5, atol=1e-7), k
     with pytest.raises(KeyError):
         H.load_speechbrain_state_dict({"foo.weight": torch.zeros(1)})
+
+
+@pytest.mark.parametrize("epilogue", ["tma", "tma_st", "direct", "auto"])
+def test_hifigan_epilogue_variants_agree_and_repeat(pkg, H, epilogue):
+    """The slab conv kernels' epilogues (per-thread stores, TMA stores, TMA stores + TMA residual loads, per-layer choice)
+    compute the same bf16 tensors - bit for bit - and every variant is reproducible run to run."""
+    W = H.init_weights(H.HifiganConfig, seed=3, std=0.03)
+    g = torch.Generator().manual_seed(4)
+    mel = -4 + 2 * torch.randn(5, 80, 37, generator=g)
+    base = H.HifiganGenerator(W, H.HifiganConfig, epilogue="direct").decode_batch(mel)
+    gen = H.HifiganGenerator(W, H.HifiganConfig, epilogue=epilogue)
+    first = gen.decode_batch(mel)
+    assert torch.equal(first, base)
+    for _ in range(5):
+        assert torch.equal(gen.decode_batch(mel), first)
+    pkg._lib.lib().adv_set_conv_epilogue(1)
