@@ -425,11 +425,13 @@ def main():
 
         t1e = t8(lambda i: ops.explain(w1[i], m1[i], length=n1, **kw1))
         t1s = t8(lambda i: ops.stft(w1[i], **kw1))
+        t1x = t8(lambda i: ops.stft(w1[i], want_mag=False, want_phase=False, **kw1))
         t1i = t8(lambda i: ops.istft(s1[i], length=n1, **kw1))
         by_e, by_s, by_i = 4 * n1 + 4 * F1 * T1 + 8 * n1, 4 * n1 + 16 * F1 * T1, 8 * F1 * T1 + 4 * n1
         refdef = {"geometry": "64 x 5 s clips, n_fft 1024 / hop 322 / win 644",
                   "explain": {"us": t1e * 1e6, "frac": by_e * BATCH / t1e / 1e9 / peak, "clips_per_s": BATCH / t1e},
                   "stft_X_mag_phase": {"us": t1s * 1e6, "frac": by_s * BATCH / t1s / 1e9 / peak},
+                  "stft_X": {"us": t1x * 1e6, "frac": (4 * n1 + 8 * F1 * T1) * BATCH / t1x / 1e9 / peak},
                   "istft": {"us": t1i * 1e6, "frac": by_i * BATCH / t1i / 1e9 / peak}}
         del w1, m1, s1
     except Exception as e:
