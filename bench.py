@@ -160,7 +160,7 @@ def run_reference(args, out=sys.stdout):
     cores = torch.get_num_threads()
     step, kind, note = reference_stepper()
     wav, mask, logits = synth_host(1234)
-    steps, warm = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3))
+    steps, warm = max(1, min(args.steps, 40)), max(1, min(args.warmup, 40))
     for _ in range(warm):
         step(wav, mask, logits)
     t0 = time.perf_counter()
