@@ -268,7 +268,7 @@ def main():
     def run_steps(k):
         """k steps on the current stream: whole pools replay the pooled graph, the remainder replays a tail graph over the
         first k % POOL buffer sets (captured on first use, i.e. during warm-up) - every step takes the same pipelined
-        schedule whatever --steps is.  3 launches of ours per step; metric sums accumulate inside lmac_reduce."""
+        schedule whatever --steps is.  2 launches of ours per step (explain; normaliser + metric CTA); metric sums accumulate inside the metric CTA."""
         if pooled:
             if k <= 4 * POOL:      # a short run is ONE graph of exactly k steps (no second launch, no un-pipelined seam)
                 pp.replay_tail(k)
@@ -402,6 +402,41 @@ def main():
         del wb, sb_
     except Exception as e:
         big = {"error": repr(e)[:200]}
+    # ... and at 1 024 clips per launch (the chunk size of BASELINE configs[3]): where the kernels settle once a launch is
+    # long against its fixed costs (2 rotating sets: 0.5 GB of waveforms, 1.7 GB of spectra)
+    huge = None
+    try:
+        BH = 1024
+        wh = [0.1 * torch.randn(BH, N, generator=gen, device="cuda") for _ in range(2)]
+        mh = [torch.rand(BH, F, T, generator=gen, device="cuda") for _ in range(2)]
+        sh = [ops.stft(w_, want_mag=False, want_phase=False, **kw)[0] for w_ in wh]
+        oh = [(torch.empty(BH, N, device="cuda"), torch.empty(BH, N, device="cuda"),
+               torch.empty((BH, ops.get_plan(ap.n_fft, ap.hop_length, ap.win_length, None, T, N, N).tiles(BH), 4),
+                           dtype=torch.float64, device="cuda")) for _ in range(2)]
+
+        def huge_time(fn):
+            fn(0)
+            torch.cuda.synchronize()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                for i in range(2):
+                    fn(i)
+            for _ in range(2):
+                g2.replay()
+            return time_loop(lambda i: g2.replay(), 6) / 12
+
+        th_s = huge_time(lambda i: ops.stft(wh[i], want_mag=False, want_phase=False, **kw))
+        th_3 = huge_time(lambda i: ops.stft(wh[i], **kw))
+        th_i = huge_time(lambda i: ops.istft(sh[i], length=N, **kw))
+        th_e = huge_time(lambda i: ops.explain(wh[i], mh[i], length=N, out=oh[i], **kw))
+        huge = {"clips_per_launch": BH,
+                "stft_X": {"us": th_s * 1e6, "frac": BYTES_STFT * BH / th_s / 1e9 / peak},
+                "stft_X_mag_phase": {"us": th_3 * 1e6, "frac": (BYTES_STFT + 8 * F * T) * BH / th_3 / 1e9 / peak},
+                "istft": {"us": th_i * 1e6, "frac": BYTES_ISTFT * BH / th_i / 1e9 / peak},
+                "explain": {"us": th_e * 1e6, "frac": BYTES_EXPLAIN * BH / th_e / 1e9 / peak, "clips_per_s": BH / th_e}}
+        del wh, mh, sh, oh
+    except Exception as e:
+        huge = {"error": repr(e)[:200]}
     # the reference's DEFAULT geometry (AudioProcessor(): n_fft 1024, hop 322, win 644, 5 s clips) through the same
     # entry points: streaming n_fft 1024 kernels for explain / istft (transform5_kernels.cu), generation-2 STFT
     refdef = None
@@ -594,6 +629,7 @@ def main():
                       "us": t_istft * 1e6},
             "mel_frontend": mel_k,
             "batch256": big,
+            "batch1024": huge,
             "reference_default_geometry": refdef,
         },
         "vocoder": voc,

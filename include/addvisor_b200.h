@@ -130,6 +130,13 @@ int adv_normalize(const float* in, float* out, int batch, int n, const double* s
 /* both outputs of adv_explain normalised in place by one launch; stats = its [B][parts][4] array */
 int adv_normalize_pair(float* rel, float* irr, int batch, int n, const double* stats, int parts, void* stream);
 
+/* adv_normalize_pair and the metric reduction of the same batch in ONE launch (an extra CTA of the normaliser's grid):
+ * the two are independent, and the fused form keeps the 4 us reduction from holding an SM after the normaliser is done.
+ * n_logits <= 1024 (else ADV_ERR_UNSUPPORTED: use adv_lmac_reduce); flags / scores / sums as for adv_lmac_reduce. */
+int adv_normalize_pair_lmac(float* rel, float* irr, int batch, int n, const double* stats, int parts, const float* p,
+                            const float* theta, const float* q, int n_logits, int flags, float* scores, double* sums,
+                            void* stream);
+
 /* ---- LMAC metrics (LMAC_metrics.py:31-73,160-172; sigmoid of classifier_embedder.py:36) ---------------
  * p / theta / q: dev float [n] classifier outputs for the clean, masked-in and masked-out clips;
  * flags: ADV_LMAC_LOGITS applies the logistic sigmoid first; ADV_LMAC_ACCUMULATE adds into `sums`

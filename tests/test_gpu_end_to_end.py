@@ -284,3 +284,43 @@ def test_cfg1_bundled_wavs_match_reference(pkg, built_lib):
         if r["flip_margin_reference"] > 2 * r["max_abs_dp"]:     # no label / AI decision can differ
             np.testing.assert_allclose(got[:2], want[:2], atol=1e-3)          # FF, fidelity (fractions)
             np.testing.assert_allclose(got[2:], want[2:], atol=0.1 + 1e-3)    # AD / AI / AG are percentages: 1e-3 * 100
+
+
+def test_fused_normalise_and_metric_launch_equals_the_two_launches(pkg, built_lib):
+    """adv_normalize_pair_lmac (the metric reduction as an extra CTA of the normaliser's grid) against adv_normalize_pair +
+    adv_lmac_reduce: bit-identical waveforms and sums, with and without accumulation; > 1 024 logits falls back."""
+    ops = pkg.ops
+    g = torch.Generator().manual_seed(21)
+    B, n = 37, 16000
+    wav = 0.1 * torch.randn(B, n, generator=g)
+    mask = torch.rand(B, 257, 101, generator=g)
+    logits = 2 * torch.randn(3, B, generator=g).cuda()
+    tiles = ops.explain_tiles(512, 160, 512, n, B, length=n)
+    outs = []
+    for fused in (False, True):
+        rel = torch.empty(B, n, device="cuda")
+        irr = torch.empty(B, n, device="cuda")
+        stats = torch.empty(B, tiles, 4, dtype=torch.float64, device="cuda")
+        ops.explain(wav, mask, 512, 160, 512, length=n, out=(rel, irr, stats))
+        ws = ops.LmacWorkspace(B, rel.device)
+        for rep in range(2):   # second pass accumulates
+            if fused:
+                if rep == 1:
+                    ops.explain(wav, mask, 512, 160, 512, length=n, out=(rel, irr, stats))
+                sums = ops.normalize_pair_lmac_(rel, irr, stats, logits[0], logits[1], logits[2], is_logit=True, workspace=ws,
+                                                accumulate=rep == 1)
+            else:
+                if rep == 1:
+                    ops.explain(wav, mask, 512, 160, 512, length=n, out=(rel, irr, stats))
+                ops.normalize_pair_(rel, irr, stats)
+                _, sums = ops.lmac(logits[0], logits[1], logits[2], is_logit=True, want_scores=False, workspace=ws,
+                                   accumulate=rep == 1)
+        outs.append((rel.clone(), irr.clone(), sums.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][2], outs[1][2]) and float(outs[0][2][5]) == 2 * B
+    big = 2 * torch.randn(3, 1500, generator=g).cuda()   # more than one metric CTA: two launches behind the same call
+    rel = torch.randn(4, 8000, device="cuda")
+    irr = torch.randn(4, 8000, device="cuda")
+    st = torch.stack([rel.double().sum(1), (rel.double() ** 2).sum(1), irr.double().sum(1), (irr.double() ** 2).sum(1)], 1).reshape(4, 1, 4)
+    sums = ops.normalize_pair_lmac_(rel, irr, st.contiguous(), big[0], big[1], big[2], is_logit=True)
+    assert float(sums[5]) == 1500

@@ -98,13 +98,75 @@ row_stats4_kernel(const float* __restrict__ in, int n, int parts, double* __rest
 // (<= 32 registers per thread: CTAs of this kernel fit next to a resident explain CTA of generation 2 / 3 - 96
 //  registers x 512 threads - so the normaliser of batch i streams through L2 while the issue-bound explain kernel of
 //  batch i+1 owns the issue slots.  The generation-4 explain kernel takes all registers of an SM, see its register cap.)
+__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// The metric reduction of the SAME batch as one extra CTA of the normaliser's grid (up to 1 024 clips): the two are
+// independent, and as separate launches the 4 us reduction held an SM - and with it the start of the next batch's
+// persistent explain CTA on that SM - after the normaliser had finished (LMAC_metrics.py:31-73,160-172; same arithmetic
+// and summation order as lmac_kernel's single-block path).
+struct LmacJob {
+    const float* p;
+    const float* th;
+    const float* q;
+    int n, flags;
+    float* scores;
+    double* sums;
+};
+__device__ __forceinline__ void lmac_single_block(const LmacJob& j, double (*red)[kPwThreads / 32]) {
+    const bool is_logit = j.flags & ADV_LMAC_LOGITS, accumulate = j.flags & ADV_LMAC_ACCUMULATE;
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < j.n; i += kPwThreads) {
+        float p = j.p[i], th = j.th[i], q = j.q[i];
+        if (is_logit) {
+            p = sigmoidf_ref(p);
+            th = sigmoidf_ref(th);
+            q = sigmoidf_ref(q);
+        }
+        const float pc = (p > 0.5f) ? p : 1.0f - p;
+        const float oc = (th > 0.5f) ? th : 1.0f - th;
+        const float d = p - 0.5f;
+        const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+        const float ff = (p - q) * sgn;
+        const float fid = ((p > 0.5f) == (th > 0.5f)) ? 1.f : 0.f;
+        const float ad = (fmaxf(pc - oc, 0.f) / (pc + 1e-10f)) * 100.f;
+        const float ai = (oc > pc) ? 100.f : 0.f;
+        const float ag = (fmaxf(oc - pc, 0.f) / ((1.f - pc) + 1e-10f)) * 100.f;
+        if (j.scores != nullptr) {
+            float* s = j.scores + (size_t)i * 7;
+            s[0] = ff; s[1] = fid; s[2] = ad; s[3] = ai; s[4] = ag; s[5] = pc; s[6] = oc;
+        }
+        acc[0] += ff; acc[1] += fid; acc[2] += ad; acc[3] += ai; acc[4] += ag;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        acc[k] = warp_sum_d(acc[k]);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double s = 0.0;
+        for (int w = 0; w < kPwThreads / 32; ++w) s += red[threadIdx.x][w];
+        s = 0.0 + s;
+        j.sums[threadIdx.x] = (accumulate ? j.sums[threadIdx.x] : 0.0) + s;
+    }
+    if (threadIdx.x == 5) j.sums[5] = (accumulate ? j.sums[5] : 0.0) + (double)j.n;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT, 2048 / NT)
 normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const float* __restrict__ in1,
-                 float* __restrict__ out1, int n, const double* __restrict__ stats, int parts, int width, int col) {
+                 float* __restrict__ out1, int n, const double* __restrict__ stats, int parts, int width, int col,
+                 LmacJob job) {
     __shared__ float s_mean, s_den;
     pdl_launch_dependents();
     pdl_wait();
+    if (NT == kPwThreads && job.p != nullptr && blockIdx.x == gridDim.x - 1) {   // the grid's extra column: the metric CTA
+        if (blockIdx.y == 0 && blockIdx.z == 0) {
+            __shared__ double red[5][kPwThreads / 32];
+            lmac_single_block(job, red);
+        }
+        return;
+    }
     const int b = blockIdx.y, z = blockIdx.z;
     const float* in = z ? in1 : in0;
     float* out = z ? out1 : out0;
@@ -161,7 +223,6 @@ normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const 
 // ---- LMAC scores + deterministic two-level sum -----------------------------------------------------
 constexpr int kLmacPerBlock = 1024;
 
-__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __global__ void __launch_bounds__(kPwThreads, 8)
 lmac_kernel(const float* __restrict__ p_in, const float* __restrict__ th_in, const float* __restrict__ q_in, int n,
@@ -698,7 +759,7 @@ int adv_normalize(const float* in, float* out, int batch, int n, const double* s
         return ADV_ERR_INVALID;
     const int chunks = (n + kRowChunk - 1) / kRowChunk;
     ADV_CUDA_CHECK(launch_pdl(normalize_kernel<kPwThreads>, dim3(chunks, batch, 1), dim3(kPwThreads), 0, (cudaStream_t)stream,
-                              in, out, in, out, n, stats, parts, width, col));
+                              in, out, in, out, n, stats, parts, width, col, LmacJob{nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr}));
     return ADV_OK;
 }
 
@@ -710,10 +771,23 @@ int adv_normalize_pair(float* rel, float* irr, int batch, int n, const double* s
     static const char* nt_env = ADV_AB_ENV("ADV_NORM_THREADS");
     if (nt_env && nt_env[0] == '1')
         ADV_CUDA_CHECK(launch_pdl(normalize_kernel<128>, dim3(chunks, batch, 2), dim3(128), 0, (cudaStream_t)stream, rel, rel,
-                                  irr, irr, n, stats, parts, 4, 0));
+                                  irr, irr, n, stats, parts, 4, 0, LmacJob{nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr}));
     else
         ADV_CUDA_CHECK(launch_pdl(normalize_kernel<256>, dim3(chunks, batch, 2), dim3(256), 0, (cudaStream_t)stream, rel, rel,
-                                  irr, irr, n, stats, parts, 4, 0));
+                                  irr, irr, n, stats, parts, 4, 0, LmacJob{nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr}));
+    return ADV_OK;
+}
+
+int adv_normalize_pair_lmac(float* rel, float* irr, int batch, int n, const double* stats, int parts, const float* p,
+                            const float* theta, const float* q, int n_logits, int flags, float* scores, double* sums,
+                            void* stream) {
+    if (!rel || !irr || !stats || batch <= 0 || n <= 1 || parts <= 0 || !p || !theta || !q || !sums || n_logits <= 0)
+        return ADV_ERR_INVALID;
+    if (n_logits > kLmacPerBlock) return ADV_ERR_UNSUPPORTED;   // more than one metric CTA: use adv_lmac_reduce
+    const int chunks = (n + kRowChunk - 1) / kRowChunk;
+    const LmacJob job{p, theta, q, n_logits, flags, scores, sums};
+    ADV_CUDA_CHECK(launch_pdl(normalize_kernel<256>, dim3(chunks + 1, batch, 2), dim3(256), 0, (cudaStream_t)stream, rel, rel,
+                              irr, irr, n, stats, parts, 4, 0, job));
     return ADV_OK;
 }
 

@@ -167,6 +167,21 @@ def normalize_pair_(rel, irr, stats):
     return rel, irr
 
 
+def normalize_pair_lmac_(rel, irr, stats, p, theta, q, is_logit=False, workspace=None, accumulate=False):
+    """``normalize_pair_`` and ``lmac`` (sums only) of the same batch in one launch - the metric reduction rides as an
+    extra CTA of the normaliser's grid.  Up to 1 024 logits; returns the float64 [6] sums tensor of the workspace."""
+    B, n_out = rel.shape
+    n = p.numel()
+    if n > 1024 or not (p.is_contiguous() and theta.is_contiguous() and q.is_contiguous()) or p.dtype != torch.float32:
+        normalize_pair_(rel, irr, stats)
+        return lmac(p, theta, q, is_logit=is_logit, want_scores=False, workspace=workspace, accumulate=accumulate)[1]
+    ws = workspace if workspace is not None and workspace.n == n else LmacWorkspace(n, rel.device)
+    flags = (1 if is_logit else 0) | (2 if accumulate else 0)
+    check(lib().adv_normalize_pair_lmac(ptr(rel), ptr(irr), B, n_out, ptr(stats), stats.shape[1], ptr(p), ptr(theta), ptr(q),
+                                        n, flags, None, ptr(ws.sums), stream_ptr()), "adv_normalize_pair_lmac")
+    return ws.sums
+
+
 def explain_tiles(n_fft, hop, win_length, n, batch, length=None, window=None):
     """Tiles per clip the explain kernel will use (second dim of its ``stats`` buffer)."""
     T = 1 + n // hop

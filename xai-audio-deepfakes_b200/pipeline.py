@@ -4,7 +4,8 @@ on preallocated buffers and (optionally) replayed as one CUDA graph.
     wave [B,n] + mask [B,F,T] --explain--> rel, irr --normalise x2--> (SSL classifier, not ours)
     logits p / theta / q [B] --lmac_reduce--> six float64 sums
 
-Launches per step: explain, normalize (both waves), lmac = 3 kernels, no allocation, no host sync.
+Launches per step: explain, then normalize (both waves) with the metric reduction riding as one extra CTA of the same
+grid = 2 kernels, no allocation, no host sync.
 ``step_host`` is the end-to-end entry: inputs arrive in pinned host memory, are copied to the device
 on a side stream (double-buffered against the previous step's compute), and the six sums come back
 to pinned host memory.
@@ -16,7 +17,7 @@ import torch
 from . import ops
 from ._lib import check, lib, ptr, stream_ptr
 
-KERNELS_PER_STEP = 3
+KERNELS_PER_STEP = 2
 
 
 class ExplainPipeline:
@@ -42,13 +43,10 @@ class ExplainPipeline:
         if use_graph:
             self._capture()
 
-    # the three launches of one step, on the current stream
+    # the launches of one step, on the current stream
     def _enqueue(self):
-        ap = self.ap
-        ops.explain(self.wav, self.mask, ap.n_fft, ap.hop_length, ap.win_length, length=self.n, mode=self.mode,
-                    normalize=True, out=(self.rel, self.irr, self.stats))
-        ops.lmac(self.logits[0], self.logits[1], self.logits[2], is_logit=True, want_scores=False,
-                 workspace=self.ws, accumulate=self.accumulate)
+        self.enqueue_explain()
+        self.enqueue_post()
 
     # the same step in two parts, for callers that overlap part 2 of batch i with part 1 of batch i+1
     def enqueue_explain(self):
@@ -57,9 +55,8 @@ class ExplainPipeline:
                     normalize=False, out=(self.rel, self.irr, self.stats))
 
     def enqueue_post(self):
-        ops.normalize_pair_(self.rel, self.irr, self.stats)
-        ops.lmac(self.logits[0], self.logits[1], self.logits[2], is_logit=True, want_scores=False,
-                 workspace=self.ws, accumulate=self.accumulate)
+        ops.normalize_pair_lmac_(self.rel, self.irr, self.stats, self.logits[0], self.logits[1], self.logits[2], is_logit=True,
+                                 workspace=self.ws, accumulate=self.accumulate)
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.dev)
