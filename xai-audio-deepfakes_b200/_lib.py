@@ -12,7 +12,8 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libaddvisor_sm100.so"
-LIB_PATH = os.path.join(_HERE, LIB_NAME)
+# ADV_LIB_PATH: load another build of the same library (A/B variants built with ADV_NVCC_EXTRA); never rebuilt from here
+LIB_PATH = os.environ.get("ADV_LIB_PATH") or os.path.join(_HERE, LIB_NAME)
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["capi.cu", "transform_kernels.cu", "transform3_kernels.cu", "transform4_kernels.cu", "transform5_kernels.cu", "pointwise_kernels.cu", "gemm_kernels.cu", "mel_fused_kernels.cu", "conv_tma_kernels.cu",
            "resunit_kernels.cu"]
@@ -32,6 +33,8 @@ def sources():
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if os.environ.get("ADV_LIB_PATH") and os.path.exists(LIB_PATH):
+        return LIB_PATH
     srcs = sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     deps.append(os.path.join(_HERE, "..", "include", "addvisor_b200.h"))

@@ -11,6 +11,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // the executing thread's earlier cp.async copies arrive on `bar` when they have landed (no pending-count increment:
 // the barrier's expected count includes one such arrival per thread)
+// non-blocking phase test (true once the phase of the given parity has completed)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -81,7 +81,8 @@ stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int t
     float* seg_all = cv.take<float>(C::WARPS * C::seg_floats(P.hop));
     uint64_t* bars = cv.take<uint64_t>(C::WARPS);
 
-    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const int tid = threadIdx.x, l = tid & 31;
+    const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (tells the compiler the warp index is warp-uniform)
     float* seg = seg_all + (size_t)w * C::seg_floats(P.hop);
     uint64_t* bar = bars + w;
     const int seglen = P.hop + NF;
@@ -142,11 +143,11 @@ stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int t
         };
 #else
     const int stride = gridDim.x * C::WARPS;
-    // CTA-uniform trip count (the grid never exceeds ceil(items / WARPS) CTAs): every warp runs the same loop, so the
-    // transforms - and their __syncwarp()s - sit in provably convergent code.  A warp whose item index runs past the
-    // list repeats the last item with its stores switched off.
-    const int first = blockIdx.x * C::WARPS;
-    const int n_iter = (total_items - first + stride - 1) / stride;
+    // per-warp trip count: a warp leaves the loop after its last item (and requests no slice it will not consume).  Until
+    // r02zz the count was CTA-uniform and a warp past the list repeated the last item with its stores switched off: at 64
+    // clips that is 4 rounds billed for 3.6.
+    const int first = blockIdx.x * C::WARPS + w;
+    const int n_iter = first < total_items ? (total_items - first + stride - 1) / stride : 0;
 
     if (l == 0) mbar_init(bar, 1);
     stage_tw3<NF, kThreads>(tw_s, win_s, P, !RECT);
@@ -157,19 +158,21 @@ stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int t
 
     float* my = scratch + w * f3::Scr<VEC>::FLOATS;
     const int q1 = q1_lane(l);
-    int item = min(first + w, total_items - 1);
+    int item = min(first, total_items - 1);
     int b = item / items_per_clip, t0 = (item - b * items_per_clip) * 2;
-    int shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar, l, ZP);
+    int shift = 0;
+    if (n_iter > 0)
+        shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar, l, ZP);
 
     for (int it = 0; it < n_iter; ++it) {
         __syncwarp();  // plain-load part of the slice visible to the warp
         mbar_wait(bar, it & 1);
         const int cur_b = b, fa = t0, cur_shift = shift;
-        const bool active = first + it * stride + w < total_items;
-        const bool more = it + 1 < n_iter;  // (CTA-uniform)
+        constexpr bool active = true;
+        const bool more = it + 1 < n_iter;  // (warp-uniform)
         auto request_next = [&]() {   // (called from inside the forward transform: every lane has consumed its samples)
             if (more) {
-                item = min(first + (it + 1) * stride + w, total_items - 1);
+                item = first + (it + 1) * stride;
                 b = item / items_per_clip;
                 t0 = (item - b * items_per_clip) * 2;
                 shift = stage_segment_async<32>(seg, seglen, wav + (size_t)b * wav_stride, t0 * P.hop - NF / 2, P.n_in, bar,

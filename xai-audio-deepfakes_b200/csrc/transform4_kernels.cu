@@ -32,6 +32,15 @@
 
 namespace adv {
 
+#ifndef ADV_E4_MASK_GW
+#define ADV_E4_MASK_GW 16
+#endif
+#ifndef ADV_E4_LATE_EMPTY
+#define ADV_E4_LATE_EMPTY 1
+#endif
+#ifndef ADV_E4_EARLY_EXIT  // 1: warps without a unit in the (last) pass leave the loop instead of transforming silence
+#define ADV_E4_EARLY_EXIT 1
+#endif
 template <int HS>
 struct E4Cfg {
     static constexpr int UNITS = 16, NT = 512, F = 257, MP = 33;
@@ -42,7 +51,9 @@ struct E4Cfg {
     static constexpr int NB = (TAIL + HEAD - 1) / HEAD;   // earlier units reaching into a unit's head
     static constexpr int SEG = (HOP + 512 + 8 + 3) & ~3;  // floats of a warp's waveform slice
     static constexpr int MASK_TILE = (F * MP + 3) & ~3;
-    static constexpr int NBARS = 3 * UNITS + 2;
+    // warps sharing one refill of their mask columns (16 = the whole tile at once; see ADV_E4_MASK_GW below)
+    static constexpr int MGW = ADV_E4_MASK_GW, MGROUPS = UNITS / MGW;
+    static constexpr int NBARS = 3 * UNITS + 2 * MGROUPS;
     // 64-bit exchanges in the transforms (half the shared-memory instructions of the planar form, and register pairs
     // arrive aligned for the packed f32x2 butterflies); their 4.6 KB of scratch per warp is paid for by keeping ONE mask
     // tile: the next tile is requested once all 16 warps have read the current one, a stage and a half ahead of its use
@@ -83,8 +94,9 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
     uint64_t* full = bars;                 // [16] tail of unit slot w written (1 arrival per pass)
     uint64_t* empty = bars + UNITS;        // [16] tail of unit slot w read by its NB consumers
     uint64_t* segbar = bars + 2 * UNITS;   // [16] waveform slice of warp w landed
-    uint64_t* mfull = bars + 3 * UNITS;    // mask tile landed (512 cp.async arrivals per pass)
-    uint64_t* mempty = mfull + 1;          // mask tile read by all 16 warps
+    constexpr int MGW = C::MGW, MGROUPS = C::MGROUPS, MNT = 32 * MGW, MGC = 2 * MGW;
+    uint64_t* mfull_all = bars + 3 * UNITS;      // [groups] the group's mask columns landed (32 MGW cp.async arrivals per pass)
+    uint64_t* mempty_all = mfull_all + MGROUPS;  // [groups] ... read by the group's MGW warps
 
     const int tid = threadIdx.x, l = tid & 31;
     const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);  // (tells the compiler the warp index is warp-uniform)
@@ -106,8 +118,10 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
             mbar_init(empty + i, NB);
             mbar_init(segbar + i, 1);
         }
-        mbar_init(mfull, NT);
-        mbar_init(mempty, UNITS);
+        for (int i = 0; i < MGROUPS; ++i) {
+            mbar_init(mfull_all + i, MNT);
+            mbar_init(mempty_all + i, MGW);
+        }
     }
     for (int i = tid; i < C::TW3N / 2; i += NT) cp_async16(tw_s + 2 * i, P.tw3 + 2 * i);
     cp_async_commit();
@@ -138,7 +152,11 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
     constexpr int seglen = HOP + 512;
 
     // ---- per-thread mask staging: column c of the tile <-> frame (c & 1) of unit slot c >> 1; rows f0 + 16 k
-    const int mc = tid & 31, mf0 = tid >> 5;
+    //      (the columns are refilled per group of MGW adjacent warps: a group's 32 MGW threads copy its 2 MGW columns)
+    const int mgrp = w / MGW, mtg = tid - mgrp * MNT;
+    const int mc = mgrp * MGC + mtg % MGC, mf0 = mtg / MGC;
+    uint64_t* mfull = mfull_all + mgrp;
+    uint64_t* mempty = mempty_all + mgrp;
     UnitPos mpos{b0, u0};           // unit of this thread's mask column in the pass being requested
     {
         int g = start + (mc >> 1);  // may precede g_begin (halo units have mask columns too)
@@ -205,6 +223,11 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
     for (int p = 0; p < n_pass; ++p) {
         const int g = start + p * UNITS + w;
         const bool active = g < g_end;
+#if ADV_E4_EARLY_EXIT
+        // (last pass only; nobody waits for anything such a warp would arrive on: its slot's consumers are idle as well, the
+        //  mask tile is not refilled any more)
+        if (!active) break;
+#endif
         const bool is_out = active && g >= g_begin;
         const UnitPos cur = pos;
         const int cur_shift = shift;
@@ -273,9 +296,14 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
         //       = frame a row r (r < 16) + frame b row r - HS (r >= HS).  Rows < HEAD stay in registers, the tail rows go
         //       to shared memory for the next NB units.
         float head_r[HEAD], head_i[HEAD];
+#if !ADV_E4_LATE_EMPTY
         if (p >= 1) mbar_wait(empty + w, (p - 1) & 1);   // the previous pass's tail of this slot has been consumed
+#endif
         {
             f3::fft_inverse<C::VEC>(v, l, tw_s, my);
+#if ADV_E4_LATE_EMPTY
+            if (p >= 1) mbar_wait(empty + w, (p - 1) & 1);   // the previous pass's tail of this slot has been consumed
+#endif
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 float o = r < 16 ? v[r < 16 ? r : 0].x : 0.0f;
@@ -486,6 +514,9 @@ istft4_kernel(PlanDev P, int upc, int total_units, const float2* __restrict__ X,
     for (int p = 0; p < n_pass; ++p) {
         const int g = start + p * UNITS + w;
         const bool active = g < g_end;
+#if ADV_E4_EARLY_EXIT
+        if (!active) break;   // (last pass only; see explain4_kernel)
+#endif
         const bool is_out = active && g >= g_begin;
         const UnitPos cur = pos;
         pos.advance(UNITS, upc);

@@ -160,6 +160,7 @@ istft5_kernel(PlanDev P, Geo5 G, int upc, int total_units, const float2* __restr
     for (int p = 0; p < n_pass; ++p) {
         const int g = start + p * UNITS + w;
         const bool active = g < g_end;
+        if (!active) break;   // (last pass only: nobody waits for an arrival of a warp without a unit; see explain4_kernel)
         const bool is_out = active && g >= g_begin;
         const UnitPos cur = pos;
         pos.advance(UNITS, upc);
@@ -384,6 +385,7 @@ explain5_kernel(PlanDev P, Geo5 G, int upc, int total_units, const float* __rest
     for (int p = 0; p < n_pass; ++p) {
         const int g = start + p * UNITS + w;
         const bool active = g < g_end;
+        if (!active) break;   // (last pass only: nobody waits for an arrival of a warp without a unit; see explain4_kernel)
         const bool is_out = active && g >= g_begin;
         const UnitPos cur = pos;
         const int cur_shift = shift;
@@ -571,14 +573,14 @@ stft5_kernel(PlanDev P, Geo5 G, const float* __restrict__ wav, int64_t wav_strid
     float* win_s = RECT ? nullptr : cv.take<float>(1024);
     uint64_t* bars = cv.take<uint64_t>(WARPS);
 
-    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const int tid = threadIdx.x, l = tid & 31;
+    const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (tells the compiler the warp index is warp-uniform)
     float* seg = seg_all + (size_t)w * SEG;
     uint64_t* bar = bars + w;
     const int stride = gridDim.x * WARPS;
-    // CTA-uniform trip count: the transforms and their __syncwarp()s sit in provably convergent code; a warp whose item
-    // index runs past the list repeats the last item with its stores switched off (see stft3_kernel)
-    const int first = blockIdx.x * WARPS;
-    const int n_iter = (total_items - first + stride - 1) / stride;
+    // per-warp trip count: a warp leaves the loop after its last item (it requests no slice it will not consume)
+    const int first = blockIdx.x * WARPS + w;
+    const int n_iter = first < total_items ? (total_items - first + stride - 1) / stride : 0;
 
     if (l == 0) mbar_init(bar, 1);
     for (int i = tid; i < f3::TW_TOTAL / 2; i += kF5Threads) cp_async16(tw_s + 2 * i, P.tw3 + 2 * i);
@@ -592,15 +594,17 @@ stft5_kernel(PlanDev P, Geo5 G, const float* __restrict__ wav, int64_t wav_strid
 
     float* my = scratch + w * f3::Scr<true>::FLOATS;
     const int q1 = l == 0 ? 32 : 64 - l;
-    int item = min(first + w, total_items - 1);
+    int item = min(first, total_items - 1);
     int b = item / P.T, t = item - b * P.T;
-    int shift = stage_segment_async<32>(seg, G.sup, wav + (size_t)b * wav_stride, t * G.hop - 512 + G.wlo, P.n_in, bar, l);
+    int shift = 0;
+    if (n_iter > 0)
+        shift = stage_segment_async<32>(seg, G.sup, wav + (size_t)b * wav_stride, t * G.hop - 512 + G.wlo, P.n_in, bar, l);
 
     for (int it = 0; it < n_iter; ++it) {
         __syncwarp();
         mbar_wait(bar, it & 1);
         const int cur_b = b, cur_t = t, cur_shift = shift;
-        const bool active = first + it * stride + w < total_items;
+        constexpr bool active = true;
         const bool more = it + 1 < n_iter;
         float2 v[16];
         {
@@ -622,7 +626,7 @@ stft5_kernel(PlanDev P, Geo5 G, const float* __restrict__ wav, int64_t wav_strid
         }
         f3::fft_forward<true>(v, l, tw_s, my, [&] {   // every lane has consumed its samples: request the next slice
             if (more) {
-                item = min(first + (it + 1) * stride + w, total_items - 1);
+                item = first + (it + 1) * stride;
                 b = item / P.T;
                 t = item - b * P.T;
                 shift = stage_segment_async<32>(seg, G.sup, wav + (size_t)b * wav_stride, t * G.hop - 512 + G.wlo, P.n_in,
