@@ -493,6 +493,16 @@ def main():
         mel_k = {"error": repr(e)[:200]}
 
     # ---- end to end through the public API with pinned host inputs
+    # A single-process run binds itself to the CPUs next to the GPU for these legs only (the pinned buffers are first-touched
+    # there; boxes whose H2D peak measured 45 - 50 instead of 55 GB/s had them on the other socket) and gives the cores back
+    # before the CPU baseline.  Ranks of a multi-process run are bound from the start.
+    saved_aff, e2e_aff = None, affinity
+    if world == 1 and os.environ.get("ADV_NO_BIND") is None:
+        try:
+            saved_aff = os.sched_getaffinity(0)
+            e2e_aff = pkg.distributed.bind_host_to_gpu(local)
+        except Exception:
+            saved_aff = None
     hp = pipeline.HostFedPipeline(ap, BATCH, use_graph=True)
     host_sets = []
     for k in range(4):
@@ -544,6 +554,11 @@ def main():
         del y1, wp
     except Exception as e:
         e2e_wave = {"error": repr(e)[:200]}
+    if saved_aff is not None:
+        try:
+            os.sched_setaffinity(0, saved_aff)
+        except Exception:
+            pass
     # ---- vocoder side path (BASELINE configs[2] geometry, smaller batch): HiFi-GAN on the tcgen05 conv kernels
     voc = None
     try:
@@ -611,7 +626,8 @@ def main():
         "config": workload_config(world),
         "run": {"cuda_graph": True, "schedule": args.schedule, "streams": ns, "burst_us_per_step": burst_us,
                 "preheat_s": round(preheat_s, 3), "preheat_steps": preheat_steps,
-                "host_affinity": (f"{len(affinity)} cpus local to the GPU (NVML)" if affinity else "unbound")},
+                "host_affinity": (f"{len(affinity)} cpus local to the GPU (NVML)" if affinity else "unbound"),
+                "e2e_host_affinity": (f"{len(e2e_aff)} cpus local to the GPU (NVML)" if e2e_aff else "unbound")},
         "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": hp.h2d_bytes,
                 "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps},
         "e2e_wave_only": e2e_wave, "pcie": pcie,
