@@ -407,13 +407,18 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
                              // spills, 29.9 us; 1 x 512 at 128: 21.1 us; 3 x 256 at 80: 20.7 us; 2 x 256 at 120: 20.3 us
 constexpr int kI4Units = ADV_ISTFT4_UNITS, kI4Threads = 32 * kI4Units;
 
+#ifndef ADV_I4_TAIL_BUFS
+#define ADV_I4_TAIL_BUFS 2
+#endif
 template <int HS>
 struct I4Cfg {
     using E = E4Cfg<HS>;
-    static constexpr int UNITS = kI4Units, NBARS = 2 * UNITS;
+    // TB tail buffers per unit slot (2: a warp writes pass p's tail while the next warps may still be reading pass p - 1's -
+    // shared memory is not what limits this kernel's occupancy)
+    static constexpr int UNITS = kI4Units, TB = ADV_I4_TAIL_BUFS, NBARS = 2 * TB * UNITS;
     static size_t bytes() {
         return al16(sizeof(float2) * E::TW3N) + al16(sizeof(float) * UNITS * f3::Scr<true>::FLOATS) +
-               al16(sizeof(float) * UNITS * E::TAIL * 32) + al16(sizeof(uint64_t) * NBARS);
+               al16(sizeof(float) * TB * UNITS * E::TAIL * 32) + al16(sizeof(uint64_t) * NBARS);
     }
 };
 
@@ -428,10 +433,11 @@ istft4_kernel(PlanDev P, int upc, int total_units, const float2* __restrict__ X,
     Carver cv{smem_raw};
     float2* tw_s = cv.take<float2>(C::TW3N);
     float* scratch = cv.take<float>(UNITS * f3::Scr<true>::FLOATS);
-    float* tails = cv.take<float>(UNITS * TAIL * 32);
+    constexpr int TB = I4Cfg<HS>::TB;
+    float* tails = cv.take<float>(TB * UNITS * TAIL * 32);            // [TB][UNITS][TAIL][32]
     uint64_t* bars = cv.take<uint64_t>(I4Cfg<HS>::NBARS);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + UNITS;
+    uint64_t* full = bars;                    // [TB][UNITS] tail of unit slot w written (pass p uses buffer p % TB)
+    uint64_t* empty = bars + TB * UNITS;      // [TB][UNITS] ... read by its NB consumers
 
     const int tid = threadIdx.x, l = tid & 31;
     const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -444,7 +450,7 @@ istft4_kernel(PlanDev P, int upc, int total_units, const float2* __restrict__ X,
     const int n_pass = (g_end - start + UNITS - 1) / UNITS;
 
     if (tid == 0)
-        for (int i = 0; i < UNITS; ++i) {
+        for (int i = 0; i < TB * UNITS; ++i) {
             mbar_init(full + i, 1);
             mbar_init(empty + i, NB);
         }
@@ -469,7 +475,6 @@ istft4_kernel(PlanDev P, int upc, int total_units, const float2* __restrict__ X,
     }
 
     float* my = scratch + w * f3::Scr<true>::FLOATS;
-    float* tail_w = tails + w * (TAIL * 32);
     const int q1 = l == 0 ? 32 : 64 - l;
     const int64_t sfe = CONTIG ? 1 : sf;
 
@@ -529,7 +534,10 @@ istft4_kernel(PlanDev P, int upc, int total_units, const float2* __restrict__ X,
         // -- 2. inverse transform, overlap-add of the two frames in registers, tail rows to shared memory
         f3::fft_inverse<true>(v, l, tw_s, my);
         float head[HEAD];
-        if (p >= 1) mbar_wait(empty + w, (p - 1) & 1);
+        // buffer p % TB of this slot was last written in pass p - TB: its phase index on either barrier is p / TB
+        const int tb = p % TB;
+        float* tail_w = tails + (tb * UNITS + w) * (TAIL * 32);
+        if (p >= TB) mbar_wait(empty + tb * UNITS + w, (p / TB - 1) & 1);
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
             float o = r < 16 ? v[r < 16 ? r : 0].x : 0.0f;
@@ -538,7 +546,7 @@ istft4_kernel(PlanDev P, int upc, int total_units, const float2* __restrict__ X,
             else tail_w[(r - HEAD) * 32 + l] = o;
         }
         __syncwarp();
-        if (l == 0) mbar_arrive(full + w);
+        if (l == 0) mbar_arrive(full + tb * UNITS + w);
 
         const int s_base = USTEP * cur.u - 256 + l;
         float env[HEAD];
@@ -554,14 +562,15 @@ istft4_kernel(PlanDev P, int upc, int total_units, const float2* __restrict__ X,
         for (int k = NB; k >= 1; --k) {
             const int slot = (w - k) & (UNITS - 1);
             const int pp = w >= k ? p : p - 1;
-            if (pp >= 0) mbar_wait(full + slot, pp & 1);
+            const int pb = pp >= 0 ? pp % TB : 0;
+            if (pp >= 0) mbar_wait(full + pb * UNITS + slot, (pp / TB) & 1);
             if (is_out && cur.u >= k) {
-                const float* tn = tails + slot * (TAIL * 32) + l;
+                const float* tn = tails + (pb * UNITS + slot) * (TAIL * 32) + l;
 #pragma unroll
                 for (int r = (k - 1) * HEAD; r < k * HEAD && r < TAIL; ++r) head[r - (k - 1) * HEAD] += tn[r * 32];
             }
             __syncwarp();
-            if (l == 0 && pp >= 0) mbar_arrive(empty + slot);
+            if (l == 0 && pp >= 0) mbar_arrive(empty + pb * UNITS + slot);
         }
         // -- 4. scale, statistics, store
         if (is_out) {
