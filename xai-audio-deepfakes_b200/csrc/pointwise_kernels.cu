@@ -152,6 +152,9 @@ __device__ __forceinline__ void lmac_single_block(const LmacJob& j, double (*red
     if (threadIdx.x == 5) j.sums[5] = (accumulate ? j.sums[5] : 0.0) + (double)j.n;
 }
 
+#ifndef ADV_NORM_PRELOAD
+#define ADV_NORM_PRELOAD 1
+#endif
 template <int NT>
 __global__ void __launch_bounds__(NT, 2048 / NT)
 normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const float* __restrict__ in1,
@@ -170,7 +173,27 @@ normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const 
     const int b = blockIdx.y, z = blockIdx.z;
     const float* in = z ? in1 : in0;
     float* out = z ? out1 : out0;
-    if (threadIdx.x < 32) {  // warp 0 folds the per-tile partials in a fixed order (lane-strided + butterfly)
+    const float* row = in + (size_t)b * n;
+    float* orow = out + (size_t)b * n;
+    const int lo = blockIdx.x * kRowChunk, hi = min(n, lo + kRowChunk);
+    const bool vec = ((n & 3) == 0) && (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    float4* o4 = reinterpret_cast<float4*>(orow);
+    constexpr int U = 4;
+    // the first samples of the chunk are requested before the statistics are folded: the whole grid is one wave, so the
+    // fold's two dependent round trips (partials, then a double-precision divide and square root) would otherwise pass
+    // with no load in flight anywhere
+    float4 v[U];
+    int i = lo / 4 + threadIdx.x;
+    if (threadIdx.x >= 32) {   // (warp 0 folds first: it has no registers to hold samples across the fold)
+#if ADV_NORM_PRELOAD
+        if (vec) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * NT < hi / 4) v[u] = __ldg(r4 + i + u * NT);
+        }
+#endif
+    } else {  // warp 0 folds the per-tile partials in a fixed order (lane-strided + butterfly)
         double s = 0.0, ss = 0.0;
         const double* st = stats + (size_t)b * parts * width + col + 2 * z;
         for (int k = threadIdx.x; k < parts; k += 32) {
@@ -191,19 +214,17 @@ normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const 
     // one reciprocal per row instead of a division per sample (<= 1.5 ulp from the reference's quotient; the
     // IEEE division was a third of this kernel's instructions)
     const float mean = s_mean, inv = 1.0f / s_den;
-    const float* row = in + (size_t)b * n;
-    float* orow = out + (size_t)b * n;
-    const int lo = blockIdx.x * kRowChunk, hi = min(n, lo + kRowChunk);
-    const bool vec = ((n & 3) == 0) && (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+#if ADV_NORM_PRELOAD
+    if (vec && threadIdx.x < 32) {
+#else
     if (vec) {
-        const float4* r4 = reinterpret_cast<const float4*>(row);
-        float4* o4 = reinterpret_cast<float4*>(orow);
-        constexpr int U = 4;
-        for (int i = lo / 4 + threadIdx.x; i < hi / 4; i += NT * U) {
-            float4 v[U];
+#endif
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (i + u * NT < hi / 4) v[u] = __ldg(r4 + i + u * NT);
+        for (int u = 0; u < U; ++u)
+            if (i + u * NT < hi / 4) v[u] = __ldg(r4 + i + u * NT);
+    }
+    if (vec) {
+        for (; i < hi / 4; i += NT * U) {
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (i + u * NT < hi / 4) {
@@ -214,9 +235,13 @@ normalize_kernel(const float* __restrict__ in0, float* __restrict__ out0, const 
                     y.w = (v[u].w - mean) * inv;
                     o4[i + u * NT] = y;
                 }
+            const int nx = i + NT * U;   // next round's loads
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (nx + u * NT < hi / 4) v[u] = __ldg(r4 + nx + u * NT);
         }
     } else {
-        for (int i = lo + threadIdx.x; i < hi; i += NT) orow[i] = (__ldg(row + i) - mean) * inv;
+        for (int j = lo + threadIdx.x; j < hi; j += NT) orow[j] = (__ldg(row + j) - mean) * inv;
     }
 }
 
