@@ -2,7 +2,7 @@
 # round-2 GPU session ZZB: final validation - whole GPU suite, smoke, bench line + launch list of the same command, the
 # reference arm, and a fresh --set full capture of the production kernels (1 024 clips) for profiles/traffic.json
 cd "$(dirname "$0")/.."
-O=gpurun_out/r02zzb; mkdir -p $O
+O=gpurun_out/${OUT:-r02zzb}; mkdir -p $O
 timeout 900 python -m pytest tests -x -q -m gpu > $O/pytest_all.log 2>&1; echo "pytest all rc=$?" | tee -a $O/summary.txt
 tail -3 $O/pytest_all.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $O/summary.txt
@@ -16,5 +16,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"explain4_kernel|stft3_kernel|istft4_kernel|mel_fused_kernel" -f -o $O/prof_full python scripts/prof_traffic.py > $O/ncu_full.log 2>&1; echo "ncu full rc=$?" | tee -a $O/summary.txt
 tail -2 $O/ncu_full.log
 ncu -i $O/prof_full.ncu-rep --page raw --csv > $O/raw_all.csv 2>/dev/null
-ncu -i $O/prof_full.ncu-rep --page source --csv --kernel-name regex:explain4 > $O/e4_source.csv 2>/dev/null
+ncu -i $O/prof_full.ncu-rep --page source --csv --kernel-name regex:explain4 > $O/e4_source.csv 2>/dev/null; rm -f $O/prof_full.ncu-rep
 ls -la $O
