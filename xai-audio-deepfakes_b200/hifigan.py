@@ -21,7 +21,6 @@ same kernel with 3 taps and N = s*C_out phase-stacked weights: its channels-last
 """
 from __future__ import annotations
 
-import math
 
 import torch
 

@@ -6,7 +6,6 @@ the reference does (audioprocessor.py:90,98); nothing is computed on the CPU.
 """
 from __future__ import annotations
 
-import ctypes as C
 
 import torch
 

@@ -15,7 +15,6 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from ._lib import check, lib, ptr, stream_ptr
 
 KERNELS_PER_STEP = 2
 
