@@ -232,7 +232,7 @@ mel_fused_kernel(PlanDev P, MelFusedArgs a) {
                 const float r2a = fmaf(xa[i].x, xa[i].x, xa[i].y * xa[i].y), r2b = fmaf(xb[i].x, xb[i].x, xb[i].y * xb[i].y);
                 float pa, pb;
                 if (p2) { pa = r2a; pb = r2b; }
-                else if (p1) { pa = r2a * rsqrtf(fmaxf(r2a, 1e-37f)); pb = r2b * rsqrtf(fmaxf(r2b, 1e-37f)); }
+                else if (p1) { pa = r2a * rsqrt_ftz(fmaxf(r2a, 1e-37f)); pb = r2b * rsqrt_ftz(fmaxf(r2b, 1e-37f)); }
                 else { pa = mel_pow_generic(r2a, half_power); pb = mel_pow_generic(r2b, half_power); }
                 if (i < 16) {
                     const __nv_bfloat16 ha = __float2bfloat16_rn(pa), hb = __float2bfloat16_rn(pb);

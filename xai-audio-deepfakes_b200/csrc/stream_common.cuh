@@ -26,16 +26,6 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ float rsqrt_ftz(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_ftz(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 // er = expm1(m log1p(a)) through MUFU (a >= 1/16) - see mask_gains() in transform_common.cuh for the error analysis
 __device__ __forceinline__ float er_mufu(float a, float m) { return ex2_approx(m * lg2_approx(1.0f + a)) - 1.0f; }

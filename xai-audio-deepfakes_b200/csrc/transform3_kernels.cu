@@ -54,10 +54,7 @@ template <bool MAG, bool PHASE>
 __device__ __forceinline__ void store_bin(float2* __restrict__ X, float* __restrict__ mag, float* __restrict__ phase,
                                           size_t idx, float2 x) {
     X[idx] = x;
-    if (MAG) {  // r2 * rsqrt(r2): <= 2 ulp, a third of the instructions of IEEE sqrtf's inlined expansion
-        const float r2 = fmaf(x.x, x.x, x.y * x.y);
-        mag[idx] = r2 * rsqrtf(fmaxf(r2, 1e-37f));
-    }
+    if (MAG) mag[idx] = fast_abs2(x);
     if (PHASE) phase[idx] = fast_atan2f(x.y, x.x);
 }
 

@@ -552,10 +552,7 @@ template <bool MAG, bool PHASE>
 __device__ __forceinline__ void store_bin5(float2* __restrict__ X, float* __restrict__ mag, float* __restrict__ phase,
                                            size_t idx, float2 x) {
     X[idx] = x;
-    if (MAG) {  // r2 * rsqrt(r2): <= 2 ulp
-        const float r2 = fmaf(x.x, x.x, x.y * x.y);
-        mag[idx] = r2 * rsqrtf(fmaxf(r2, 1e-37f));
-    }
+    if (MAG) mag[idx] = fast_abs2(x);
     if (PHASE) phase[idx] = fast_atan2f(x.y, x.x);
 }
 
@@ -752,7 +749,10 @@ int launch_stft5(const adv_plan* p, const float* wav, int64_t wav_stride, int ba
     // With |X| and angle on the rectangular default window the two-frames-per-transform generation-2 kernel needs fewer
     // instructions per frame (this kernel: 1 484, 63 % of the issue slots, ncu) and stays ahead - 40.4 vs 41.3 us, and 52.9 vs
     // 62.4 us on 16 x 30 s clips - so that call keeps it.
-    if (rect && (mag || phase)) return ADV_ERR_UNSUPPORTED;
+#ifndef ADV_STFT5_RECT_MP   // 1: also serve the rectangular window with magnitude / phase outputs (A/B against the generation-2 kernel)
+#define ADV_STFT5_RECT_MP 0
+#endif
+    if (rect && (mag || phase) && !ADV_STFT5_RECT_MP) return ADV_ERR_UNSUPPORTED;
     return rect ? launch_stft5_t<true>(p, g, wav, wav_stride, batch, X, mag, phase, s)
                 : launch_stft5_t<false>(p, g, wav, wav_stride, batch, X, mag, phase, s);
 }

@@ -235,12 +235,32 @@ __device__ __forceinline__ int stage_segment_async(float* seg, int seglen, const
     return shift;
 }
 
+// MUFU forms without the denormal fix-ups the default-precision intrinsics carry (a compare, a predicate and two
+// scalings per call: rsqrtf / __fdividef cost 5 - 9 instructions, these 1 - 2); callers keep the argument normal
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// |x| of a complex value as r2 * rsqrt(r2): <= 2 ulp, a third of the instructions of IEEE sqrtf's inlined expansion
+__device__ __forceinline__ float fast_abs2(float2 x) {
+    const float r2 = fmaf(x.x, x.x, x.y * x.y);
+    return r2 * rsqrt_ftz(fmaxf(r2, 1e-37f));
+}
+
 // atan2 for the phase output: odd minimax polynomial on [0, 1] (max abs error 1.3e-7 rad before the
-// quadrant fix-up, i.e. fp32 round-off of a result up to pi) - a third of libm atan2f's instructions
+// quadrant fix-up, i.e. fp32 round-off of a result up to pi) - a third of libm atan2f's instructions.  The quotient is
+// min * rcp(max) with the denominator clamped to 1e-30 (keeps the MUFU argument normal; 0 / 0 gives 0 as atan2 does, and
+// a bin below 1e-30 in both parts - which the |X| > 1e-3 max gate of the parity tests never sees - gets some angle of its quadrant)
 __device__ __forceinline__ float fast_atan2f(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float a = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+    const float a = mn * rcp_ftz(fmaxf(mx, 1e-30f));
     const float s = a * a;
     float p = -0.004355369135737419f;
     p = fmaf(p, s, 0.023040004074573517f);

@@ -397,10 +397,7 @@ stft_w_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int 
                 const int bin = bin_of<NF>(l, i);
                 if (bin < 0) continue;
                 X[row + bin] = x[i];
-                if (MAG) {  // r2 * rsqrt(r2): <= 2 ulp, a third of the instructions of IEEE sqrtf's inlined expansion
-                    const float r2 = fmaf(x[i].x, x[i].x, x[i].y * x[i].y);
-                    mag[row + bin] = r2 * rsqrtf(fmaxf(r2, 1e-37f));
-                }
+                if (MAG) mag[row + bin] = fast_abs2(x[i]);
                 if (PHASE) phase[row + bin] = fast_atan2f(x[i].y, x[i].x);
             }
         }
@@ -1548,10 +1545,7 @@ stft_ww_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int
             for (int i = 0; i < 9; ++i) {
                 if (i == 8 && l != 1) continue;  // slot 8 is the Nyquist bin (256 = bin0 + 128 on lane 1)
                 X[row + 16 * i] = x[i];
-                if (MAG) {
-                    const float r2 = fmaf(x[i].x, x[i].x, x[i].y * x[i].y);
-                    mag[row + 16 * i] = r2 * rsqrtf(fmaxf(r2, 1e-37f));
-                }
+                if (MAG) mag[row + 16 * i] = fast_abs2(x[i]);
                 if (PHASE) phase[row + 16 * i] = fast_atan2f(x[i].y, x[i].x);
             }
         }
