@@ -344,7 +344,7 @@ __device__ __forceinline__ void mask_gains(float2 x, float m, float& g_rel, floa
     // |X|^2 clamped away from 0: for a -> 0 the gains tend to (m, 1 - m) and the product with X vanishes either
     // way, so the clamp replaces a branch per bin (1e-30 keeps rsqrt and a = r2 * ia normal numbers)
     const float r2 = fmaxf(fmaf(x.x, x.x, x.y * x.y), 1e-30f);
-    const float ia = rsqrtf(r2);
+    const float ia = rsqrt_ftz(r2);
     const float a = r2 * ia;
     float er;
     if (a >= 0.0625f) {
@@ -364,7 +364,7 @@ __device__ __forceinline__ void mask_gains(float2 x, float m, float& g_rel, floa
         e = fmaf(y, e, 1.0f);
         er = y * e;
     }
-    const float ei = __fdividef(a - er, 1.0f + er);
+    const float ei = (a - er) * rcp_ftz(1.0f + er);   // (1 + er = (1 + a)^m is a normal number: no denormal fix-up needed)
     g_rel = er * ia;
     g_irr = ei * ia;
 }
