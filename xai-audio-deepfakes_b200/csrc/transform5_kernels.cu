@@ -358,7 +358,7 @@ explain5_kernel(PlanDev P, Geo5 G, int upc, int total_units, const float* __rest
     }
     auto request_seg = [&](const UnitPos& q, bool live) -> int {
         const int base = q.u * G.hop - 512 + G.wlo;
-        if (live) return stage_segment_async<32>(seg, G.sup, wav + (size_t)q.b * wav_stride, base, P.n_in, segbar + w, l);
+        if (live) return stage_segment_async<32, true>(seg, G.sup, wav + (size_t)q.b * wav_stride, base, P.n_in, segbar + w, l);
         if (l == 0) mbar_expect_tx(segbar + w, 0);   // (a unit past the run still arms the barrier)
         return 0;
     };
@@ -393,6 +393,7 @@ explain5_kernel(PlanDev P, Geo5 G, int upc, int total_units, const float* __rest
         // -- 1. windowed samples of the frame (zeros outside the window support, for frames that do not exist or are
         //       dropped, and for units past the run - no branch encloses the transforms)
         float2 v[16];
+        cp_async_wait_group<0>();   // the slice's edge samples (groups committed so far: not the mask copies requested after them)
         __syncwarp();
         mbar_wait(segbar + w, p & 1);
         {

@@ -209,7 +209,13 @@ static size_t al16(size_t b) { return (b + 15) & ~size_t(15); }
 // Request samples [base, base + seglen) of `row` (reflect-padded outside [0, n_in)) into seg; sample
 // idx lands at seg[idx - base + shift], shift = base mod 4 (returned).  Thread 0 arms `bar` with the
 // bulk byte count (possibly 0) - one phase per call.  All threads must call it.
-template <int NT>
+// AE ("async edges"): the samples outside the 16-byte-aligned bulk part (up to 3 on either side when base is not a multiple
+// of 4 - every other frame at hop 322 - and the reflected ones at the clip edges) travel as 4-byte cp.async copies, committed
+// as one group per call, instead of LDG -> STS pairs on whose load the issuing lanes stall; the consumer then runs
+// cp.async.wait_group 0 before the barrier / __syncwarp() that publishes the slice.  Measured at the reference-default
+// geometry (same box): fused explain5_kernel 92.6 -> 91.5 us (kept there); the forward-only kernels, whose iterations are
+// short, lose 1 % to the extra wait and keep the plain form.
+template <int NT, bool AE = false>
 __device__ __forceinline__ int stage_segment_async(float* seg, int seglen, const float* __restrict__ row, int base,
                                                    int n_in, uint64_t* bar, int gtid = -1, bool pad_zero = false) {
     if (gtid < 0) gtid = threadIdx.x;  // index inside the cooperating group of NT threads (CTA or warp)
@@ -230,8 +236,17 @@ __device__ __forceinline__ int stage_segment_async(float* seg, int seglen, const
             if (idx < 0) idx = -idx;
             else if (idx >= n_in) idx = 2 * (n_in - 1) - idx;
         }
-        seg[pos - base + shift] = (idx >= 0 && idx < n_in) ? __ldg(row + idx) : 0.0f;
+        if constexpr (AE) {
+            if (idx >= 0 && idx < n_in)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(seg + (pos - base + shift))), "l"(row + idx)
+                             : "memory");
+            else
+                seg[pos - base + shift] = 0.0f;
+        } else {
+            seg[pos - base + shift] = (idx >= 0 && idx < n_in) ? __ldg(row + idx) : 0.0f;
+        }
     }
+    if constexpr (AE) cp_async_commit();
     return shift;
 }
 
