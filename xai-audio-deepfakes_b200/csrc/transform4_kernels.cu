@@ -62,7 +62,7 @@ struct E4Cfg {
     static size_t bytes() {
         return al16(sizeof(float2) * TW3N) + al16(sizeof(float) * UNITS * f3::Scr<VEC>::FLOATS) +
                al16(sizeof(float) * UNITS * 2 * TAIL * 32) + al16(sizeof(float) * UNITS * SEG) +
-               al16(sizeof(float) * MASK_TILE) + al16(sizeof(uint64_t) * NBARS);
+               al16(sizeof(float) * MASK_TILE) + al16(sizeof(uint64_t) * NBARS) + al16(sizeof(float) * 4 * NT);
     }
     static constexpr int TW3N = f3::TW1024_OFF;
 };
@@ -91,6 +91,10 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
     float* seg_all = cv.take<float>(UNITS * C::SEG);
     float* mask_s = cv.take<float>(C::MASK_TILE);
     uint64_t* bars = cv.take<uint64_t>(C::NBARS);
+    // per-thread statistics accumulators live in shared memory ([4][NT]): held in registers across the transforms they were
+    // what the compiler spilled, and a local-memory reload misses the small L1 this kernel leaves (2 % of the warp samples
+    // sat on it; explain5_kernel: 6 %)
+    float* acc_s = cv.take<float>(4 * NT) + threadIdx.x;
     uint64_t* full = bars;                 // [16] tail of unit slot w written (1 arrival per pass)
     uint64_t* empty = bars + UNITS;        // [16] tail of unit slot w read by its NB consumers
     uint64_t* segbar = bars + 2 * UNITS;   // [16] waveform slice of warp w landed
@@ -204,12 +208,13 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
     request_mask(0);
     int shift = request_seg(pos, start + w < g_end);
 
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};   // (sum, sum sq) of rel, irr stored by this lane for clip acc_b
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc_s[i * NT] = 0.f;   // (sum, sum sq) of rel, irr stored by this lane for clip acc_b
     int acc_b = -1;
     auto flush = [&]() {   // warp-uniform call sites
         double q[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) q[i] = warp_sum((double)acc[i]);
+        for (int i = 0; i < 4; ++i) q[i] = warp_sum((double)acc_s[i * NT]);
         if (stats != nullptr && acc_b >= 0 && l == 0) {
             const int c_first = (int)((((long)acc_b * upc + 1) * G - 1) / total_units);
             double* row = stats + ((size_t)acc_b * slots + ((int)blockIdx.x - c_first) * UNITS + w) * 4;
@@ -217,7 +222,7 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
             for (int i = 0; i < 4; ++i) row[i] = q[i];
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = 0.f;
+        for (int i = 0; i < 4; ++i) acc_s[i * NT] = 0.f;
     };
 
     for (int p = 0; p < n_pass; ++p) {
@@ -372,6 +377,9 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
             }
             float* rrow = rel + (size_t)cur.b * P.n_out;
             float* irow = irr + (size_t)cur.b * P.n_out;
+            float acc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = acc_s[i * NT];
 #pragma unroll
             for (int r = 0; r < HEAD; ++r) {
                 const int sidx = s_base + 32 * r;
@@ -385,6 +393,8 @@ explain4_kernel(PlanDev P, int upc, int total_units, const float* __restrict__ w
                     irow[sidx] = c;
                 }
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc_s[i * NT] = acc[i];
         }
     }
     if (acc_b >= 0) flush();

@@ -246,7 +246,7 @@ struct E5Cfg {
         return al16(sizeof(float2) * f3::TW_TOTAL) + al16(sizeof(float) * kE5Units * f3::Scr<false>::FLOATS) +
                al16(sizeof(float) * kE5Units * 2 * ((sup + 3) & ~3)) + al16(sizeof(float) * kE5Units * seg_floats(sup)) +
                al16(sizeof(float) * MASK_TILE) + (rect ? 0 : al16(sizeof(float) * 1024)) +
-               al16(sizeof(uint64_t) * (3 * kE5Units + 2));
+               al16(sizeof(uint64_t) * (3 * kE5Units + 2)) + al16(sizeof(float) * 4 * kE5Threads);
     }
 };
 
@@ -266,6 +266,7 @@ explain5_kernel(PlanDev P, Geo5 G, int upc, int total_units, const float* __rest
     float* mask_s = cv.take<float>(E5Cfg::MASK_TILE);
     float* win_s = RECT ? nullptr : cv.take<float>(1024);
     uint64_t* bars = cv.take<uint64_t>(3 * UNITS + 2);
+    float* acc_s = cv.take<float>(4 * NT) + threadIdx.x;   // per-thread statistics accumulators [4][NT] (see explain4_kernel)
     uint64_t* full = bars;                 // [16] strips of unit slot w written
     uint64_t* empty = bars + UNITS;        // [16] strips of unit slot w read by their NB consumers
     uint64_t* segbar = bars + 2 * UNITS;   // [16] waveform slice of warp w landed
@@ -366,12 +367,13 @@ explain5_kernel(PlanDev P, Geo5 G, int upc, int total_units, const float* __rest
     request_mask(0);
     int shift = request_seg(pos, start + w < g_end);
 
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc_s[i * NT] = 0.f;
     int acc_b = -1;
     auto flush = [&]() {
         double q[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) q[i] = warp_sum((double)acc[i]);
+        for (int i = 0; i < 4; ++i) q[i] = warp_sum((double)acc_s[i * NT]);
         if (stats != nullptr && acc_b >= 0 && l == 0) {
             const int c_first = (int)((((long)acc_b * upc + 1) * NG - 1) / total_units);
             double* row = stats + ((size_t)acc_b * slots + ((int)blockIdx.x - c_first) * UNITS + w) * 4;
@@ -379,7 +381,7 @@ explain5_kernel(PlanDev P, Geo5 G, int upc, int total_units, const float* __rest
             for (int i = 0; i < 4; ++i) row[i] = q[i];
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = 0.f;
+        for (int i = 0; i < 4; ++i) acc_s[i * NT] = 0.f;
     };
 
     for (int p = 0; p < n_pass; ++p) {
@@ -510,6 +512,9 @@ explain5_kernel(PlanDev P, Geo5 G, int upc, int total_units, const float* __rest
             }
             float* rrow = rel + (size_t)cur.b * P.n_out;
             float* irow = irr + (size_t)cur.b * P.n_out;
+            float acc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = acc_s[i * NT];
 #pragma unroll
             for (int r = 0; r < kS5MaxRows; ++r) {
                 const int i = 2 * l + 64 * r;
@@ -525,6 +530,8 @@ explain5_kernel(PlanDev P, Geo5 G, int upc, int total_units, const float* __rest
                     *reinterpret_cast<float2*>(irow + s) = c;
                 }
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc_s[i * NT] = acc[i];
         }
     }
     if (acc_b >= 0) flush();
