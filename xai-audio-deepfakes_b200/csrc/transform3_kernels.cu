@@ -15,6 +15,7 @@
 // the transform, the bin ownership (32 consecutive bins per load / store instruction) and that no instruction in
 // the hot loops is a shuffle.  Strip origins are rounded down to a multiple of 4 samples per unit ("rem" shift), so
 // the 128-bit gather also serves hops that are only even (322).
+#include <type_traits>
 #include "transform_common.cuh"
 #include "fft3.cuh"
 
@@ -61,6 +62,9 @@ __device__ __forceinline__ void store_bin(float2* __restrict__ X, float* __restr
 template <int NF, bool MAG, bool PHASE, bool RECT, bool VEC, bool ZP>
 #ifndef ADV_STFT3_VEC_CTAS
 #define ADV_STFT3_VEC_CTAS 3
+#endif
+#ifndef ADV_STFT3_SHARED_ROWS
+#define ADV_STFT3_SHARED_ROWS 1
 #endif
 #ifndef ADV_STFT3_DYN
 #define ADV_STFT3_DYN 0   // 1: items drawn from per-group counters instead of the static round-robin (A/B, see the kernel)
@@ -181,11 +185,32 @@ stft3_kernel(PlanDev P, const float* __restrict__ wav, int64_t wav_stride, int t
             float2 v[16];
             {
                 const float* sa = seg + cur_shift + l;
-                const float* sb = sa + P.hop;
+#if ADV_STFT3_SHARED_ROWS
+                // hop = 32 HS: frame b's row j is frame a's row j + HS - the two frames need 16 + HS distinct rows of 32
+                // samples, not 32 (shared-memory instructions are this kernel's top stall: mio_throttle)
+                auto load_rows = [&](auto hs) {
+                    constexpr int HS = decltype(hs)::value;
+                    float r[16 + HS];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float ww = RECT ? 1.0f : win_s[32 * j + l];
-                    v[j] = make_float2(sa[32 * j] * ww, sb[32 * j] * ww);
+                    for (int j = 0; j < 16 + HS; ++j) r[j] = sa[32 * j];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float ww = RECT ? 1.0f : win_s[32 * j + l];
+                        v[j] = make_float2(r[j] * ww, r[j + HS] * ww);
+                    }
+                };
+                if (P.hop == 160) load_rows(std::integral_constant<int, 5>{});
+                else if (P.hop == 128) load_rows(std::integral_constant<int, 4>{});
+                else if (P.hop == 256) load_rows(std::integral_constant<int, 8>{});
+                else
+#endif
+                {
+                    const float* sb = sa + P.hop;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float ww = RECT ? 1.0f : win_s[32 * j + l];
+                        v[j] = make_float2(sa[32 * j] * ww, sb[32 * j] * ww);
+                    }
                 }
             }
             f3::fft_forward<VEC>(v, l, tw_s, my, request_next);
